@@ -1,0 +1,121 @@
+"""CPU: the oracle restatement reproduces the fixtures dumped from the REAL reference modules
+(oracle/gen_golden.py) and the reference's own known-answer tests for this path."""
+import numpy as np
+import torch
+
+from oracle.streamspeech_oracle import (StreamSpeechOracle, kaldi_fbank, online_features, rel_positional_encoding,
+                                        rel_shift, ctc_collapse, num_fbank_frames)
+from streamspeech_b200 import synth
+from streamspeech_b200.config import ModelConfig, VocoderConfig
+
+torch.set_grad_enabled(False)
+
+
+def golden_cfg():
+    cfg = ModelConfig()
+    cfg.enc_layers = 3  # what oracle/gen_golden.py used
+    return cfg
+
+
+def test_kat_rel_shift_and_positional_encoding(gold):
+    # fairseq/tests/test_espnet_multihead_attention.py:99-115 and test_positional_encoding.py:17-59
+    g = gold["kat_relpos"]
+    assert np.array_equal(rel_shift(torch.from_numpy(g["shift_in"])).numpy(), g["shift_out"])
+    assert np.array_equal(rel_positional_encoding(3, 4).numpy(), g["pe_T3_d4"])
+    # the values the reference test hard-codes for rel_shift on arange(30).view(1,2,3,5)
+    exp = torch.tensor([[[[2.0, 3, 4], [6, 7, 8], [10, 11, 12]], [[17, 18, 19], [21, 22, 23], [25, 26, 27]]]])
+    assert torch.equal(rel_shift(torch.arange(0, 30, dtype=torch.float32).view(1, 2, 3, 5)), exp)
+
+
+def test_fbank_matches_torchaudio_fixture(gold):
+    g = gold["fbank"]
+    mine = kaldi_fbank(torch.from_numpy(g["wav"]) * 2 ** 15)
+    assert mine.shape == g["fbank"].shape
+    assert np.abs(mine.numpy() - g["fbank"]).max() < 1e-4
+
+
+def test_num_frames_rule():
+    # agent:70-81: F = floor((n - 240) / 160)
+    assert num_fbank_frames(160000) == 998 and num_fbank_frames(5120) == 30 and num_fbank_frames(239) == 0
+    assert num_fbank_frames(400) == 1 and num_fbank_frames(399) == 0
+
+
+def test_encoder_fixtures(gold):
+    g = gold["encoder"]
+    cfg = golden_cfg()
+    sd = synth.make_model_state_dict(cfg, seed=0)
+    feats = torch.from_numpy(g["feats"])
+    for chunk, conv in ((4, 8), (8, 8), (16, 16), (None, None)):
+        o = StreamSpeechOracle(cfg, sd, None, None, chunk_size=chunk, conv_chunk_size=conv)
+        out = o.encoder(feats.unsqueeze(0), torch.tensor([feats.size(0)]), return_layers=True)
+        assert np.abs(out["encoder_out"][0][:, 0].numpy() - g[f"out_c{chunk}"]).max() < 2e-5
+        assert np.abs(out["encoder_states"][0][:, 0].numpy() - g[f"layer0_c{chunk}"]).max() < 2e-5
+        sub, _ = o.subsample(feats.unsqueeze(0), torch.tensor([feats.size(0)]))
+        assert np.abs(sub[:, 0].numpy() - g[f"sub_c{chunk}"]).max() < 2e-5
+    o = StreamSpeechOracle(cfg, sd, None, None, chunk_size=8, conv_chunk_size=8)
+    fb = torch.zeros(2, feats.size(0), 80)
+    fb[0] = feats
+    fb[1, :150] = feats[:150]
+    out = o.encoder(fb, torch.from_numpy(g["batched_lens"]))
+    assert np.abs(out["encoder_out"][0].numpy() - g["batched_out"]).max() < 2e-5
+
+
+def test_decoder_fixtures(gold):
+    g = gold["decoders"]
+    cfg = golden_cfg()
+    sd = synth.make_model_state_dict(cfg, seed=0)
+    o = StreamSpeechOracle(cfg, sd, None, None, chunk_size=8)
+    eo = torch.from_numpy(g["enc_out"]).unsqueeze(1)
+    for name in ("source_unigram", "ctc_target_unigram"):
+        h = o.ctc_greedy(name, eo)[0]
+        assert h["org_tokens"] == g[f"ctc_{name}_argmax"].tolist()
+        assert h["tokens"] == g[f"ctc_{name}_tokens"].tolist()
+        assert h["index"] == g[f"ctc_{name}_index"].tolist()
+    toks = torch.from_numpy(g["mt_tokens"])
+    assert np.abs(o.mt_features(toks, eo)[0].numpy() - g["mt_feats"]).max() < 2e-5
+    assert np.abs(o.mt_logits(toks, eo)[0, -1].numpy() - g["mt_logits_last"]).max() < 5e-5
+    tp = torch.from_numpy(g["mt_tokens_pad"])
+    fp = o.mt_features(tp, eo)
+    assert np.abs(fp[0].numpy() - g["mt_feats_pad"]).max() < 2e-5
+    x = torch.from_numpy(g["mt_feats"]).unsqueeze(1)
+    t2u = o.t2u_encoder(x, None)
+    assert np.abs(t2u[:, 0].numpy() - g["t2u_out"]).max() < 2e-5
+    lg = o.unit_decoder_logits(t2u, None)
+    assert np.abs(lg[0, :4].numpy() - g["unit_logits_first"]).max() < 1e-4
+    h = o.unit_ctc_greedy(lg)[0]
+    assert h["org_tokens"] == g["unit_argmax"].tolist()
+    assert h["tokens"] == g["unit_tokens"].tolist()
+    pm = tp.eq(1)
+    lgp = o.unit_decoder_logits(o.t2u_encoder(fp.transpose(0, 1), pm), pm)
+    assert lgp[0].argmax(-1).tolist() == g["unit_argmax_pad"].tolist()
+
+
+def test_vocoder_fixture(gold):
+    g = gold["vocoder"]
+    cfg = golden_cfg()
+    for wn in (True, False):
+        vsd = synth.make_vocoder_state_dict(VocoderConfig(), seed=1, weight_norm=wn)
+        o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg.tiny(), 0, None), vsd, None)
+        wav, dur = o.vocoder(g["code"][0].tolist(), True)
+        assert np.array_equal(dur.numpy(), g["dur"])
+        assert np.abs(wav.numpy() - g["wav"]).max() < 1e-5
+
+
+def test_ctc_collapse_edge_cases():
+    assert ctc_collapse([], 0, 1) == ([], [])
+    assert ctc_collapse([0, 0, 0], 0, 1) == ([], [])
+    assert ctc_collapse([5, 5, 0, 5, 1, 7, 7], 0, 1) == ([5, 5, 7], [0, 3, 5])
+
+
+def test_mt_greedy_semantics():
+    """Forced EOS at max_len, min_len ban of EOS at step 0, prefix forcing (agent/sequence_generator.py:205-215,362-379)."""
+    cfg = ModelConfig().tiny()
+    sd = synth.make_model_state_dict(cfg, seed=0)
+    o = StreamSpeechOracle(cfg, sd, None, None, chunk_size=8)
+    eo = torch.randn(12, 1, cfg.enc_dim, generator=torch.Generator().manual_seed(0))
+    h = o.mt_greedy(eo, None, 3)
+    assert h[-1] == cfg.eos and 2 <= len(h) <= 4 and cfg.eos not in h[:-1]
+    h2 = o.mt_greedy(eo, h[:-1], 2)
+    assert h2[: len(h) - 1] == h[:-1] and h2[-1] == cfg.eos and len(h2) <= len(h) - 1 + 3
+    h0 = o.mt_greedy(eo, h[:-1], 0)  # no new tokens allowed: eos is forced immediately
+    assert h0 == h[:-1] + [cfg.eos]
