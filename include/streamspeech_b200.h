@@ -1,0 +1,146 @@
+/* C-ABI of libstreamspeech_b200.so — the drop-in boundary under the SimulEval agent / fairseq model surface.
+ *
+ * The reference (ictnlp/StreamSpeech) has no FFI: its hot path is Python objects calling PyTorch
+ * (SURVEY.md §8b).  Each entry point below replaces one reference call site; the citation names the
+ * reference function whose arithmetic it reproduces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative ss_status otherwise; nothing throws across the ABI;
+ *    ss_last_error(h) returns a message for the last failure on that handle;
+ *  - pointers named *_dev are CUDA device pointers on the handle's device, *_host are host pointers;
+ *  - the caller allocates all inputs/outputs (torch tensors -> data_ptr()); the library owns weights,
+ *    workspaces and per-stream caches only;
+ *  - `stream` is a cudaStream_t (as void*).  Work is enqueued on it; functions documented as
+ *    "enqueue only" never synchronise, the others synchronise that stream where stated;
+ *  - one handle may be used from one host thread at a time; distinct handles are independent.
+ */
+#ifndef STREAMSPEECH_B200_H_
+#define STREAMSPEECH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ss_engine ss_engine;
+
+enum ss_status {
+  SS_OK = 0,
+  SS_ERR_INVALID = -1,   /* bad argument / shape */
+  SS_ERR_MISSING = -2,   /* a required state-dict key was not loaded */
+  SS_ERR_CUDA = -3,      /* CUDA runtime error */
+  SS_ERR_STATE = -4,     /* call order (e.g. run before finalize) */
+  SS_ERR_CAPACITY = -5   /* sequence longer than the configured maximum */
+};
+
+#define SS_MAX_UPS 8
+#define SS_MAX_RB 4
+#define SS_MAX_DIL 4
+
+/* Model dimensions: fairseq cfg of the checkpoint + vocoder config.json
+ * (researches/ctc_unity/models/streamspeech_model.py:418-430, agent/tts/codehifigan.py:9-33). */
+typedef struct ss_config {
+  int32_t feat_dim, enc_dim, enc_ffn, enc_heads, enc_layers, dw_kernel, conv_channels, conv_kernel;
+  int32_t src_vocab, tgt_vocab;
+  int32_t mt_dim, mt_ffn, mt_heads, mt_layers;
+  int32_t t2u_layers, unit_dim, unit_ffn, unit_heads, unit_layers, unit_vocab, ctc_upsample_rate;
+  int32_t bos, pad, eos, unk, uni_encoder;
+  int32_t max_enc_frames;   /* longest encoder sequence (40 ms frames) the rel-pos tables cover */
+  int32_t max_mt_positions; /* MT decoder max positions (1024) */
+  /* CodeHiFiGAN */
+  int32_t voc_n_ups, voc_up_rates[SS_MAX_UPS], voc_up_kernels[SS_MAX_UPS], voc_init_channels;
+  int32_t voc_n_rb, voc_rb_kernels[SS_MAX_RB], voc_rb_ndil, voc_rb_dils[SS_MAX_RB][SS_MAX_DIL];
+  int32_t voc_num_embeddings, voc_embedding_dim, voc_in_dim, voc_dur_hidden, voc_dur_kernel;
+} ss_config;
+
+/* ---- lifecycle --------------------------------------------------------------------------------------- */
+int ss_create(ss_engine** out, int device, const ss_config* cfg);
+int ss_destroy(ss_engine* h);
+const char* ss_last_error(const ss_engine* h);
+const char* ss_version(void);
+
+/* Load one fp32 tensor of the checkpoint by its fairseq state-dict key (host memory, row-major).
+ * Replaces load_state_dict: fairseq/checkpoint_utils.py load_model_ensemble -> agent:355-393;
+ * vocoder keys are prefixed "vocoder." (agent/tts/vocoder.py:37-45, weight_norm already removed).
+ * Constants the reference computes at construction (sinusoid tables, mel bank, Povey window, gcmvn)
+ * are passed the same way under "__const__." keys by the Python host. */
+int ss_load_tensor(ss_engine* h, const char* key, const float* data_host, int ndim, const int64_t* shape);
+/* Repack to kernel layouts (GLU interleave, conv im2col order, BN fold, rel-pos projections,
+ * transposed-conv polyphase split) and upload.  Fails with SS_ERR_MISSING naming the first missing key. */
+int ss_finalize(ss_engine* h);
+
+/* encoder.chunk_size / conv chunk (agent:395-413; ASR agent :361-375).  0 = offline model (N10). */
+int ss_set_chunk(ss_engine* h, int attn_chunk, int conv_chunk);
+
+/* ---- F1/F2: OnlineFeatureExtractor.__call__ + transform (agent:66-98) --------------------------------- */
+/* number of fbank frames for n 16 kHz samples: floor((n - 240) / 160), >= 0 */
+int64_t ss_fbank_num_frames(int64_t n_samples);
+/* frames [frame0, frame0+n_frames) of the utterance `samples_dev` (fp32, NOT scaled) -> out_dev[n_frames][80]. enqueue only */
+int ss_fbank(ss_engine* h, void* stream, const float* samples_dev, int64_t n_samples, int64_t frame0, int64_t n_frames,
+             float* out_dev);
+
+/* ---- E1-E6: ChunkS2SConformerEncoder.forward (chunk_unity/models/s2t_conformer.py:111-163) -------------- */
+/* encoder frames for F fbank frames: two stride-2 convs (chunk_unity/modules/convolution.py:75-79) */
+int64_t ss_encoder_out_frames(int64_t n_fbank_frames);
+/* feats_dev [B][F][80] (zero padded), lengths_host[B] (or NULL = all F) -> out_dev [B][T][enc_dim], T = ss_encoder_out_frames(F).
+ * Full recompute of the prefix, like the reference.  enqueue only. */
+int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const int32_t* lengths_host, int B, int F,
+                       float* out_dev);
+
+/* ---- C1: CTCDecoder.generate (agent/ctc_decoder.py:40-111): Linear -> log_softmax -> mask pad,unk -> argmax -> collapse.
+ * head 0 = source_unigram (ASR), 1 = ctc_target_unigram (ST).  enc_dev [rows][enc_dim] of ONE utterance.
+ * argmax_dev[rows] int64; tokens_dev[rows] int64 / index_dev[rows] int32 hold *count_dev collapsed entries. enqueue only */
+int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev,
+                  int64_t* tokens_dev, int32_t* index_dev, int32_t* count_dev);
+
+/* ---- M1/M2: SequenceGenerator.generate_decoder, beam 1 (agent/sequence_generator.py:165-582) + the extra
+ * mt_decoder(prev_output_tokens, features_only=True) forward (agent:638-642).
+ * prefix_host[n_prefix] = tgt_subwords_indices; max_new_tokens as in the agent (-1 = source finished:
+ * max_len = min(max_len_b, max_positions-1)).  Writes the finalized hypothesis WITHOUT the trailing eos to
+ * tokens_out_host (capacity max_out) and the decoder features of [eos, tokens...] to feats_out_dev[(n_out+1)][mt_dim].
+ * Synchronises `stream` once per generated token (the arg-max is needed on the host for the stop test). */
+int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* prefix_host, int n_prefix,
+                 int max_new_tokens, int max_len_b, int64_t* tokens_out_host, int max_out, int* n_out,
+                 float* feats_out_dev);
+/* teacher-forced features for tokens_host[n] (pads allowed only as a tail): TransformerDecoderBase.extract_features_scriptable
+ * (ctc_unity/modules/transformer_decoder.py:257-403).  feats_out_dev [n][mt_dim]; logits_last_dev (optional) [tgt_vocab]. enqueue only */
+int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* tokens_host, int n,
+                   float* feats_out_dev, float* logits_last_dev);
+
+/* ---- T1/U1/U2: synthesizer_encoder -> CTCTransformerUnitDecoder -> CTCSequenceGenerator.generate
+ * (ctc_unity/modules/transformer_encoder.py:32-77, ctc_transformer_unit_decoder.py:53-260, agent/ctc_generator.py:41-123).
+ * mt_feats_dev [S][mt_dim]; n_pad_tail = number of trailing <pad> positions of prev_output_tokens_mt (whole_word).
+ * argmax_dev [S*rate] int64, units_dev [S*rate] int64 (dictionary indices, blank/pad removed), count_dev. mask_eos = offline generator (N3).
+ * t2u_out_dev / logits_dev optional (NULL) debug outputs [S][unit_dim], [S*rate][unit_vocab].  enqueue only */
+int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, int S, int n_pad_tail, int mask_eos,
+                       int64_t* argmax_dev, int64_t* units_dev, int32_t* count_dev, float* t2u_out_dev, float* logits_dev);
+
+/* ---- V1: CodeGenerator.forward front half (agent/tts/codehifigan.py:56-66): embedding + duration predictor.
+ * codes_dev[U] int64 unit ids (0..num_embeddings-1); dur_out_dev[U] int64; cumsum_out_dev[U+1] int32 (frame offsets).
+ * dur_prediction=0 -> every duration is 1.  The expanded frame sequence stays cached in the handle for ss_vocoder_generate. enqueue only */
+int ss_vocoder_durations(ss_engine* h, void* stream, const int64_t* codes_dev, int U, int dur_prediction, int64_t* dur_out_dev,
+                         int32_t* cumsum_out_dev);
+/* ---- V2: HiFi-GAN Generator.forward (fairseq/models/text_to_speech/hifigan.py:154-170) on frames
+ * [frame0 - ctx, frame0 + n_frames) of the cached sequence of total_frames frames (ctx = min(left_context, frame0);
+ * left_context < 0 = the generator's full receptive field, which makes the result equal to a full-sequence pass);
+ * writes n_frames*hop samples for frames [frame0, frame0+n_frames) to wav_out_dev.  frame0 + n_frames must equal total_frames
+ * (the agent always emits the tail).  enqueue only */
+int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0, int n_frames, int left_context,
+                        float* wav_out_dev);
+int ss_vocoder_hop(const ss_engine* h);
+int ss_vocoder_receptive_field(const ss_engine* h);
+
+/* ---- single ops exported for the parity tests (same kernels the entry points above launch) ------------- */
+int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N,
+                 int act, float* out_dev);
+int ss_op_layer_norm(ss_engine* h, void* stream, const float* x_dev, int rows, int C, const float* g_dev, const float* b_dev,
+                     float* out_dev);
+
+/* number of kernels this handle has launched since creation (bench.py reports it as gpu_launches) */
+int64_t ss_launch_count(const ss_engine* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMSPEECH_B200_H_ */

@@ -124,6 +124,30 @@ class ModelConfig:
     def unit_blank(self) -> int:
         return self.unit_vocab - 1
 
+    @staticmethod
+    def from_state_dict(sd) -> "ModelConfig":
+        """Infer the dimensions from a fairseq StreamSpeech state dict (checkpoint `cfg` is hydra-pickled and
+        not loadable without fairseq; every size is recoverable from tensor shapes)."""
+        c = ModelConfig()
+        c.conv_channels, c.feat_dim, c.conv_kernel = (int(x) for x in sd["encoder.subsample.conv_layers.0.weight"].shape)
+        c.enc_dim = int(sd["encoder.linear.weight"].shape[0])
+        c.enc_ffn = int(sd["encoder.conformer_layers.0.ffn1.w_1.weight"].shape[0])
+        c.enc_heads = int(sd["encoder.conformer_layers.0.self_attn.pos_bias_u"].shape[0])
+        c.dw_kernel = int(sd["encoder.conformer_layers.0.conv_module.depthwise_conv.weight"].shape[-1])
+        n = lambda prefix: 1 + max(int(k[len(prefix):].split(".")[0]) for k in sd if k.startswith(prefix))  # noqa: E731
+        c.enc_layers = n("encoder.conformer_layers.")
+        c.src_vocab = int(sd["source_unigram_decoder.proj.weight"].shape[0])
+        c.tgt_vocab, c.mt_dim = (int(x) for x in sd["target_unigram_decoder.embed_tokens.weight"].shape)
+        c.mt_ffn = int(sd["target_unigram_decoder.layers.0.fc1.weight"].shape[0])
+        c.mt_heads = c.mt_dim // 64
+        c.mt_layers = n("target_unigram_decoder.layers.")
+        c.t2u_layers = n("synthesizer_encoder.layers.")
+        c.unit_vocab, c.unit_dim = (int(x) for x in sd["decoder.embed_tokens.weight"].shape)
+        c.unit_ffn = int(sd["decoder.layers.0.fc1.weight"].shape[0])
+        c.unit_heads = c.unit_dim // 64
+        c.unit_layers = n("decoder.layers.")
+        return c
+
     def tiny(self) -> "ModelConfig":
         """A shrunken variant with the same structure (used by fast CPU tests)."""
         c = ModelConfig(**{k: v for k, v in asdict(self).items() if k != "vocoder"})

@@ -1,0 +1,148 @@
+// Engine state behind the C-ABI handle: host copies of the loaded tensors, repacked device weights,
+// a bump-allocated workspace and the per-call scratch of the decoders.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/streamspeech_b200.h"
+#include "kernels.h"
+
+namespace ss {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct Linear {
+  float* w = nullptr;  // [N][K]
+  float* b = nullptr;  // [N] or null
+  int N = 0, K = 0;
+};
+struct LNorm {
+  float* g = nullptr;
+  float* b = nullptr;
+  int C = 0;
+};
+
+struct ConformerLayerW {
+  LNorm ffn1_ln, ffn2_ln, attn_ln, conv_ln, final_ln;
+  Linear ffn1_w1, ffn1_w2, ffn2_w1, ffn2_w2;
+  Linear qkv, attn_out;
+  float* pos_u = nullptr;
+  float* pos_v = nullptr;
+  float* pos_proj = nullptr;  // [2*Tpos-1][D]: linear_pos(pe(r)), row r + Tpos - 1
+  Linear pw1;                 // GLU-interleaved rows
+  float* dw_w = nullptr;      // [k][C]
+  float* bn_scale = nullptr;
+  float* bn_shift = nullptr;
+  Linear pw2;
+};
+
+struct DecLayerW {  // transformer layer (self-attn [+ cross-attn] + FFN), pre-LN
+  LNorm self_ln, cross_ln, final_ln;
+  Linear q, k, v, qkv, out;      // self attention (qkv = fused rows q|k|v)
+  Linear cq, ckv, cout;          // cross attention (ckv = fused k|v)
+  Linear fc1, fc2;
+  bool has_cross = false;
+};
+
+struct ConvW {  // conv-as-GEMM weight [Cout][ksize*Cin]
+  Linear lin;
+  int ksize = 1, cin = 0, cout = 0, dil = 1;
+};
+
+struct UpsampleW {
+  int u = 1, k = 1, pad = 0, cin = 0, cout = 0;
+  std::vector<Linear> phase_w;  // per output phase: [Cout][J*Cin]
+  std::vector<int> phase_J, phase_q0;
+  float* bias = nullptr;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  float* f32(size_t n) { return (float*)raw(n * 4); }
+  void* raw(size_t bytes);
+  void reset() { off = 0; }
+  bool ensure(size_t bytes);  // (re)allocate when empty; must be called when off == 0
+};
+
+}  // namespace ss
+
+struct ss_engine {
+  int device = 0;
+  ss_config cfg{};
+  std::string err;
+  bool finalized = false;
+  int attn_chunk = 8, conv_chunk = 8;
+  std::map<std::string, ss::HostTensor> host;  // loaded tensors by key
+  std::vector<void*> dev_allocs;
+
+  // ---- packed weights
+  ss::Linear sub_conv[2];
+  ss::Linear enc_linear;
+  std::vector<ss::ConformerLayerW> enc;
+  int Tpos = 0;
+  ss::Linear ctc_head[2];
+  float* mt_emb = nullptr;
+  float* mt_pos = nullptr;  // sinusoid table [max_mt_positions + pad + 2][mt_dim]
+  int mt_pos_rows = 0;
+  std::vector<ss::DecLayerW> mt;
+  ss::LNorm mt_ln;
+  std::vector<ss::DecLayerW> t2u;
+  ss::LNorm t2u_ln;
+  std::vector<ss::DecLayerW> unit;
+  ss::LNorm unit_ln;
+  float* unit_emb = nullptr;
+  float* unit_pos_row = nullptr;  // sinusoid row pad+1 (N1 quirk)
+  float* mel_bank = nullptr;
+  float* window = nullptr;
+  float* cmvn_mean = nullptr;
+  float* cmvn_std = nullptr;
+  int* mask_pad_unk = nullptr;      // device [3] = {pad, unk, eos}
+  int* mask_pad_eos = nullptr;      // device [2] = {pad, eos}
+  // vocoder
+  bool has_vocoder = false;
+  float* voc_dict = nullptr;
+  ss::ConvW dur_conv1, dur_conv2;
+  ss::LNorm dur_ln1, dur_ln2;
+  ss::Linear dur_proj;
+  ss::ConvW conv_pre;
+  std::vector<ss::UpsampleW> ups;
+  std::vector<std::vector<std::vector<ss::ConvW>>> rb1, rb2;  // [stage][resblock][dil idx]
+  float* conv_post_w = nullptr;  // [k][C]
+  float conv_post_b = 0.f;
+  int conv_post_k = 7, conv_post_c = 0;
+  int hop = 1, receptive_field = 0;
+
+  // ---- workspaces
+  ss::Arena ws;        // per-call scratch
+  // MT decoder per-call caches
+  float* mt_self_k = nullptr;  // [layers][max_pos][mt_dim]
+  float* mt_self_v = nullptr;
+  float* mt_cross_kv = nullptr;  // [layers][Tcap][2*mt_dim]
+  int mt_cross_cap = 0;
+  int64_t* mt_tok_dev = nullptr;  // [max_pos]
+  int64_t* mt_next_dev = nullptr;
+  int64_t* mt_next_pinned = nullptr;
+  // vocoder cached frame sequence
+  float* voc_unit_emb = nullptr;  // [Ucap][emb]
+  int* voc_cumsum = nullptr;      // [Ucap+1]
+  int voc_ucap = 0, voc_U = 0;
+  int* lengths_dev = nullptr;     // [Bcap]
+  int lengths_cap = 0;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+};

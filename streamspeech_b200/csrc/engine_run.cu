@@ -1,0 +1,561 @@
+// The per-block entry points of the C-ABI: each one enqueues the kernels of one reference call site.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+#include "engine.h"
+
+using namespace ss;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+int check_launch(ss_engine* h, const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return h->fail(SS_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+  return SS_OK;
+}
+
+// plain linear: out[M][N] = epilogue(x[M][K] @ W^T)
+void linear(const float* x, int ldx, int M, const Linear& l, Epilogue ep, cudaStream_t st) {
+  ConvA a;
+  a.x = x; a.B = 1; a.L_in = M; a.L_rows = M; a.C_in = l.K; a.ldx = ldx;
+  ep.bias = l.b;
+  gemm_conv(a, l.w, l.N, ep, st);
+}
+Epilogue ep_out(float* out, int ldo, int act = ACT_NONE) {
+  Epilogue e;
+  e.out = out; e.ldo = ldo; e.act = act;
+  return e;
+}
+Epilogue ep_residual(float* inout, int ldo, float alpha = 1.0f) {  // inout = inout + alpha * y
+  Epilogue e;
+  e.out = inout; e.ldo = ldo; e.alpha = alpha; e.residual = inout; e.res_scale = 1.0f;
+  return e;
+}
+
+bool ws_begin(ss_engine* h, size_t bytes) {
+  h->ws.reset();
+  return h->ws.ensure(bytes);
+}
+
+struct DecScratch {
+  float *y, *q, *kv, *attn, *hid, *qkv;
+};
+
+// pre-LN transformer layer over x[n][dim] (TransformerDecoderLayerBase.forward / TransformerEncoderLayerBase.forward,
+// ctc_unity/modules/transformer_layer.py:165-230,388-551).  Self-attention keys/values come either from the
+// layer's own fused qkv (full sequence, cache == nullptr) or from an external KV cache that already holds `past` rows.
+void dec_layer(const DecLayerW& L, float* x, int n, int dim, int ffn, int heads, bool causal, int self_kv_len_limit,
+               const int* self_kv_len_dev, float* cache_k, float* cache_v, int past, const float* cross_kv, int Tk,
+               const int* cross_len_dev, DecScratch& s, cudaStream_t st) {
+  const float scale = 0.125f;  // head_dim ** -0.5, head_dim = 64
+  layer_norm(x, dim, s.y, dim, L.self_ln.g, L.self_ln.b, n, dim, st);
+  if (cache_k) {
+    linear(s.y, dim, n, L.q, ep_out(s.q, dim), st);
+    linear(s.y, dim, n, L.k, ep_out(cache_k + (size_t)past * dim, dim), st);
+    linear(s.y, dim, n, L.v, ep_out(cache_v + (size_t)past * dim, dim), st);
+    mha_attention(s.q, dim, cache_k, dim, cache_v, dim, s.attn, dim, 1, n, past + n, heads, scale, 1, past, self_kv_len_dev, st);
+  } else {
+    linear(s.y, dim, n, L.qkv, ep_out(s.qkv, 3 * dim), st);
+    mha_attention(s.qkv, 3 * dim, s.qkv + dim, 3 * dim, s.qkv + 2 * dim, 3 * dim, s.attn, dim, 1, n, n, heads, scale,
+                  causal ? 1 : 0, 0, self_kv_len_dev, st);
+  }
+  (void)self_kv_len_limit;
+  linear(s.attn, dim, n, L.out, ep_residual(x, dim), st);
+  if (L.has_cross) {
+    layer_norm(x, dim, s.y, dim, L.cross_ln.g, L.cross_ln.b, n, dim, st);
+    linear(s.y, dim, n, L.cq, ep_out(s.q, dim), st);
+    mha_attention(s.q, dim, cross_kv, 2 * dim, cross_kv + dim, 2 * dim, s.attn, dim, 1, n, Tk, heads, scale, 0, 0, cross_len_dev, st);
+    linear(s.attn, dim, n, L.cout, ep_residual(x, dim), st);
+  }
+  layer_norm(x, dim, s.y, dim, L.final_ln.g, L.final_ln.b, n, dim, st);
+  linear(s.y, dim, n, L.fc1, ep_out(s.hid, ffn, ACT_RELU), st);
+  linear(s.hid, ffn, n, L.fc2, ep_residual(x, dim), st);
+}
+
+int ensure_mt_cross(ss_engine* h, int T) {
+  if (T <= h->mt_cross_cap) return SS_OK;
+  if (h->mt_cross_kv) cudaFree(h->mt_cross_kv);
+  h->mt_cross_kv = nullptr;
+  int cap = std::max(T + T / 2, 512);
+  size_t bytes = (size_t)h->cfg.mt_layers * cap * 2 * h->cfg.mt_dim * sizeof(float);
+  if (cudaMalloc((void**)&h->mt_cross_kv, bytes) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc(mt cross kv) failed");
+  h->mt_cross_cap = cap;
+  return SS_OK;
+}
+
+// run the MT decoder on n tokens (already on the device at h->mt_tok_dev[past .. past+n)) with the KV cache holding `past` rows;
+// writes final-LN features to feats[n][dim]
+void mt_forward(ss_engine* h, int past, int n, int T, const int* self_kv_len_dev, float* feats, DecScratch& s, float* x, cudaStream_t st) {
+  const ss_config& c = h->cfg;
+  const int dim = c.mt_dim;
+  embed_tokens_pos(h->mt_tok_dev + past, nullptr, past, h->mt_emb, h->mt_pos, sqrtf((float)dim), x, n, dim, c.pad, st);
+  for (int l = 0; l < c.mt_layers; ++l) {
+    float* ck = h->mt_self_k + (size_t)l * c.max_mt_positions * dim;
+    float* cv = h->mt_self_v + (size_t)l * c.max_mt_positions * dim;
+    const float* cross = h->mt_cross_kv + (size_t)l * h->mt_cross_cap * 2 * dim;
+    dec_layer(h->mt[l], x, n, dim, c.mt_ffn, c.mt_heads, true, 0, self_kv_len_dev, ck, cv, past, cross, T, nullptr, s, st);
+  }
+  layer_norm(x, dim, feats, dim, h->mt_ln.g, h->mt_ln.b, n, dim, st);
+}
+
+void mt_begin(ss_engine* h, const float* enc_dev, int T, cudaStream_t st) {
+  const ss_config& c = h->cfg;
+  for (int l = 0; l < c.mt_layers; ++l) {
+    float* cross = h->mt_cross_kv + (size_t)l * h->mt_cross_cap * 2 * c.mt_dim;
+    linear(enc_dev, c.enc_dim, T, h->mt[l].ckv, ep_out(cross, 2 * c.mt_dim), st);
+  }
+}
+
+DecScratch dec_scratch(ss_engine* h, int n, int dim, int ffn) {
+  DecScratch s;
+  s.y = h->ws.f32((size_t)n * dim);
+  s.q = h->ws.f32((size_t)n * dim);
+  s.attn = h->ws.f32((size_t)n * dim);
+  s.hid = h->ws.f32((size_t)n * ffn);
+  s.qkv = h->ws.f32((size_t)n * 3 * dim);
+  s.kv = nullptr;
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ss_launch_count(const ss_engine*) { return (int64_t)ss::g_launches; }
+
+int64_t ss_fbank_num_frames(int64_t n) {
+  if (n < 240) return 0;
+  int64_t f = (n - 240) / 160;
+  return f < 0 ? 0 : f;
+}
+
+int64_t ss_encoder_out_frames(int64_t F) {
+  if (F <= 0) return 0;
+  int64_t t = (F - 1) / 2 + 1;
+  return (t - 1) / 2 + 1;
+}
+
+int ss_fbank(ss_engine* h, void* stream, const float* samples_dev, int64_t n_samples, int64_t frame0, int64_t n_frames,
+             float* out_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (n_frames <= 0) return SS_OK;
+  if (frame0 < 0 || (frame0 + n_frames - 1) * 160 + 400 > n_samples) return h->fail(SS_ERR_INVALID, "fbank frame range exceeds samples");
+  fbank_cmvn(samples_dev, n_samples, (int)frame0, (int)n_frames, h->mel_bank, h->window, h->cmvn_mean, nullptr, h->cmvn_std, out_dev, S(stream));
+  return check_launch(h, "ss_fbank");
+}
+
+int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const int32_t* lengths_host, int B, int F, float* out_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (B <= 0 || F <= 0) return h->fail(SS_ERR_INVALID, "empty encoder input");
+  const ss_config& c = h->cfg;
+  cudaStream_t st = S(stream);
+  const int D = c.enc_dim;
+  const int T1 = (F - 1) / 2 + 1, T = (T1 - 1) / 2 + 1;
+  if (T > h->Tpos) return h->fail(SS_ERR_CAPACITY, "encoder sequence longer than max_enc_frames");
+  const size_t rows = (size_t)B * T;
+  size_t need = ((size_t)B * T1 * (c.conv_channels / 2) + rows * (size_t)(D * 6 + c.enc_ffn + 3 * D) + 4096) * sizeof(float) + 16 * 256;
+  if (!ws_begin(h, need)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  float* c1 = h->ws.f32((size_t)B * T1 * (c.conv_channels / 2));
+  float* x = out_dev;  // the residual stream lives in the caller's output buffer
+  float* y = h->ws.f32(rows * D);
+  float* hid = h->ws.f32(rows * c.enc_ffn);
+  float* qkv = h->ws.f32(rows * 3 * D);
+  float* att = h->ws.f32(rows * D);
+  float* glu = h->ws.f32(rows * D);
+  float* dw = h->ws.f32(rows * D);
+  float* x0 = h->ws.f32(rows * D);
+  if (!c1 || !y || !hid || !qkv || !att || !glu || !dw || !x0) return h->fail(SS_ERR_CUDA, "workspace too small");
+  // per-sample encoder lengths (Conv1dSubsampler.get_out_seq_lens_tensor, convolution.py:75-79)
+  const int* len_dev = nullptr;
+  if (lengths_host) {
+    bool all_full = true;
+    std::vector<int> lens(B);
+    for (int b = 0; b < B; ++b) {
+      int l = lengths_host[b];
+      if (l < 1 || l > F) return h->fail(SS_ERR_INVALID, "bad src_lengths");
+      l = (l - 1) / 2 + 1;
+      l = (l - 1) / 2 + 1;
+      lens[b] = l;
+      all_full &= (l == T);
+    }
+    if (!all_full) {
+      if (B > h->lengths_cap) {
+        if (h->lengths_dev) cudaFree(h->lengths_dev);
+        cudaMalloc((void**)&h->lengths_dev, (size_t)B * 2 * sizeof(int));
+        h->lengths_cap = B * 2;
+      }
+      cudaMemcpyAsync(h->lengths_dev, lens.data(), B * sizeof(int), cudaMemcpyHostToDevice, st);
+      cudaStreamSynchronize(st);  // `lens` is a stack vector
+      len_dev = h->lengths_dev;
+    }
+  }
+  const int cc = h->conv_chunk;
+  // E1: two chunk-causal stride-2 convs + GLU (convolution.py:81-89).  conv_chunk == 0: plain Conv1d(padding=k//2)
+  {
+    ConvA a;
+    a.x = feats_dev; a.B = B; a.L_in = F; a.L_rows = T1; a.C_in = c.feat_dim; a.ldx = c.feat_dim;
+    a.ksize = c.conv_kernel; a.stride = 2; a.pad_left = c.conv_kernel / 2; a.chunk = cc;
+    Epilogue ep = ep_out(c1, c.conv_channels / 2);
+    ep.bias = h->sub_conv[0].b; ep.glu = 1;
+    gemm_conv(a, h->sub_conv[0].w, h->sub_conv[0].N, ep, st);
+    ConvA a2;
+    a2.x = c1; a2.B = B; a2.L_in = T1; a2.L_rows = T; a2.C_in = c.conv_channels / 2; a2.ldx = c.conv_channels / 2;
+    a2.ksize = c.conv_kernel; a2.stride = 2; a2.pad_left = c.conv_kernel / 2; a2.chunk = cc;
+    Epilogue ep2 = ep_out(x0, D);
+    ep2.bias = h->sub_conv[1].b; ep2.glu = 1; ep2.alpha = sqrtf((float)D);  // x = embed_scale * x (s2t_conformer.py:127)
+    gemm_conv(a2, h->sub_conv[1].w, h->sub_conv[1].N, ep2, st);
+  }
+  linear(x0, D, (int)rows, h->enc_linear, ep_out(x, D), st);  // s2t_conformer.py:139
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const ConformerLayerW& L = h->enc[i];
+    // x = x + 0.5 * ffn1(x)
+    layer_norm(x, D, y, D, L.ffn1_ln.g, L.ffn1_ln.b, (int)rows, D, st);
+    linear(y, D, (int)rows, L.ffn1_w1, ep_out(hid, c.enc_ffn, ACT_SILU), st);
+    linear(hid, c.enc_ffn, (int)rows, L.ffn1_w2, ep_residual(x, D, 0.5f), st);
+    // x = x + self_attn(LN(x))
+    layer_norm(x, D, y, D, L.attn_ln.g, L.attn_ln.b, (int)rows, D, st);
+    linear(y, D, (int)rows, L.qkv, ep_out(qkv, 3 * D), st);
+    relpos_attention(qkv, L.pos_proj, h->Tpos, L.pos_u, L.pos_v, att, B, T, c.enc_heads, D, h->attn_chunk, len_dev, st);
+    linear(att, D, (int)rows, L.attn_out, ep_residual(x, D), st);
+    // x = x + conv_module(x)
+    layer_norm(x, D, y, D, L.conv_ln.g, L.conv_ln.b, (int)rows, D, st);
+    {
+      Epilogue ep = ep_out(glu, D);
+      ep.glu = 1;
+      linear(y, D, (int)rows, L.pw1, ep, st);
+    }
+    depthwise_bn_silu(glu, D, L.dw_w, L.bn_scale, L.bn_shift, dw, D, B, T, D, c.dw_kernel, cc, nullptr, st);
+    linear(dw, D, (int)rows, L.pw2, ep_residual(x, D), st);
+    // x = LN(x + 0.5 * ffn2(x))
+    layer_norm(x, D, y, D, L.ffn2_ln.g, L.ffn2_ln.b, (int)rows, D, st);
+    linear(y, D, (int)rows, L.ffn2_w1, ep_out(hid, c.enc_ffn, ACT_SILU), st);
+    linear(hid, c.enc_ffn, (int)rows, L.ffn2_w2, ep_residual(x, D, 0.5f), st);
+    layer_norm(x, D, x, D, L.final_ln.g, L.final_ln.b, (int)rows, D, st);
+  }
+  return check_launch(h, "ss_encoder_forward");
+}
+
+int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev, int64_t* tokens_dev,
+                  int32_t* index_dev, int32_t* count_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (head < 0 || head > 1 || rows <= 0) return h->fail(SS_ERR_INVALID, "bad ctc head / rows");
+  const Linear& l = h->ctc_head[head];
+  cudaStream_t st = S(stream);
+  if (!ws_begin(h, (size_t)rows * l.N * sizeof(float) + 4096)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  float* logits = h->ws.f32((size_t)rows * l.N);
+  linear(enc_dev, h->cfg.enc_dim, rows, l, ep_out(logits, l.N), st);
+  argmax_rows(logits, l.N, rows, l.N, h->mask_pad_unk, 2, argmax_dev, nullptr, st);  // never select pad, unk
+  ctc_collapse(argmax_dev, rows, 0 /* <s> is the CTC blank (agent/ctc_decoder.py:72-76) */, h->cfg.pad, tokens_dev, index_dev, count_dev, st);
+  return check_launch(h, "ss_ctc_greedy");
+}
+
+int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* tokens_host, int n, float* feats_out_dev,
+                   float* logits_last_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  const ss_config& c = h->cfg;
+  if (n <= 0 || n > c.max_mt_positions || T <= 0) return h->fail(SS_ERR_INVALID, "bad MT sequence length");
+  cudaStream_t st = S(stream);
+  int rc = ensure_mt_cross(h, T);
+  if (rc) return rc;
+  int n_valid = n;  // trailing pads (whole_word path, agent:576-591) are masked as keys
+  while (n_valid > 0 && tokens_host[n_valid - 1] == c.pad) --n_valid;
+  for (int i = 0; i < n_valid; ++i)
+    if (tokens_host[i] == c.pad) return h->fail(SS_ERR_INVALID, "pads are only supported as a tail");
+  const int dim = c.mt_dim;
+  if (!ws_begin(h, ((size_t)n * (dim * 7 + c.mt_ffn) + 4096) * sizeof(float))) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  DecScratch s = dec_scratch(h, n, dim, c.mt_ffn);
+  float* x = h->ws.f32((size_t)n * dim);
+  int* kvlen = nullptr;
+  cudaMemcpyAsync(h->mt_tok_dev, tokens_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+  if (n_valid < n) {
+    kvlen = (int*)h->ws.raw(sizeof(int));
+    cudaMemcpyAsync(kvlen, &n_valid, sizeof(int), cudaMemcpyHostToDevice, st);
+  }
+  cudaStreamSynchronize(st);  // tokens_host / n_valid are caller / stack memory
+  mt_begin(h, enc_dev, T, st);
+  mt_forward(h, 0, n, T, kvlen, feats_out_dev, s, x, st);
+  if (logits_last_dev) {
+    Linear out;
+    out.w = h->mt_emb; out.b = nullptr; out.N = c.tgt_vocab; out.K = dim;
+    linear(feats_out_dev + (size_t)(n - 1) * dim, dim, 1, out, ep_out(logits_last_dev, c.tgt_vocab), st);
+  }
+  return check_launch(h, "ss_mt_features");
+}
+
+int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* prefix_host, int n_prefix, int max_new_tokens,
+                 int max_len_b, int64_t* tokens_out_host, int max_out, int* n_out, float* feats_out_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  const ss_config& c = h->cfg;
+  cudaStream_t st = S(stream);
+  if (T <= 0 || n_prefix < 0 || !n_out) return h->fail(SS_ERR_INVALID, "bad arguments to ss_mt_greedy");
+  const int start = n_prefix;
+  int max_len = (max_new_tokens == -1) ? std::min(max_len_b, c.max_mt_positions - 1) : start + max_new_tokens;
+  if (max_len < 1) return h->fail(SS_ERR_INVALID, "min_len cannot be larger than max_len");
+  if (start > max_len) return h->fail(SS_ERR_INVALID, "prefix longer than max_len");
+  if (max_len + 2 > c.max_mt_positions || max_len > max_out) return h->fail(SS_ERR_CAPACITY, "MT hypothesis longer than capacity");
+  int rc = ensure_mt_cross(h, T);
+  if (rc) return rc;
+  const int dim = c.mt_dim;
+  const int nmax = std::max(start + 1, 1);
+  if (!ws_begin(h, ((size_t)nmax * (dim * 7 + c.mt_ffn) + c.tgt_vocab + 4096) * sizeof(float))) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  DecScratch s = dec_scratch(h, nmax, dim, c.mt_ffn);
+  float* x = h->ws.f32((size_t)nmax * dim);
+  float* logits = h->ws.f32(c.tgt_vocab);
+  Linear outp;
+  outp.w = h->mt_emb; outp.b = nullptr; outp.N = c.tgt_vocab; outp.K = dim;
+  // tokens buffer = [eos, prefix...]
+  std::vector<int64_t> toks(start + 1);
+  toks[0] = c.eos;
+  for (int i = 0; i < start; ++i) toks[i + 1] = prefix_host[i];
+  cudaMemcpyAsync(h->mt_tok_dev, toks.data(), toks.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  mt_begin(h, enc_dev, T, st);
+  int fed = 0;  // rows in the KV cache
+  int n_tok = start;  // hypothesis length so far (without eos)
+  for (int i = 0; i < start; ++i) tokens_out_host[i] = prefix_host[i];
+  for (int step = start; step <= max_len; ++step) {
+    // feed tokens[fed .. step]  (first iteration: the whole prefix; afterwards one token)
+    int n = step + 1 - fed;
+    mt_forward(h, fed, n, T, nullptr, feats_out_dev + (size_t)fed * dim, s, x, st);
+    fed = step + 1;
+    if (step >= max_len) break;  // eos is forced here (sequence_generator.py:362-364): no need for the logits
+    linear(feats_out_dev + (size_t)step * dim, dim, 1, outp, ep_out(logits, c.tgt_vocab), st);
+    // lprobs[pad] = -inf; eos banned while step < min_len (=1)
+    if (step < 1)
+      argmax_rows(logits, c.tgt_vocab, 1, c.tgt_vocab, h->mask_pad_eos, 2, h->mt_next_dev, nullptr, st);
+    else
+      argmax_rows(logits, c.tgt_vocab, 1, c.tgt_vocab, h->mask_pad_unk, 1, h->mt_next_dev, nullptr, st);
+    cudaMemcpyAsync(h->mt_next_pinned, h->mt_next_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    // also append the chosen token to the device token buffer for the next step
+    cudaMemcpyAsync(h->mt_tok_dev + step + 1, h->mt_next_dev, sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return h->fail(SS_ERR_CUDA, std::string("ss_mt_greedy: ") + cudaGetErrorString(cudaGetLastError()));
+    int64_t next = h->mt_next_pinned[0];
+    if (next == c.eos) break;
+    tokens_out_host[n_tok++] = next;
+  }
+  *n_out = n_tok;
+  return check_launch(h, "ss_mt_greedy");
+}
+
+int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, int Slen, int n_pad_tail, int mask_eos, int64_t* argmax_dev,
+                       int64_t* units_dev, int32_t* count_dev, float* t2u_out_dev, float* logits_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  const ss_config& c = h->cfg;
+  cudaStream_t st = S(stream);
+  if (Slen <= 0 || n_pad_tail < 0 || n_pad_tail >= Slen) return h->fail(SS_ERR_INVALID, "bad T2U sequence length");
+  const int dim = c.unit_dim, R = c.ctc_upsample_rate, L = Slen * R;
+  size_t need = ((size_t)L * (dim * 8 + c.unit_ffn + c.unit_vocab) + (size_t)Slen * dim * 12 + (size_t)Slen * c.unit_ffn + 8192) * sizeof(float);
+  if (!ws_begin(h, need)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  // ---- T1: UniTransformerEncoderNoEmb.forward
+  DecScratch s1 = dec_scratch(h, Slen, dim, c.unit_ffn);
+  float* x = h->ws.f32((size_t)Slen * dim);
+  float* t2u = t2u_out_dev ? t2u_out_dev : h->ws.f32((size_t)Slen * dim);
+  int* kvlen = nullptr;
+  int* kvlen_up = nullptr;
+  if (n_pad_tail > 0) {  // encoder_padding_mask on the trailing pad positions
+    int v[2] = {Slen - n_pad_tail, (Slen - n_pad_tail) * R};
+    kvlen = (int*)h->ws.raw(2 * sizeof(int));
+    kvlen_up = kvlen + 1;
+    cudaMemcpyAsync(kvlen, v, sizeof(v), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+  }
+  copy_f32(mt_feats_dev, x, (int64_t)Slen * dim, st);
+  for (int l = 0; l < c.t2u_layers; ++l)
+    dec_layer(h->t2u[l], x, Slen, dim, c.unit_ffn, c.unit_heads, c.uni_encoder != 0, 0, kvlen, nullptr, nullptr, 0, nullptr, 0, nullptr, s1, st);
+  layer_norm(x, dim, t2u, dim, h->t2u_ln.g, h->t2u_ln.b, Slen, dim, st);
+  // ---- U1: CTCTransformerUnitDecoder: x25 upsample + (quirky) positional embedding, 2 layers, out-proj
+  DecScratch s2 = dec_scratch(h, L, dim, c.unit_ffn);
+  float* xu = h->ws.f32((size_t)L * dim);
+  float* ckv = h->ws.f32((size_t)Slen * 2 * dim);
+  float* logits = logits_dev ? logits_dev : h->ws.f32((size_t)L * c.unit_vocab);
+  if (!xu || !ckv || !logits) return h->fail(SS_ERR_CUDA, "workspace too small");
+  repeat_rows_add(t2u, Slen, R, dim, h->unit_pos_row, xu, st);
+  for (int l = 0; l < c.unit_layers; ++l) {
+    linear(t2u, dim, Slen, h->unit[l].ckv, ep_out(ckv, 2 * dim), st);
+    dec_layer(h->unit[l], xu, L, dim, c.unit_ffn, c.unit_heads, true, 0, kvlen_up, nullptr, nullptr, 0, ckv, Slen, kvlen, s2, st);
+  }
+  layer_norm(xu, dim, xu, dim, h->unit_ln.g, h->unit_ln.b, L, dim, st);
+  Linear outp;
+  outp.w = h->unit_emb; outp.b = nullptr; outp.N = c.unit_vocab; outp.K = dim;
+  linear(xu, dim, L, outp, ep_out(logits, c.unit_vocab), st);
+  // ---- U2: never select pad, unk (agent version) [+ eos: offline version]
+  argmax_rows(logits, c.unit_vocab, L, c.unit_vocab, h->mask_pad_unk, mask_eos ? 3 : 2, argmax_dev, nullptr, st);
+  ctc_collapse(argmax_dev, L, c.unit_vocab - 1, c.pad, units_dev, nullptr, count_dev, st);
+  return check_launch(h, "ss_t2u_unit_decode");
+}
+
+int ss_vocoder_durations(ss_engine* h, void* stream, const int64_t* codes_dev, int U, int dur_prediction, int64_t* dur_out_dev,
+                         int32_t* cumsum_out_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (!h->has_vocoder) return h->fail(SS_ERR_STATE, "no vocoder weights were loaded");
+  if (U <= 0) return h->fail(SS_ERR_INVALID, "empty code sequence");
+  const ss_config& c = h->cfg;
+  cudaStream_t st = S(stream);
+  const int E = c.voc_embedding_dim, Hd = c.voc_dur_hidden;
+  if (U > h->voc_ucap) {
+    if (h->voc_unit_emb) cudaFree(h->voc_unit_emb);
+    if (h->voc_cumsum) cudaFree(h->voc_cumsum);
+    h->voc_ucap = std::max(2 * U, 1024);
+    cudaMalloc((void**)&h->voc_unit_emb, (size_t)h->voc_ucap * E * sizeof(float));
+    cudaMalloc((void**)&h->voc_cumsum, (size_t)(h->voc_ucap + 1) * sizeof(int));
+  }
+  h->voc_U = U;
+  if (!ws_begin(h, ((size_t)U * (2 * Hd + 2) + 4096) * sizeof(float))) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  gather_rows(codes_dev, U, 0, h->voc_dict, E, h->voc_unit_emb, st);
+  float* a = h->ws.f32((size_t)U * Hd);
+  float* b = h->ws.f32((size_t)U * Hd);
+  float* ld = h->ws.f32(U);
+  if (dur_prediction) {
+    // VariancePredictor.forward (fairseq/models/text_to_speech/fastspeech2.py:144-151)
+    ConvA c1;
+    c1.x = h->voc_unit_emb; c1.B = 1; c1.L_in = U; c1.L_rows = U; c1.C_in = E; c1.ldx = E;
+    c1.ksize = h->dur_conv1.ksize; c1.pad_left = (h->dur_conv1.ksize - 1) / 2;
+    Epilogue e1 = ep_out(a, Hd, ACT_RELU);
+    e1.bias = h->dur_conv1.lin.b;
+    gemm_conv(c1, h->dur_conv1.lin.w, Hd, e1, st);
+    layer_norm(a, Hd, a, Hd, h->dur_ln1.g, h->dur_ln1.b, U, Hd, st);
+    ConvA c2;
+    c2.x = a; c2.B = 1; c2.L_in = U; c2.L_rows = U; c2.C_in = Hd; c2.ldx = Hd;
+    c2.ksize = h->dur_conv2.ksize; c2.pad_left = 1;  // padding=1 is hard-coded for conv2 (fastspeech2.py:137)
+    Epilogue e2 = ep_out(b, Hd, ACT_RELU);
+    e2.bias = h->dur_conv2.lin.b;
+    gemm_conv(c2, h->dur_conv2.lin.w, Hd, e2, st);
+    layer_norm(b, Hd, b, Hd, h->dur_ln2.g, h->dur_ln2.b, U, Hd, st);
+    linear(b, Hd, U, h->dur_proj, ep_out(ld, 1), st);
+  } else {
+    // no duration prediction: every code is one frame; log(2) rounds to dur 1
+    std::vector<float> v(U, 0.6931472f);
+    cudaMemcpyAsync(ld, v.data(), U * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+  }
+  duration_from_log(ld, U, dur_out_dev, h->voc_cumsum, st);
+  if (cumsum_out_dev) cudaMemcpyAsync(cumsum_out_dev, h->voc_cumsum, (U + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st);
+  return check_launch(h, "ss_vocoder_durations");
+}
+
+int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0, int n_frames, int left_context, float* wav_out_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (!h->has_vocoder || h->voc_U <= 0) return h->fail(SS_ERR_STATE, "ss_vocoder_durations must run first");
+  if (n_frames <= 0 || frame0 < 0 || frame0 + n_frames != total_frames) return h->fail(SS_ERR_INVALID, "vocoder frame range must be the tail of the sequence");
+  const ss_config& c = h->cfg;
+  cudaStream_t st = S(stream);
+  int ctx = left_context < 0 ? h->receptive_field : left_context;
+  ctx = std::min(ctx, frame0);
+  const int f_lo = frame0 - ctx;
+  const int N = n_frames + ctx;
+  // workspace: input frames + per-stage buffers
+  size_t maxbuf = 0;
+  {
+    int ch = c.voc_init_channels;
+    size_t L = N;
+    maxbuf = L * ch;
+    for (int i = 0; i < c.voc_n_ups; ++i) {
+      L *= c.voc_up_rates[i];
+      ch /= 2;
+      maxbuf = std::max(maxbuf, L * ch);
+    }
+  }
+  size_t total = ((size_t)N * c.voc_in_dim + 5 * maxbuf + (size_t)N * h->hop + 8192) * sizeof(float);
+  if (!ws_begin(h, total)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  float* frames = h->ws.f32((size_t)N * c.voc_in_dim);
+  float* bufX = h->ws.f32(maxbuf);   // stage input / output
+  float* bufY = h->ws.f32(maxbuf);   // upsampled stage activation
+  float* bufA = h->ws.f32(maxbuf);
+  float* bufB = h->ws.f32(maxbuf);
+  float* bufT = h->ws.f32(maxbuf);
+  float* wav = h->ws.f32((size_t)N * h->hop);
+  if (!frames || !bufX || !bufY || !bufA || !bufB || !bufT || !wav) return h->fail(SS_ERR_CUDA, "workspace too small");
+  // V1 tail: repeat_interleave(x, dur) for the frame window (agent/tts/codehifigan.py:66)
+  expand_frames(h->voc_unit_emb, h->voc_cumsum, h->voc_U, f_lo, N, c.voc_embedding_dim, frames, st);
+  // conv_pre
+  {
+    ConvA a;
+    a.x = frames; a.B = 1; a.L_in = N; a.L_rows = N; a.C_in = c.voc_in_dim; a.ldx = c.voc_in_dim; a.ksize = 7; a.pad_left = 3;
+    Epilogue e = ep_out(bufX, c.voc_init_channels);
+    e.bias = h->conv_pre.lin.b;
+    gemm_conv(a, h->conv_pre.lin.w, c.voc_init_channels, e, st);
+  }
+  int L = N, ch = c.voc_init_channels;
+  for (int i = 0; i < c.voc_n_ups; ++i) {
+    const UpsampleW& U = h->ups[i];
+    const int Lout = L * U.u;
+    // x = ups[i](leaky_relu(x, 0.1)): one GEMM per output phase, rows scattered with stride u
+    for (int phi = 0; phi < U.u; ++phi) {
+      int J = U.phase_J[phi], q0 = U.phase_q0[phi];
+      int qmax = (Lout - 1 - phi + U.pad) / U.u;
+      int nrows = qmax - q0 + 1;
+      if (nrows <= 0) continue;
+      ConvA a;
+      a.x = bufX; a.B = 1; a.L_in = L; a.L_rows = nrows; a.C_in = U.cin; a.ldx = U.cin; a.ksize = J; a.pad_left = (J - 1) - q0;
+      a.pre_lrelu = 0.1f;
+      Epilogue e = ep_out(bufY, U.cout);
+      e.bias = U.bias;
+      e.out_L = Lout; e.out_row_stride = U.u; e.out_row_offset = q0 * U.u + phi - U.pad;
+      gemm_conv(a, U.phase_w[phi].w, U.cout, e, st);
+    }
+    L = Lout;
+    ch = U.cout;
+    // xs = sum_j resblock_j(x) / num_kernels  (hifigan.py:158-165); ResBlock.forward :95-102
+    for (int j = 0; j < c.voc_n_rb; ++j) {
+      const float* cur = bufY;
+      float* pingpong[2] = {bufA, bufB};
+      int nd = c.voc_rb_ndil;
+      for (int m = 0; m < nd; ++m) {
+        const ConvW& w1 = h->rb1[i][j][m];
+        const ConvW& w2 = h->rb2[i][j][m];
+        ConvA a1;
+        a1.x = cur; a1.B = 1; a1.L_in = L; a1.L_rows = L; a1.C_in = ch; a1.ldx = ch; a1.ksize = w1.ksize; a1.dil = w1.dil;
+        a1.pad_left = (w1.ksize * w1.dil - w1.dil) / 2; a1.pre_lrelu = 0.1f;
+        Epilogue e1 = ep_out(bufT, ch);
+        e1.bias = w1.lin.b;
+        gemm_conv(a1, w1.lin.w, ch, e1, st);
+        ConvA a2;
+        a2.x = bufT; a2.B = 1; a2.L_in = L; a2.L_rows = L; a2.C_in = ch; a2.ldx = ch; a2.ksize = w2.ksize; a2.dil = 1;
+        a2.pad_left = (w2.ksize - 1) / 2; a2.pre_lrelu = 0.1f;
+        Epilogue e2;
+        e2.bias = w2.lin.b;
+        e2.ldo = ch;
+        if (m + 1 < nd) {
+          e2.out = pingpong[m & 1];
+          e2.residual = cur;  // x = xt + x
+          e2.res_scale = 1.0f;
+        } else {
+          // last pair of the block: accumulate (xt + x) / num_kernels into the stage output
+          e2.out = bufX;
+          e2.alpha = 1.0f / c.voc_n_rb;
+          e2.residual = cur;
+          e2.res_scale = 1.0f / c.voc_n_rb;
+          e2.accumulate = (j > 0);
+        }
+        // NB: residual and out must not alias for the accumulate form; cur is bufY/bufA/bufB, out is bufX or the other ping-pong
+        gemm_conv(a2, w2.lin.w, ch, e2, st);
+        cur = e2.out;
+      }
+    }
+  }
+  // x = leaky_relu(x) [slope 0.01, hifigan.py:166]; conv_post; tanh
+  conv_post_tanh(bufX, L, ch, h->conv_post_w, h->conv_post_b, h->conv_post_k, 0.01f, wav, st);
+  copy_f32(wav + (size_t)ctx * h->hop, wav_out_dev, (int64_t)n_frames * h->hop, st);
+  return check_launch(h, "ss_vocoder_generate");
+}
+
+int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N, int act,
+                 float* out_dev) {
+  if (!h) return SS_ERR_INVALID;
+  Linear l;
+  l.w = const_cast<float*>(w_dev); l.b = const_cast<float*>(bias_dev); l.N = N; l.K = K;
+  linear(x_dev, K, M, l, ep_out(out_dev, N, act), S(stream));
+  return check_launch(h, "ss_op_linear");
+}
+
+int ss_op_layer_norm(ss_engine* h, void* stream, const float* x_dev, int rows, int C, const float* g_dev, const float* b_dev, float* out_dev) {
+  if (!h) return SS_ERR_INVALID;
+  layer_norm(x_dev, C, out_dev, C, g_dev, b_dev, rows, C, S(stream));
+  return check_launch(h, "ss_op_layer_norm");
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Attention kernels (fp32, head_dim 64).  One CTA per (query tile, head, batch element); the score
+// tile lives in shared memory, softmax uses warp-shuffle reductions.
+//   relpos_attention: RelPositionMultiHeadedAttention.forward with the rel_shift folded into the index
+//                     bd[i][j] = (q_i + v) . P[i - j]   (uni_unity/modules/espnet_multihead_attention.py:133-209)
+//   mha_attention   : fairseq MultiheadAttention slow path (ctc_unity/modules/multihead_attention.py:555-784)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ss {
+namespace {
+
+constexpr int QT = 16;    // queries per CTA
+constexpr int ATT_NT = 128;
+constexpr int HD = 64;    // head dim
+
+__device__ __forceinline__ float dot64(const float* __restrict__ a_smem, const float* __restrict__ b_gmem) {
+  float acc = 0.f;
+#pragma unroll
+  for (int d = 0; d < HD; d += 4) {
+    float4 b = *reinterpret_cast<const float4*>(b_gmem + d);
+    acc = fmaf(a_smem[d + 0], b.x, acc);
+    acc = fmaf(a_smem[d + 1], b.y, acc);
+    acc = fmaf(a_smem[d + 2], b.z, acc);
+    acc = fmaf(a_smem[d + 3], b.w, acc);
+  }
+  return acc;
+}
+
+// softmax over S[q][0..n) for every query row of the tile; rows are handled one warp at a time
+__device__ __forceinline__ void softmax_rows(float* S, int ld, int nq, const int* nvis) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = warp; q < nq; q += ATT_NT / 32) {
+    float* row = S + q * ld;
+    int n = nvis[q];
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      float e = expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int j = lane; j < n; j += 32) row[j] = row[j] / sum;
+  }
+}
+
+// out[q][d] = sum_j S[q][j] * V[j][d]; thread -> (q = tid/8, 8 dims starting at (tid%8)*8)
+__device__ __forceinline__ void pv_store(const float* S, int ld, int nq, const int* nvis, const float* __restrict__ vbase,
+                                         int64_t ldv, float* __restrict__ obase, int64_t ldo, int i0) {
+  int q = threadIdx.x >> 3, d0 = (threadIdx.x & 7) * 8;
+  if (q >= nq) return;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  int n = nvis[q];
+  const float* row = S + q * ld;
+  for (int j = 0; j < n; ++j) {
+    float p = row[j];
+    const float* vp = vbase + (int64_t)j * ldv + d0;
+    float4 a = *reinterpret_cast<const float4*>(vp);
+    float4 b = *reinterpret_cast<const float4*>(vp + 4);
+    acc[0] = fmaf(p, a.x, acc[0]);
+    acc[1] = fmaf(p, a.y, acc[1]);
+    acc[2] = fmaf(p, a.z, acc[2]);
+    acc[3] = fmaf(p, a.w, acc[3]);
+    acc[4] = fmaf(p, b.x, acc[4]);
+    acc[5] = fmaf(p, b.y, acc[5]);
+    acc[6] = fmaf(p, b.z, acc[6]);
+    acc[7] = fmaf(p, b.w, acc[7]);
+  }
+  float* op = obase + (int64_t)(i0 + q) * ldo + d0;
+  *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+__global__ void __launch_bounds__(ATT_NT) relpos_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ pos,
+                                                                  int Tpos, const float* __restrict__ bias_u,
+                                                                  const float* __restrict__ bias_v, float* __restrict__ out,
+                                                                  int T, int H, int D, int chunk,
+                                                                  const int* __restrict__ lengths, int ldS) {
+  extern __shared__ __align__(16) float smem[];
+  float* Qu = smem;                 // [QT][64]
+  float* Qv = Qu + QT * HD;         // [QT][64]
+  float* S = Qv + QT * HD;          // [QT][ldS]
+  __shared__ int nvis[QT];
+  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QT;
+  const int nq = min(QT, T - i0);
+  const int len = lengths ? min(lengths[b], T) : T;
+  const int64_t ld3 = 3 * (int64_t)D;
+  const float* qb = qkv + ((int64_t)b * T) * ld3 + h * HD;
+  const float* kb = qb + D;
+  const float* vb = qb + 2 * D;
+  for (int e = threadIdx.x; e < QT * HD; e += ATT_NT) {
+    int q = e / HD, d = e % HD;
+    float v = (q < nq) ? qb[(int64_t)(i0 + q) * ld3 + d] : 0.f;
+    Qu[e] = v + bias_u[h * HD + d];
+    Qv[e] = v + bias_v[h * HD + d];
+  }
+  if (threadIdx.x < QT) {
+    int i = i0 + threadIdx.x;
+    int lim = chunk > 0 ? min((i / chunk + 1) * chunk, T) : T;   // chunk mask (s2t_conformer.py:195-213)
+    nvis[threadIdx.x] = max(1, min(lim, len));                   // key padding mask (forward_attention)
+    if (len <= 0) nvis[threadIdx.x] = lim;
+  }
+  __syncthreads();
+  const int kmax = nvis[nq - 1];  // limits are non-decreasing in i
+  const float* pb = pos + h * HD;
+  for (int e = threadIdx.x; e < nq * kmax; e += ATT_NT) {
+    int q = e / kmax, j = e - q * kmax;
+    if (j >= nvis[q]) continue;
+    int i = i0 + q;
+    float ac = dot64(Qu + q * HD, kb + (int64_t)j * ld3);
+    float bd = dot64(Qv + q * HD, pb + (int64_t)(i - j + Tpos - 1) * D);
+    S[q * ldS + j] = (ac + bd) * 0.125f;  // / sqrt(d_k), d_k = 64
+  }
+  __syncthreads();
+  softmax_rows(S, ldS, nq, nvis);
+  __syncthreads();
+  pv_store(S, ldS, nq, nvis, vb, ld3, out + ((int64_t)b * T) * D + h * HD, D, i0);
+}
+
+__global__ void __launch_bounds__(ATT_NT) mha_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+                                                               int ldk, const float* __restrict__ v, int ldv,
+                                                               float* __restrict__ out, int ldo, int Tq, int Tk, float scale,
+                                                               int causal, int causal_offset,
+                                                               const int* __restrict__ kv_len, int ldS) {
+  extern __shared__ __align__(16) float smem[];
+  float* Q = smem;            // [QT][64]
+  float* S = Q + QT * HD;     // [QT][ldS]
+  __shared__ int nvis[QT];
+  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QT;
+  const int nq = min(QT, Tq - i0);
+  const int len = kv_len ? min(kv_len[b], Tk) : Tk;
+  const float* qb = q + ((int64_t)b * Tq) * ldq + h * HD;
+  const float* kb = k + ((int64_t)b * Tk) * ldk + h * HD;
+  const float* vb = v + ((int64_t)b * Tk) * ldv + h * HD;
+  for (int e = threadIdx.x; e < QT * HD; e += ATT_NT) {
+    int qq = e / HD, d = e % HD;
+    Q[e] = (qq < nq) ? qb[(int64_t)(i0 + qq) * ldq + d] * scale : 0.f;  // q *= scaling (multihead_attention.py:573)
+  }
+  if (threadIdx.x < QT) {
+    int i = i0 + threadIdx.x;
+    int lim = causal ? min(i + causal_offset + 1, Tk) : Tk;
+    nvis[threadIdx.x] = max(1, min(lim, len));
+  }
+  __syncthreads();
+  int kmax = 0;
+  for (int qq = 0; qq < nq; ++qq) kmax = max(kmax, nvis[qq]);
+  for (int e = threadIdx.x; e < nq * kmax; e += ATT_NT) {
+    int qq = e / kmax, j = e - qq * kmax;
+    if (j >= nvis[qq]) continue;
+    S[qq * ldS + j] = dot64(Q + qq * HD, kb + (int64_t)j * ldk);
+  }
+  __syncthreads();
+  softmax_rows(S, ldS, nq, nvis);
+  __syncthreads();
+  pv_store(S, ldS, nq, nvis, vb, ldv, out + ((int64_t)b * Tq) * ldo + h * HD, ldo, i0);
+}
+
+}  // namespace
+
+void relpos_attention(const float* qkv, const float* pos, int Tpos, const float* bias_u, const float* bias_v, float* out,
+                      int B, int T, int H, int D, int chunk, const int* lengths_dev, cudaStream_t st) {
+  ++g_launches;
+  if (B <= 0 || T <= 0) return;
+  int ldS = (T + 3) & ~3;
+  size_t smem = (size_t)(2 * QT * HD + QT * ldS) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(relpos_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid((T + QT - 1) / QT, H, B);
+  relpos_attention_kernel<<<grid, ATT_NT, smem, st>>>(qkv, pos, Tpos, bias_u, bias_v, out, T, H, D, chunk, lengths_dev, ldS);
+}
+
+void mha_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int B,
+                   int Tq, int Tk, int H, float scale, int causal, int causal_offset, const int* kv_len_dev,
+                   cudaStream_t st) {
+  ++g_launches;
+  if (B <= 0 || Tq <= 0 || Tk <= 0) return;
+  int ldS = (Tk + 3) & ~3;
+  size_t smem = (size_t)(QT * HD + QT * ldS) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(mha_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid((Tq + QT - 1) / QT, H, B);
+  mha_attention_kernel<<<grid, ATT_NT, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, scale, causal, causal_offset,
+                                                   kv_len_dev, ldS);
+}
+
+}  // namespace ss

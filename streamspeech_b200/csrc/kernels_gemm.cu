@@ -1,0 +1,221 @@
+// fp32 SIMT GEMM with an implicit-im2col A operand (conv-as-GEMM over channels-last activations)
+// and fused epilogues (bias, activation, GLU, residual, strided row scatter for transposed convs).
+//
+// Why fp32 CUDA cores here: the parity bar is bit-exact arg-max tokens against the reference's fp32
+// CPU path (BASELINE.json north_star); every GEMM on the path feeds an arg-max within a few layers.
+// This kernel is the exact-precision baseline; the tcgen05 path (kernels_umma.cu) is opt-in per GEMM.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ss {
+
+namespace {
+
+constexpr int BK = 16;
+constexpr int NT = 256;
+
+template <bool CONV>
+__device__ __forceinline__ float4 load_a4(const ConvA& a, int m, int kk, int M, int K) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (m >= M || kk >= K) return v;
+  const float* p;
+  if (CONV) {
+    int b = m / a.L_rows;
+    int t = m - b * a.L_rows;
+    int tap = kk / a.C_in;
+    int ci = kk - tap * a.C_in;
+    int center = t * a.stride;
+    int pos = center + tap * a.dil - a.pad_left;
+    if (pos < 0 || pos >= a.L_in) return v;
+    if (a.chunk > 0 && pos >= (center / a.chunk + 1) * a.chunk) return v;
+    if (a.lengths != nullptr && pos >= a.lengths[b]) return v;
+    p = a.x + ((int64_t)b * a.L_in + pos) * a.ldx + ci;
+  } else {
+    p = a.x + (int64_t)m * a.ldx + kk;
+  }
+  v = *reinterpret_cast<const float4*>(p);
+  if (a.pre_lrelu != 1.0f) {
+    v.x = v.x > 0.f ? v.x : v.x * a.pre_lrelu;
+    v.y = v.y > 0.f ? v.y : v.y * a.pre_lrelu;
+    v.z = v.z > 0.f ? v.z : v.z * a.pre_lrelu;
+    v.w = v.w > 0.f ? v.w : v.w * a.pre_lrelu;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return x > 0.f ? x : 0.f;
+    case ACT_SILU: return x / (1.0f + expf(-x));
+    case ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+template <int BM, int BN, bool CONV>
+__global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restrict__ W, int M, int N, int K, Epilogue ep) {
+  constexpr int TM = BM / 16;
+  constexpr int TN = BN / 16;
+  constexpr int A_F4 = BM * BK / 4;  // float4 loads per A tile
+  constexpr int B_F4 = BN * BK / 4;
+  constexpr int A_PER = (A_F4 + NT - 1) / NT;
+  constexpr int B_PER = (B_F4 + NT - 1) / NT;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[A_PER], rb[B_PER];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int idx = tid + i * NT;
+      if (idx < A_F4) ra[i] = load_a4<CONV>(a, m0 + (idx >> 2), k0 + ((idx & 3) << 2), M, K);
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int idx = tid + i * NT;
+      if (idx < B_F4) {
+        int n = n0 + (idx >> 2), kk = k0 + ((idx & 3) << 2);
+        rb[i] = (n < N && kk < K) ? *reinterpret_cast<const float4*>(W + (int64_t)n * K + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int idx = tid + i * NT;
+      if (idx < A_F4) {
+        int r = idx >> 2, kq = (idx & 3) << 2;
+        As[buf][kq + 0][r] = ra[i].x;
+        As[buf][kq + 1][r] = ra[i].y;
+        As[buf][kq + 2][r] = ra[i].z;
+        As[buf][kq + 3][r] = ra[i].w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int idx = tid + i * NT;
+      if (idx < B_F4) {
+        int r = idx >> 2, kq = (idx & 3) << 2;
+        Bs[buf][kq + 0][r] = rb[i].x;
+        Bs[buf][kq + 1][r] = rb[i].y;
+        Bs[buf][kq + 2][r] = rb[i].z;
+        Bs[buf][kq + 3][r] = rb[i].w;
+      }
+    }
+  };
+
+  const int nk = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[buf][k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    int64_t orow = m;
+    if (ep.out_L > 0) {
+      int b = m / a.L_rows;
+      int t = m - b * a.L_rows;
+      orow = (int64_t)b * ep.out_L + (int64_t)t * ep.out_row_stride + ep.out_row_offset;
+    }
+    float* orow_p = ep.out + orow * ep.ldo;
+    const float* rrow_p = ep.residual ? ep.residual + orow * ep.ldo : nullptr;
+    if (ep.glu) {
+      if (TN >= 2) {
+#pragma unroll
+        for (int j = 0; j + 1 < TN; j += 2) {
+          int n = n0 + tx * TN + j;
+          if (n >= N) continue;
+          float av_ = acc[i][j] + (ep.bias ? ep.bias[n] : 0.f);
+          float gv = acc[i][j + 1] + (ep.bias ? ep.bias[n + 1] : 0.f);
+          float y = ep.alpha * (av_ * (1.0f / (1.0f + expf(-gv))));
+          int oc = n >> 1;
+          if (rrow_p) y += ep.res_scale * rrow_p[oc];
+          if (ep.accumulate) y += orow_p[oc];
+          orow_p[oc] = y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int n = n0 + tx * TN + j;
+        if (n >= N) continue;
+        float y = acc[i][j] + (ep.bias ? ep.bias[n] : 0.f);
+        y = ep.alpha * apply_act(y, ep.act);
+        if (rrow_p) y += ep.res_scale * rrow_p[n];
+        if (ep.accumulate) y += orow_p[n];
+        orow_p[n] = y;
+      }
+    }
+  }
+}
+
+template <int BM, int BN>
+void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue& ep, bool conv, cudaStream_t st) {
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if (conv)
+    gemm_kernel<BM, BN, true><<<grid, NT, 0, st>>>(a, W, M, N, K, ep);
+  else
+    gemm_kernel<BM, BN, false><<<grid, NT, 0, st>>>(a, W, M, N, K, ep);
+}
+
+}  // namespace
+
+void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaStream_t st) {
+  ++g_launches;
+  const int M = a.B * a.L_rows;
+  const int K = a.ksize * a.C_in;
+  if (M <= 0 || N <= 0) return;
+  const bool conv = !(a.ksize == 1 && a.stride == 1 && a.pad_left == 0 && a.chunk == 0 && a.lengths == nullptr &&
+                      a.L_in == a.L_rows);
+  auto ctas = [&](int bm, int bn) { return (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
+  const long target = 148;  // one wave of SMs
+  if (N <= 16 && !ep.glu) {
+    if (ctas(128, 16) >= target) launch<128, 16>(a, W, M, N, K, ep, conv, st);
+    else launch<32, 16>(a, W, M, N, K, ep, conv, st);
+    return;
+  }
+  if (N <= 32) {
+    if (ctas(64, 32) >= target) launch<64, 32>(a, W, M, N, K, ep, conv, st);
+    else launch<32, 32>(a, W, M, N, K, ep, conv, st);
+    return;
+  }
+  if (ctas(128, 64) >= 2 * target) launch<128, 64>(a, W, M, N, K, ep, conv, st);
+  else if (ctas(64, 64) >= target) launch<64, 64>(a, W, M, N, K, ep, conv, st);
+  else if (ctas(32, 64) >= target) launch<32, 64>(a, W, M, N, K, ep, conv, st);
+  else launch<32, 32>(a, W, M, N, K, ep, conv, st);
+}
+
+}  // namespace ss

@@ -1,0 +1,313 @@
+// Streaming / scan kernels of the path: LayerNorm, depthwise chunk-causal conv + BN + SiLU, embedding
+// gathers, arg-max over the vocabulary, CTC collapse, duration rounding, frame expansion, conv_post.
+// All HBM-bound: coalesced row-major accesses, warp-shuffle reductions, no re-reads.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ss {
+unsigned long long g_launches = 0;
+namespace {
+
+// one warp per row; two-pass (mean, then centred sum of squares) like ATen's RowwiseMoments result
+template <int N>  // N = C / 32
+__global__ void layer_norm_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
+  constexpr int C = N * 32;
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * ldx;
+  float v[N];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    v[i] = xr[lane + (i << 5)];
+    s += v[i];
+  }
+  float mean = warp_sum(s) / (float)C;
+  float ss_ = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float d = v[i] - mean;
+    ss_ = fmaf(d, d, ss_);
+  }
+  float var = warp_sum(ss_) / (float)C;
+  float rstd = 1.0f / sqrtf(var + 1e-5f);
+  float* yr = y + (int64_t)row * ldy;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    int c = lane + (i << 5);
+    yr[c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+__global__ void depthwise_bn_silu_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                         float* __restrict__ y, int ldy, int T, int C, int k, int chunk,
+                                         const int* __restrict__ lengths) {
+  int row = blockIdx.x;  // b*T + t
+  int b = row / T, t = row - b * T;
+  int half = (k - 1) >> 1;
+  int lim = T;
+  if (chunk > 0) lim = min(T, (t / chunk + 1) * chunk);  // future beyond the chunk end is zero (chunk_causal_conv1d.py:40-62)
+  (void)lengths;  // the reference convolves over padded frames too (padding is only masked in attention)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      int p = t - half + j;
+      if (p < 0 || p >= lim) continue;
+      acc = fmaf(w[j * C + c], x[((int64_t)b * T + p) * ldx + c], acc);
+    }
+    float v = acc * scale[c] + shift[c];
+    y[(int64_t)row * ldy + c] = v / (1.0f + expf(-v));
+  }
+}
+
+__global__ void scale_kernel(float* x, int64_t n, float s) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= s;
+}
+
+__global__ void copy_kernel(const float* __restrict__ s, float* __restrict__ d, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = s[i];
+}
+
+__global__ void embed_tokens_pos_kernel(const int64_t* __restrict__ tokens, const int* __restrict__ positions, int pos_offset,
+                                        const float* __restrict__ emb, const float* __restrict__ pos_table, float scale,
+                                        float* __restrict__ out, int rows, int C, int pad_idx) {
+  int r = blockIdx.x;
+  int64_t tok = tokens[r];
+  // make_positions (fairseq/utils.py:256-266) for sequences whose pads are trailing:
+  // non-pad token at index i gets pad_idx + 1 + i, pad gets pad_idx (a zero row)
+  int p = positions ? positions[r] : (tok == pad_idx ? pad_idx : pad_idx + 1 + pos_offset + r);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    out[(int64_t)r * C + c] = scale * emb[tok * C + c] + pos_table[(int64_t)p * C + c];
+}
+
+__global__ void repeat_rows_add_kernel(const float* __restrict__ x, int S, int R, int C, const float* __restrict__ addvec,
+                                       float* __restrict__ out) {
+  int r = blockIdx.x;  // output row s*R + rr
+  int s = r / R;
+  const float* xr = x + (int64_t)s * C;
+  // N1 quirk: position index comes from the VALUE x[t, b, 0]: != 1.0 -> pad+1 (addvec), == 1.0 -> pad (zero row)
+  bool add = addvec != nullptr && xr[0] != 1.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(int64_t)r * C + c] = xr[c] + (add ? addvec[c] : 0.f);
+}
+
+// arg-max of log_softmax(logits) with masked columns, first index wins on ties
+// (CTCDecoder.generate, agent/ctc_decoder.py:53-62; F.log_softmax = (x - max) - log(sum(exp(x - max))))
+__global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ masked, int n_masked,
+                                   int64_t* __restrict__ out_idx, float* __restrict__ out_lprob) {
+  __shared__ float red[32];
+  __shared__ float sval[32];
+  __shared__ int sidx[32];
+  int row = blockIdx.x;
+  const float* x = logits + (int64_t)row * ld;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, x[c]);
+  mx = warp_max(mx);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) red[w] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(x[c] - mx);
+  s = block_sum(s, red);
+  float lse = logf(s);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    bool m = false;
+    for (int q = 0; q < n_masked; ++q) m |= (masked[q] == c);
+    float lp = m ? -INFINITY : (x[c] - mx) - lse;
+    if (lp > best || (lp == best && c < bi)) {
+      best = lp;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+    sval[w] = best;
+    sidx[w] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < nw; ++i)
+      if (sval[i] > best || (sval[i] == best && sidx[i] < bi)) {
+        best = sval[i];
+        bi = sidx[i];
+      }
+    out_idx[row] = bi;
+    if (out_lprob) out_lprob[row] = best;
+  }
+}
+
+__global__ void ctc_collapse_kernel(const int64_t* __restrict__ am, int n, int blank, int pad, int64_t* __restrict__ toks,
+                                    int* __restrict__ index, int* __restrict__ count) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int c = 0;
+  for (int i = 0; i < n; ++i) {
+    int64_t v = am[i];
+    if (i == 0 || v != am[i - 1]) {
+      if (v != blank && v != pad) {
+        toks[c] = v;
+        if (index) index[c] = i;
+        ++c;
+      }
+    }
+  }
+  *count = c;
+}
+
+__global__ void gather_rows_kernel(const int64_t* __restrict__ idx, int idx_offset, const float* __restrict__ table, int C,
+                                   float* __restrict__ out) {
+  int r = blockIdx.x;
+  int64_t t = idx[r] + idx_offset;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(int64_t)r * C + c] = table[t * C + c];
+}
+
+__global__ void duration_kernel(const float* __restrict__ logdur, int n, int64_t* __restrict__ dur, int* __restrict__ cumsum) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int acc = 0;
+  cumsum[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    // torch.clamp(torch.round(torch.exp(x) - 1).long(), min=1)  (agent/tts/codehifigan.py:63-65); round = half-to-even
+    float d = rintf(expf(logdur[i]) - 1.0f);
+    long long di = (long long)d;
+    if (di < 1) di = 1;
+    if (di > 100000) di = 100000;
+    dur[i] = di;
+    acc += (int)di;
+    cumsum[i + 1] = acc;
+  }
+}
+
+__global__ void expand_frames_kernel(const float* __restrict__ emb, const int* __restrict__ cumsum, int U, int f0, int C,
+                                     float* __restrict__ out) {
+  int f = f0 + blockIdx.x;
+  int lo = 0, hi = U;  // find u with cumsum[u] <= f < cumsum[u+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (cumsum[mid] <= f) lo = mid; else hi = mid;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(int64_t)blockIdx.x * C + c] = emb[(int64_t)lo * C + c];
+}
+
+__global__ void conv_post_tanh_kernel(const float* __restrict__ x, int L, int C, const float* __restrict__ w, float bias, int k,
+                                      float pre_slope, float* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  int half = (k - 1) >> 1;
+  float acc = bias;
+  for (int j = 0; j < k; ++j) {
+    int p = t - half + j;
+    if (p < 0 || p >= L) continue;
+    const float* xr = x + (int64_t)p * C;
+    for (int c = 0; c < C; ++c) {
+      float v = xr[c];
+      v = v > 0.f ? v : v * pre_slope;
+      acc = fmaf(w[j * C + c], v, acc);
+    }
+  }
+  out[t] = tanhf(acc);
+}
+
+}  // namespace
+
+void layer_norm(const float* x, int ldx, float* y, int ldy, const float* gamma, const float* beta, int rows, int C,
+                cudaStream_t st) {
+  ++g_launches;
+  if (rows <= 0) return;
+  const int wpb = 8;
+  dim3 grid((rows + wpb - 1) / wpb);
+  switch (C) {
+    case 128: layer_norm_kernel<4><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
+    case 256: layer_norm_kernel<8><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
+    case 512: layer_norm_kernel<16><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
+    case 1024: layer_norm_kernel<32><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
+    default: break;  // engine validates C at finalize
+  }
+}
+
+void depthwise_bn_silu(const float* x, int ldx, const float* w, const float* scale, const float* shift, float* y, int ldy,
+                       int B, int T, int C, int k, int chunk, const int* lengths_dev, cudaStream_t st) {
+  ++g_launches;
+  if (B * T <= 0) return;
+  depthwise_bn_silu_kernel<<<B * T, 256, 0, st>>>(x, ldx, w, scale, shift, y, ldy, T, C, k, chunk, lengths_dev);
+}
+
+void scale_rows(float* x, int64_t n, float s, cudaStream_t st) {
+  ++g_launches;
+  if (n <= 0) return;
+  scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s);
+}
+
+void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st) {
+  ++g_launches;
+  if (n <= 0) return;
+  copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+}
+
+void embed_tokens_pos(const int64_t* tokens, const int* positions_or_null, int pos_offset, const float* emb,
+                      const float* pos_table, float scale, float* out, int rows, int C, int pad_idx, cudaStream_t st) {
+  ++g_launches;
+  if (rows <= 0) return;
+  embed_tokens_pos_kernel<<<rows, 128, 0, st>>>(tokens, positions_or_null, pos_offset, emb, pos_table, scale, out, rows, C, pad_idx);
+}
+
+void repeat_rows_add(const float* x, int S, int R, int C, const float* addvec_or_null, float* out, cudaStream_t st) {
+  ++g_launches;
+  if (S * R <= 0) return;
+  repeat_rows_add_kernel<<<S * R, 128, 0, st>>>(x, S, R, C, addvec_or_null, out);
+}
+
+void argmax_rows(const float* logits, int ld, int rows, int V, const int* masked_cols, int n_masked, int64_t* out_idx,
+                 float* out_lprob_or_null, cudaStream_t st) {
+  ++g_launches;
+  if (rows <= 0) return;
+  argmax_rows_kernel<<<rows, 256, 0, st>>>(logits, ld, V, masked_cols, n_masked, out_idx, out_lprob_or_null);
+}
+
+void ctc_collapse(const int64_t* argmax, int n, int blank, int pad, int64_t* out_tokens, int* out_index, int* out_count,
+                  cudaStream_t st) {
+  ++g_launches;
+  ctc_collapse_kernel<<<1, 32, 0, st>>>(argmax, n, blank, pad, out_tokens, out_index, out_count);
+}
+
+void gather_rows(const int64_t* idx, int n, int idx_offset, const float* table, int C, float* out, cudaStream_t st) {
+  ++g_launches;
+  if (n <= 0) return;
+  gather_rows_kernel<<<n, 128, 0, st>>>(idx, idx_offset, table, C, out);
+}
+
+void duration_from_log(const float* logdur, int n, int64_t* dur, int* cumsum, cudaStream_t st) {
+  ++g_launches;
+  duration_kernel<<<1, 32, 0, st>>>(logdur, n, dur, cumsum);
+}
+
+void expand_frames(const float* emb, const int* cumsum, int U, int f0, int nf, int C, float* out, cudaStream_t st) {
+  ++g_launches;
+  if (nf <= 0) return;
+  expand_frames_kernel<<<nf, 128, 0, st>>>(emb, cumsum, U, f0, C, out);
+}
+
+void conv_post_tanh(const float* x, int L, int C, const float* w, float bias, int k, float pre_slope, float* out,
+                    cudaStream_t st) {
+  ++g_launches;
+  if (L <= 0) return;
+  conv_post_tanh_kernel<<<(L + 127) / 128, 128, 0, st>>>(x, L, C, w, bias, k, pre_slope, out);
+}
+
+}  // namespace ss

@@ -1,0 +1,310 @@
+"""ctypes binding of libstreamspeech_b200.so (include/streamspeech_b200.h): PyTorch tensors in, PyTorch tensors out.
+
+PyTorch is plumbing here (device memory, streams); every FLOP of the path runs in the library's own
+sm_100a kernels.  There is NO CPU fallback: importing this module without the built library, or
+constructing an Engine without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import constants
+from .config import ModelConfig
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstreamspeech_b200.so")
+SS_MAX_UPS, SS_MAX_RB, SS_MAX_DIL = 8, 4, 4
+
+
+class SSConfig(ctypes.Structure):
+    _fields_ = (
+        [(n, ctypes.c_int32) for n in (
+            "feat_dim", "enc_dim", "enc_ffn", "enc_heads", "enc_layers", "dw_kernel", "conv_channels", "conv_kernel",
+            "src_vocab", "tgt_vocab", "mt_dim", "mt_ffn", "mt_heads", "mt_layers",
+            "t2u_layers", "unit_dim", "unit_ffn", "unit_heads", "unit_layers", "unit_vocab", "ctc_upsample_rate",
+            "bos", "pad", "eos", "unk", "uni_encoder", "max_enc_frames", "max_mt_positions", "voc_n_ups")]
+        + [("voc_up_rates", ctypes.c_int32 * SS_MAX_UPS), ("voc_up_kernels", ctypes.c_int32 * SS_MAX_UPS),
+           ("voc_init_channels", ctypes.c_int32), ("voc_n_rb", ctypes.c_int32),
+           ("voc_rb_kernels", ctypes.c_int32 * SS_MAX_RB), ("voc_rb_ndil", ctypes.c_int32),
+           ("voc_rb_dils", (ctypes.c_int32 * SS_MAX_DIL) * SS_MAX_RB)]
+        + [(n, ctypes.c_int32) for n in ("voc_num_embeddings", "voc_embedding_dim", "voc_in_dim", "voc_dur_hidden", "voc_dur_kernel")]
+    )
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the in-tree shared library; raise loudly if it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: build it with `make -C streamspeech_b200/csrc` "
+                          "(or __graft_entry__.build()).  There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.ss_create.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(SSConfig)]
+    lib.ss_destroy.argtypes = [vp]
+    lib.ss_last_error.argtypes = [vp]
+    lib.ss_last_error.restype = ctypes.c_char_p
+    lib.ss_version.restype = ctypes.c_char_p
+    lib.ss_load_tensor.argtypes = [vp, ctypes.c_char_p, vp, i32, ctypes.POINTER(i64)]
+    lib.ss_finalize.argtypes = [vp]
+    lib.ss_set_chunk.argtypes = [vp, i32, i32]
+    lib.ss_fbank_num_frames.argtypes = [i64]
+    lib.ss_fbank_num_frames.restype = i64
+    lib.ss_encoder_out_frames.argtypes = [i64]
+    lib.ss_encoder_out_frames.restype = i64
+    lib.ss_fbank.argtypes = [vp, vp, vp, i64, i64, i64, vp]
+    lib.ss_encoder_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    lib.ss_ctc_greedy.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    lib.ss_mt_greedy.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, i32, ctypes.POINTER(i32), vp]
+    lib.ss_mt_features.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp]
+    lib.ss_t2u_unit_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.ss_vocoder_durations.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.ss_vocoder_generate.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.ss_vocoder_hop.argtypes = [vp]
+    lib.ss_vocoder_receptive_field.argtypes = [vp]
+    lib.ss_op_linear.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, vp]
+    lib.ss_op_layer_norm.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    lib.ss_launch_count.argtypes = [vp]
+    lib.ss_launch_count.restype = i64
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
+    "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_ctc_greedy", "ss_mt_greedy",
+    "ss_mt_features", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
+    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_layer_norm", "ss_launch_count",
+]
+
+
+def make_ss_config(cfg: ModelConfig, max_enc_frames: int, max_mt_positions: int = 1024) -> SSConfig:
+    c = SSConfig()
+    for n in ("feat_dim", "enc_dim", "enc_ffn", "enc_heads", "enc_layers", "dw_kernel", "conv_channels", "conv_kernel",
+              "src_vocab", "tgt_vocab", "mt_dim", "mt_ffn", "mt_heads", "mt_layers", "t2u_layers", "unit_dim", "unit_ffn",
+              "unit_heads", "unit_layers", "unit_vocab", "ctc_upsample_rate", "bos", "pad", "eos", "unk"):
+        setattr(c, n, int(getattr(cfg, n)))
+    c.uni_encoder = int(cfg.uni_encoder)
+    c.max_enc_frames = max_enc_frames
+    c.max_mt_positions = max_mt_positions
+    v = cfg.vocoder
+    c.voc_n_ups = len(v.upsample_rates)
+    for i, (u, k) in enumerate(zip(v.upsample_rates, v.upsample_kernel_sizes)):
+        c.voc_up_rates[i], c.voc_up_kernels[i] = u, k
+    c.voc_init_channels = v.upsample_initial_channel
+    c.voc_n_rb = len(v.resblock_kernel_sizes)
+    c.voc_rb_ndil = len(v.resblock_dilation_sizes[0])
+    for j, (k, dils) in enumerate(zip(v.resblock_kernel_sizes, v.resblock_dilation_sizes)):
+        c.voc_rb_kernels[j] = k
+        assert len(dils) == c.voc_rb_ndil
+        for m, d in enumerate(dils):
+            c.voc_rb_dils[j][m] = d
+    c.voc_num_embeddings, c.voc_embedding_dim, c.voc_in_dim = v.num_embeddings, v.embedding_dim, v.model_in_dim
+    c.voc_dur_hidden, c.voc_dur_kernel = v.dur_hidden, v.dur_kernel
+    return c
+
+
+def remove_weight_norm(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """`model.remove_weight_norm()` at vocoder load (agent/tts/vocoder.py:45): w = v * (g / ||v||)."""
+    out = dict(sd)
+    for k in list(sd.keys()):
+        if k.endswith(".weight_g"):
+            base = k[: -len(".weight_g")]
+            g, v = sd[k].float(), sd[base + ".weight_v"].float()
+            norm = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+            out[base + ".weight"] = v * (g / norm)
+            del out[k], out[base + ".weight_v"]
+    return out
+
+
+class Engine:
+    """One model replica on one GPU.  Not thread-safe (one host thread per handle)."""
+
+    def __init__(self, cfg: ModelConfig, model_sd: Dict[str, torch.Tensor], vocoder_sd: Optional[Dict[str, torch.Tensor]] = None,
+                 gcmvn: Optional[dict] = None, device: int = 0, max_enc_frames: int = 1024, max_mt_positions: int = 1024):
+        if not torch.cuda.is_available():
+            raise EngineError("streamspeech_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.max_mt_positions = max_mt_positions
+        self._h = ctypes.c_void_p()
+        sc = make_ss_config(cfg, max_enc_frames, max_mt_positions)
+        rc = self.lib.ss_create(ctypes.byref(self._h), device, ctypes.byref(sc))
+        if rc != 0:
+            raise EngineError(f"ss_create failed with {rc}")
+        try:
+            for k, v in model_sd.items():
+                if v.is_floating_point():
+                    self._load(k, v)
+            if vocoder_sd is not None:
+                for k, v in remove_weight_norm(vocoder_sd).items():
+                    self._load("vocoder." + k, v)
+            self._load("__const__.mel_bank", constants.mel_bank())
+            self._load("__const__.window", constants.povey_window())
+            self._load("__const__.enc_pe", constants.rel_pos_table(max_enc_frames, cfg.enc_dim))
+            self._load("__const__.mt_pos_table", constants.sinusoidal_table(max_mt_positions + cfg.pad + 2, cfg.mt_dim, cfg.pad))
+            self._load("__const__.unit_pos_row", constants.sinusoidal_table(cfg.pad + 4, cfg.unit_dim, cfg.pad)[cfg.pad + 1])
+            if gcmvn is not None:
+                self._load("__const__.gcmvn_mean", torch.as_tensor(gcmvn["mean"], dtype=torch.float32))
+                self._load("__const__.gcmvn_std", torch.as_tensor(gcmvn["std"], dtype=torch.float32))
+            self._check(self.lib.ss_finalize(self._h))
+        except Exception:
+            self.close()
+            raise
+        self.hop = self.lib.ss_vocoder_hop(self._h)
+        self.vocoder_receptive_field = self.lib.ss_vocoder_receptive_field(self._h)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.ss_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(f"libstreamspeech_b200 error {rc}: {self.lib.ss_last_error(self._h).decode()}")
+
+    def _load(self, key: str, t: torch.Tensor):
+        t = t.detach().to(torch.float32).cpu().contiguous()
+        shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+        self._check(self.lib.ss_load_tensor(self._h, key.encode(), t.data_ptr(), t.dim(), shape))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _f32(self, *shape) -> torch.Tensor:
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else t.data_ptr()
+
+    def launch_count(self) -> int:
+        return int(self.lib.ss_launch_count(self._h))
+
+    def set_chunk(self, attn_chunk: Optional[int], conv_chunk: Optional[int] = None):
+        """encoder.chunk_size and the conv chunk sizes the agents poke (agent:395-413).  None = offline model."""
+        a = 0 if attn_chunk is None else int(attn_chunk)
+        if conv_chunk is None:
+            conv_chunk = 0 if attn_chunk is None else (16 if a >= 16 else 8)
+        self._check(self.lib.ss_set_chunk(self._h, a, int(conv_chunk)))
+
+    # ------------------------------------------------------------------ blocks
+    def num_fbank_frames(self, n_samples: int) -> int:
+        return int(self.lib.ss_fbank_num_frames(n_samples))
+
+    def encoder_out_frames(self, F: int) -> int:
+        return int(self.lib.ss_encoder_out_frames(F))
+
+    def fbank(self, samples: torch.Tensor, frame0: int = 0, n_frames: Optional[int] = None) -> torch.Tensor:
+        """samples: fp32 [n] on the engine's device (16 kHz, unscaled) -> [F, 80] features after global CMVN."""
+        assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()
+        F = self.num_fbank_frames(samples.numel())
+        if n_frames is None:
+            n_frames = F - frame0
+        out = self._f32(max(n_frames, 0), self.cfg.feat_dim)
+        if n_frames > 0:
+            self._check(self.lib.ss_fbank(self._h, self._stream(), samples.data_ptr(), samples.numel(), frame0, n_frames, out.data_ptr()))
+        return out
+
+    def encoder(self, feats: torch.Tensor, lengths: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """feats [B, F, 80] -> [B, T, enc_dim] (batch-major; the reference's encoder_out is the T x B x C transpose)."""
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous() and feats.dim() == 3
+        B, F, _ = feats.shape
+        T = self.encoder_out_frames(F)
+        out = self._f32(B, T, self.cfg.enc_dim)
+        lens = None
+        if lengths is not None:
+            lens = (ctypes.c_int32 * B)(*[int(x) for x in lengths])
+        self._check(self.lib.ss_encoder_forward(self._h, self._stream(), feats.data_ptr(), lens, B, F, out.data_ptr()))
+        return out
+
+    def ctc_greedy(self, head: int, enc: torch.Tensor):
+        """enc [T, enc_dim] of one utterance -> dict of device tensors (argmax, tokens, index, count)."""
+        assert enc.is_cuda and enc.is_contiguous() and enc.dim() == 2
+        T = enc.shape[0]
+        am = torch.empty(T, dtype=torch.int64, device=self.device)
+        toks = torch.empty(T, dtype=torch.int64, device=self.device)
+        idx = torch.empty(T, dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.ss_ctc_greedy(self._h, self._stream(), head, enc.data_ptr(), T, am.data_ptr(), toks.data_ptr(), idx.data_ptr(), cnt.data_ptr()))
+        return {"argmax": am, "tokens": toks, "index": idx, "count": cnt}
+
+    def mt_greedy(self, enc: torch.Tensor, prefix: Optional[Sequence[int]], max_new_tokens: int, max_len_b: int = 100) -> Tuple[List[int], torch.Tensor]:
+        """Returns (tokens without the trailing eos, decoder features of [eos]+tokens as [n+1, mt_dim])."""
+        assert enc.is_cuda and enc.is_contiguous() and enc.dim() == 2
+        prefix = list(prefix) if prefix is not None else []
+        cap = self.max_mt_positions
+        pfx = (ctypes.c_int64 * max(len(prefix), 1))(*prefix)
+        out = (ctypes.c_int64 * cap)()
+        n_out = ctypes.c_int32(0)
+        feats = self._f32(cap, self.cfg.mt_dim)
+        self._check(self.lib.ss_mt_greedy(self._h, self._stream(), enc.data_ptr(), enc.shape[0], pfx, len(prefix), int(max_new_tokens),
+                                          int(max_len_b), out, cap, ctypes.byref(n_out), feats.data_ptr()))
+        n = n_out.value
+        return [int(out[i]) for i in range(n)], feats[: n + 1]
+
+    def mt_features(self, enc: torch.Tensor, tokens: Sequence[int], want_logits: bool = False):
+        toks = (ctypes.c_int64 * len(tokens))(*[int(t) for t in tokens])
+        feats = self._f32(len(tokens), self.cfg.mt_dim)
+        logits = self._f32(self.cfg.tgt_vocab) if want_logits else None
+        self._check(self.lib.ss_mt_features(self._h, self._stream(), enc.data_ptr(), enc.shape[0], toks, len(tokens), feats.data_ptr(), self._ptr(logits)))
+        return (feats, logits) if want_logits else feats
+
+    def t2u_unit_decode(self, mt_feats: torch.Tensor, n_pad_tail: int = 0, mask_eos: bool = False, debug: bool = False):
+        assert mt_feats.is_cuda and mt_feats.is_contiguous() and mt_feats.dim() == 2
+        S = mt_feats.shape[0]
+        L = S * self.cfg.ctc_upsample_rate
+        am = torch.empty(L, dtype=torch.int64, device=self.device)
+        units = torch.empty(L, dtype=torch.int64, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        t2u = self._f32(S, self.cfg.unit_dim) if debug else None
+        logits = self._f32(L, self.cfg.unit_vocab) if debug else None
+        self._check(self.lib.ss_t2u_unit_decode(self._h, self._stream(), mt_feats.data_ptr(), S, n_pad_tail, int(mask_eos), am.data_ptr(),
+                                                units.data_ptr(), cnt.data_ptr(), self._ptr(t2u), self._ptr(logits)))
+        return {"argmax": am, "units": units, "count": cnt, "t2u_out": t2u, "logits": logits}
+
+    def vocoder_durations(self, codes: torch.Tensor, dur_prediction: bool = True):
+        assert codes.is_cuda and codes.dtype == torch.int64 and codes.is_contiguous()
+        U = codes.numel()
+        dur = torch.empty(U, dtype=torch.int64, device=self.device)
+        cum = torch.empty(U + 1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.ss_vocoder_durations(self._h, self._stream(), codes.data_ptr(), U, int(dur_prediction), dur.data_ptr(), cum.data_ptr()))
+        return dur, cum
+
+    def vocoder_generate(self, total_frames: int, frame0: int, n_frames: int, left_context: int = -1) -> torch.Tensor:
+        wav = self._f32(n_frames * self.hop)
+        self._check(self.lib.ss_vocoder_generate(self._h, self._stream(), total_frames, frame0, n_frames, left_context, wav.data_ptr()))
+        return wav
+
+    # single ops (parity tests)
+    def op_linear(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
+        M, K = x.shape
+        N = w.shape[0]
+        out = self._f32(M, N)
+        self._check(self.lib.ss_op_linear(self._h, self._stream(), x.data_ptr(), M, K, w.data_ptr(), self._ptr(b), N, act, out.data_ptr()))
+        return out
+
+    def op_layer_norm(self, x: torch.Tensor, g: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(x)
+        self._check(self.lib.ss_op_layer_norm(self._h, self._stream(), x.data_ptr(), x.shape[0], x.shape[1], g.data_ptr(), b.data_ptr(), out.data_ptr()))
+        return out

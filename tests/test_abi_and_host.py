@@ -1,0 +1,125 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/streamspeech_b200.h declares;
+host-side logic (dictionary, constants, SimulEval API mirror, synthetic checkpoint keys)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    from streamspeech_b200 import engine
+
+    if not os.path.exists(engine.LIB_PATH):
+        g.build()
+    lib = engine.load_library()
+    header = open(os.path.join(ROOT, "include", "streamspeech_b200.h")).read()
+    declared = set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(engine.EXPORTED_SYMBOLS), declared ^ set(engine.EXPORTED_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in lib.ss_version()
+    # pure host helpers need no GPU
+    assert lib.ss_fbank_num_frames(160000) == 998 and lib.ss_fbank_num_frames(239) == 0
+    assert lib.ss_encoder_out_frames(998) == 250 and lib.ss_encoder_out_frames(1498) == 375 and lib.ss_encoder_out_frames(1) == 1
+
+
+def test_engine_refuses_to_run_without_cuda():
+    from streamspeech_b200.config import ModelConfig
+    from streamspeech_b200.engine import Engine, EngineError
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(EngineError, match="no CPU fallback"):
+        Engine(ModelConfig(), {}, None, None)
+
+
+def test_ss_config_struct_layout_matches_header():
+    """ctypes mirror of `struct ss_config`: same field order and count as the header."""
+    from streamspeech_b200.engine import SSConfig
+
+    header = open(os.path.join(ROOT, "include", "streamspeech_b200.h")).read()
+    body = header[header.index("typedef struct ss_config {"):header.index("} ss_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\b([a-z_0-9]+)(?:\[[A-Z_]+\])*\s*[,;]", body)
+    assert names == [n for n, _ in SSConfig._fields_], (names, [n for n, _ in SSConfig._fields_])
+
+
+def test_constants_match_oracle_tables():
+    from oracle import streamspeech_oracle as so
+    from streamspeech_b200 import constants
+
+    assert torch.equal(constants.rel_pos_table(17, 256), so.rel_positional_encoding(17, 256))
+    assert torch.equal(constants.sinusoidal_table(40, 512, 1), so.sinusoidal_table(40, 512, 1))
+    assert torch.equal(constants.mel_bank()[:, :256], so._mel_banks())
+
+
+def test_dictionary_and_simuleval_mirror():
+    from streamspeech_b200.dictionary import Dictionary
+    from streamspeech_b200.simuleval_compat import (AgentStates, EmptySegment, ReadAction, SpeechSegment, SpeechToSpeechAgent,
+                                                    WriteAction)
+
+    d = Dictionary.units(1000)
+    assert len(d) == 1005 and d[4] == "0" and d[1003] == "999" and d.blank_index == 1004 and d[2] == "</s>"
+    s = Dictionary.synthetic(6000)
+    assert len(s) == 6000 and s[4].startswith("▁") and not s[5].startswith("▁")
+
+    class Echo(SpeechToSpeechAgent):
+        def policy(self):
+            if len(self.states.source) < 4:
+                return ReadAction()
+            return WriteAction(SpeechSegment(content=list(self.states.source), sample_rate=16000, finished=self.states.source_finished),
+                               finished=self.states.source_finished)
+
+    a = Echo(None)
+    assert a.pushpop(SpeechSegment(content=[0.1, 0.2], sample_rate=16000)).is_empty
+    out = a.pushpop(SpeechSegment(content=[0.3, 0.4], sample_rate=16000, finished=True))
+    assert out.content == [0.1, 0.2, 0.3, 0.4] and out.finished
+    st = AgentStates()
+    st.update_source(EmptySegment(finished=True))
+    assert st.source_finished and st.source == []
+
+
+def test_synthetic_checkpoint_keys_and_determinism():
+    from streamspeech_b200 import synth
+    from streamspeech_b200.config import ModelConfig
+
+    cfg = ModelConfig()
+    a, b = synth.make_model_state_dict(cfg, 0), synth.make_model_state_dict(cfg, 0)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert a["encoder.conformer_layers.11.conv_module.depthwise_conv.weight"].shape == (256, 1, 31)
+    assert a["decoder.embed_tokens.weight"].shape == (1005, 512)
+    assert ModelConfig.from_state_dict(a).enc_layers == 12 and ModelConfig.from_state_dict(a).unit_vocab == 1005
+    n_enc = sum(v.numel() for k, v in a.items() if k.startswith("encoder.") and "num_batches" not in k)
+    assert abs(n_enc - 33.45e6) < 0.1e6  # encoder ~33.45 M parameters
+
+
+def test_utterances_shard_across_ranks_gloo():
+    """N>1 path of bench.py: utterance ids are partitioned over ranks with no data-path collective."""
+    import torch.distributed as dist
+    import torch.multiprocessing as mp
+
+    mp.spawn(_shard_worker, args=(2,), nprocs=2, join=True)
+
+
+def _shard_worker(rank, world):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = "29533"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+
+    mine = bench.shard_utterances(7, rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    flat = sorted(x for g in gathered for x in g)
+    assert flat == list(range(7))
+    t = torch.tensor([float(len(mine))])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == 4.0
+    dist.destroy_process_group()

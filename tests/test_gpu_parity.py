@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the golden fixtures dumped from the real
+reference modules and against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): integer outputs (CTC / MT / unit tokens, durations) bit-exact;
+floating-point intermediates 2e-4 max-abs (fp32 kernels, different summation order than ATen);
+vocoder waveform 1e-3 max-abs.
+"""
+import argparse
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from streamspeech_b200 import synth  # noqa: E402
+from streamspeech_b200.config import ModelConfig, VocoderConfig  # noqa: E402
+
+torch.set_grad_enabled(False)
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+FP_TOL = 2e-4
+WAV_TOL = 1e-3
+
+
+def report(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **{k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in kw.items()}}) + "\n")
+
+
+def maxdiff(a, b):
+    a = a.detach().float().cpu() if torch.is_tensor(a) else torch.as_tensor(a)
+    b = b.detach().float().cpu() if torch.is_tensor(b) else torch.as_tensor(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max())
+
+
+def golden_cfg():
+    cfg = ModelConfig()
+    cfg.enc_layers = 3
+    return cfg
+
+
+@pytest.fixture(scope="module")
+def eng3():
+    from streamspeech_b200.engine import Engine
+
+    cfg = golden_cfg()
+    e = Engine(cfg, synth.make_model_state_dict(cfg, 0), synth.make_vocoder_state_dict(cfg.vocoder, 1, weight_norm=True), None)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def full():
+    """12-layer engine + oracle on the same synthetic checkpoint."""
+    from oracle.streamspeech_oracle import StreamSpeechOracle
+    from streamspeech_b200.engine import Engine
+
+    cfg = ModelConfig()
+    sd = synth.make_model_state_dict(cfg, 0)
+    vsd = synth.make_vocoder_state_dict(cfg.vocoder, 1)
+    gc = synth.make_gcmvn(cfg)
+    e = Engine(cfg, sd, vsd, gc)
+    o = StreamSpeechOracle(cfg, sd, vsd, gc, chunk_size=8)
+    yield cfg, e, o
+    e.close()
+
+
+def cuda(x):
+    return torch.as_tensor(x).cuda().contiguous()
+
+
+# --------------------------------------------------------------------------------------------- single ops
+def test_linear_and_layernorm_ops(eng3):
+    g = torch.Generator().manual_seed(0)
+    worst = 0.0
+    for (M, K, N, act) in [(1, 256, 2048, 2), (7, 2048, 256, 0), (250, 256, 768, 0), (33, 512, 6000, 0), (1000, 128, 1, 0), (129, 512, 1005, 1)]:
+        x = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g)
+        ref = torch.nn.functional.linear(x, w, b)
+        ref = {0: ref, 1: torch.relu(ref), 2: torch.nn.functional.silu(ref)}[act]
+        got = eng3.op_linear(cuda(x), cuda(w), cuda(b), act)
+        d = maxdiff(got, ref)
+        worst = max(worst, d)
+        assert d < 1e-4, (M, K, N, act, d)
+    for C in (128, 256, 512):
+        x = torch.randn(37, C, generator=g) * 3 + 1
+        gam, bet = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        ref = torch.nn.functional.layer_norm(x, (C,), gam, bet, 1e-5)
+        d = maxdiff(eng3.op_layer_norm(cuda(x), cuda(gam), cuda(bet)), ref)
+        worst = max(worst, d)
+        assert d < 2e-5, (C, d)
+    report("ops", worst=worst)
+
+
+# --------------------------------------------------------------------------------------------- fbank
+def test_fbank_matches_torchaudio_fixture(eng3, gold):
+    g = gold["fbank"]
+    wav = cuda(g["wav"])
+    got = eng3.fbank(wav)  # engine built without gcmvn -> raw log-mel
+    assert got.shape == g["fbank"].shape
+    d = maxdiff(got, g["fbank"])
+    report("fbank", maxdiff=d)
+    assert d < 2e-3, d  # log-mel of a 2^15-scaled signal (values ~10-20); fp32 FFT ordering differs from pocketfft
+    # frame caching: any sub-range equals the same rows
+    part = eng3.fbank(wav, 10, 25)
+    assert torch.equal(part, got[10:35])
+    # ragged / empty inputs
+    assert eng3.fbank(wav[:239]).shape[0] == 0 and eng3.fbank(wav[:400]).shape[0] == 1
+
+
+def test_fbank_cmvn_vs_oracle(full):
+    from oracle.streamspeech_oracle import online_features
+
+    cfg, e, o = full
+    wav = synth.make_audio(3.1, seed=5)
+    ref = online_features(wav, o.gcmvn)
+    got = e.fbank(cuda(wav))
+    d = maxdiff(got, ref)
+    report("fbank_cmvn", maxdiff=d)
+    assert d < 2e-3, d
+
+
+# --------------------------------------------------------------------------------------------- encoder
+@pytest.mark.parametrize("chunk,conv", [(4, 8), (8, 8), (16, 16), (None, None)])
+def test_encoder_golden(eng3, gold, chunk, conv):
+    g = gold["encoder"]
+    eng3.set_chunk(chunk, conv)
+    feats = cuda(g["feats"]).unsqueeze(0)
+    out = eng3.encoder(feats)[0]
+    d = maxdiff(out, g[f"out_c{chunk}"])
+    report(f"encoder_c{chunk}", maxdiff=d)
+    assert d < FP_TOL, d
+
+
+def test_encoder_batched_padded(eng3, gold):
+    g = gold["encoder"]
+    eng3.set_chunk(8, 8)
+    feats = torch.zeros(2, g["feats"].shape[0], 80)
+    feats[0] = torch.from_numpy(g["feats"])
+    feats[1, :150] = torch.from_numpy(g["feats"][:150])
+    out = eng3.encoder(cuda(feats), lengths=g["batched_lens"].tolist())
+    ref = torch.from_numpy(g["batched_out"]).transpose(0, 1)  # T x B x C -> B x T x C
+    d = maxdiff(out, ref)
+    report("encoder_batched", maxdiff=d)
+    assert d < FP_TOL, d
+
+
+def test_encoder_streaming_prefix_invariance(full):
+    """Size-independent property: every frame of a *completed* chunk is final, i.e. the encoder output
+    on a longer prefix agrees with the shorter prefix on all chunks but the last one."""
+    cfg, e, o = full
+    e.set_chunk(8, 8)
+    feats = e.fbank(cuda(synth.make_audio(10.0, seed=21)))
+    F = feats.shape[0]
+    a = e.encoder(feats[: F - 64].unsqueeze(0).contiguous())[0]
+    b = e.encoder(feats.unsqueeze(0).contiguous())[0]
+    Ta = a.shape[0]
+    stable = (Ta // 8 - 1) * 8
+    d = maxdiff(a[:stable], b[:stable])
+    report("encoder_prefix_invariance", maxdiff=d, frames=stable)
+    assert d < 1e-4, d
+
+
+def test_encoder_full_size_vs_oracle(full):
+    cfg, e, o = full
+    from oracle.streamspeech_oracle import online_features
+
+    o.set_chunk(8)
+    e.set_chunk(8)
+    wav = synth.make_audio(10.0, seed=1234)
+    ref_f = online_features(wav, o.gcmvn)
+    ref = o.encoder(ref_f.unsqueeze(0), torch.tensor([ref_f.size(0)]))["encoder_out"][0][:, 0]
+    got = e.encoder(cuda(ref_f).unsqueeze(0))[0]
+    d = maxdiff(got, ref)
+    report("encoder_12L_10s", maxdiff=d)
+    assert d < 5e-4, d
+    for head, name in ((0, "source_unigram"), (1, "ctc_target_unigram")):
+        r = e.ctc_greedy(head, got)
+        h = o.ctc_greedy(name, ref.unsqueeze(1))[0]
+        n = int(r["count"].item())
+        assert r["argmax"].tolist() == h["org_tokens"], name
+        assert r["tokens"][:n].tolist() == h["tokens"] and r["index"][:n].tolist() == h["index"], name
+
+
+# --------------------------------------------------------------------------------------------- decoders
+def test_ctc_heads_golden(eng3, gold):
+    g = gold["decoders"]
+    enc = cuda(g["enc_out"])
+    for head, name in ((0, "source_unigram"), (1, "ctc_target_unigram")):
+        r = eng3.ctc_greedy(head, enc)
+        n = int(r["count"].item())
+        assert r["argmax"].cpu().numpy().tolist() == g[f"ctc_{name}_argmax"].tolist()
+        assert r["tokens"][:n].tolist() == g[f"ctc_{name}_tokens"].tolist()
+        assert r["index"][:n].tolist() == g[f"ctc_{name}_index"].tolist()
+
+
+def test_mt_decoder_golden(eng3, gold):
+    g = gold["decoders"]
+    enc = cuda(g["enc_out"])
+    feats, logits = eng3.mt_features(enc, g["mt_tokens"][0].tolist(), want_logits=True)
+    d1, d2 = maxdiff(feats, g["mt_feats"]), maxdiff(logits, g["mt_logits_last"])
+    fp = eng3.mt_features(enc, g["mt_tokens_pad"][0].tolist())
+    d3 = maxdiff(fp, g["mt_feats_pad"])
+    report("mt_decoder", feats=d1, logits=d2, feats_pad=d3)
+    assert d1 < FP_TOL and d2 < FP_TOL and d3 < FP_TOL, (d1, d2, d3)
+
+
+def test_t2u_unit_decoder_golden(eng3, gold):
+    g = gold["decoders"]
+    r = eng3.t2u_unit_decode(cuda(g["mt_feats"]), debug=True)
+    d1 = maxdiff(r["t2u_out"], g["t2u_out"])
+    d2 = maxdiff(r["logits"][:4], g["unit_logits_first"])
+    report("t2u_unit", t2u=d1, logits=d2)
+    assert d1 < FP_TOL and d2 < 5e-4, (d1, d2)
+    assert r["argmax"].tolist() == g["unit_argmax"].tolist()
+    n = int(r["count"].item())
+    assert r["units"][:n].tolist() == g["unit_tokens"].tolist()
+    rp = eng3.t2u_unit_decode(cuda(g["mt_feats_pad"]), n_pad_tail=1)
+    assert rp["argmax"].tolist() == g["unit_argmax_pad"].tolist()
+
+
+def test_mt_greedy_vs_oracle(full):
+    cfg, e, o = full
+    from oracle.streamspeech_oracle import online_features
+
+    o.set_chunk(8)
+    e.set_chunk(8)
+    f = online_features(synth.make_audio(4.0, seed=9), o.gcmvn)
+    eo = o.encoder(f.unsqueeze(0), torch.tensor([f.size(0)]))["encoder_out"][0]
+    enc = cuda(eo[:, 0])
+    for prefix, new in ((None, 3), ([17, 256, 4099], 2), ([17, 256, 4099], 0), (None, -1)):
+        ref = o.mt_greedy(eo, prefix, new)
+        toks, feats = e.mt_greedy(enc, prefix, new)
+        assert toks == ref[:-1], (prefix, new, toks, ref)
+        rf = o.mt_features(torch.tensor([[cfg.eos] + toks]), eo)[0]
+        d = maxdiff(feats, rf)
+        assert d < FP_TOL, d
+
+
+# --------------------------------------------------------------------------------------------- vocoder
+def test_vocoder_golden(eng3, gold):
+    g = gold["vocoder"]
+    codes = cuda(g["code"][0].astype(np.int64))
+    dur, cum = eng3.vocoder_durations(codes, True)
+    assert dur.tolist() == g["dur"][0].tolist()
+    total = int(cum[-1].item())
+    wav = eng3.vocoder_generate(total, 0, total, 0)
+    d = maxdiff(wav, g["wav"])
+    report("vocoder", maxdiff=d, samples=wav.numel())
+    assert wav.numel() == g["wav"].shape[0] and d < WAV_TOL, d
+    # tail generation with the receptive field as left context == the same samples of the full pass
+    tail = 17
+    part = eng3.vocoder_generate(total, total - tail, tail, -1)
+    d2 = maxdiff(part, wav[-tail * eng3.hop:])
+    report("vocoder_incremental", maxdiff=d2, receptive_field=eng3.vocoder_receptive_field)
+    assert d2 < 1e-5, d2
+    # no duration prediction: one frame per code
+    dur1, cum1 = eng3.vocoder_durations(codes, False)
+    assert dur1.tolist() == [1] * codes.numel() and int(cum1[-1].item()) == codes.numel()
+
+
+# --------------------------------------------------------------------------------------------- end to end
+def agent_args(**kw):
+    d = dict(model_path="synthetic", data_bin=".", config_yaml=None, multitask_config_yaml=None, global_stats=None,
+             tgt_splitter_type="SentencePiece", tgt_splitter_path=None, user_dir="", agent_dir="", max_len=200, force_finish=False,
+             shift_size=10, window_size=25, sample_rate=16000, feature_dim=80, vocoder="synthetic", vocoder_cfg=None,
+             dur_prediction=True, lagging_k1=0, lagging_k2=0, segment_size=320, stride_n=1, stride_n2=1, unit_per_subword=15,
+             extra_output_dir=None, output_asr_translation=False, source_segment_size=320, vocoder_context="receptive-field",
+             device_index=0, device="gpu")
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+@pytest.mark.parametrize("seconds,seed", [(4.0, 1234), (6.4, 77)])
+def test_streaming_s2st_agent_vs_oracle(seconds, seed):
+    """Config 2 shape (chunk 320 ms, batch 1): every policy() call must reproduce the oracle agent's action,
+    token sequences bit-exactly and the emitted waveform within 1e-3."""
+    from oracle.agent_oracle import OracleS2STAgent
+    from oracle.streamspeech_oracle import StreamSpeechOracle
+    from streamspeech_b200.agent import StreamSpeechS2STAgent
+    from streamspeech_b200.simuleval_compat import SpeechSegment
+
+    cfg = ModelConfig()
+    o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), synth.make_vocoder_state_dict(cfg.vocoder, 1), synth.make_gcmvn(cfg))
+    ref = OracleS2STAgent(o, 320)
+    agent = StreamSpeechS2STAgent(agent_args())
+    wav = synth.make_audio(seconds, seed=seed)
+    n = 5120
+    worst, writes = 0.0, 0
+    for i in range(0, len(wav), n):
+        fin = i + n >= len(wav)
+        chunk = wav[i:i + n].tolist()
+        ref.push(chunk, finished=fin)
+        a_ref = ref.policy()
+        seg = agent.pushpop(SpeechSegment(content=chunk, sample_rate=16000, finished=fin))
+        for k in ("asr_tokens", "st_tokens", "new_subword_tokens", "mt_tokens", "units", "dur"):
+            assert agent.trace.get(k) == a_ref.trace.get(k), (i // n, k, agent.trace.get(k), a_ref.trace.get(k))
+        if a_ref.kind == "read":
+            assert seg.is_empty, i // n
+        else:
+            assert not seg.is_empty and len(seg.content) == len(a_ref.wav), (i // n, len(seg.content), len(a_ref.wav))
+            assert seg.finished == a_ref.seg_finished
+            if len(a_ref.wav):
+                worst = max(worst, float(np.abs(np.array(seg.content) - np.array(a_ref.wav)).max()))
+                writes += 1
+    report("s2st_streaming", seconds=seconds, wav_maxdiff=worst, writes=writes)
+    assert writes >= 2 and worst < WAV_TOL, (writes, worst)
+    agent.engine.close()
+
+
+def test_streaming_asr_agent_vs_oracle():
+    from oracle.agent_oracle import OracleASRAgent
+    from oracle.streamspeech_oracle import StreamSpeechOracle
+    from streamspeech_b200.agent import StreamSpeechASRAgent
+    from streamspeech_b200.simuleval_compat import SpeechSegment
+
+    cfg = ModelConfig()
+    o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), None, synth.make_gcmvn(cfg))
+    ref = OracleASRAgent(o, 160)
+    agent = StreamSpeechASRAgent(agent_args(source_segment_size=160))
+    wav = synth.make_audio(3.0, seed=3)
+    n = 2560
+    for i in range(0, len(wav), n):
+        fin = i + n >= len(wav)
+        chunk = wav[i:i + n].tolist()
+        ref.push(chunk, finished=fin)
+        a_ref = ref.policy()
+        agent.pushpop(SpeechSegment(content=chunk, sample_rate=16000, finished=fin))
+        if a_ref.kind == "write":
+            assert agent.trace["asr_tokens"] == a_ref.trace["asr_tokens"], i // n
+    agent.engine.close()
+
+
+def test_missing_weight_fails_loudly():
+    from streamspeech_b200.engine import Engine, EngineError
+
+    cfg = golden_cfg()
+    sd = synth.make_model_state_dict(cfg, 0)
+    del sd["encoder.conformer_layers.1.ffn2.w_2.weight"]
+    with pytest.raises(EngineError, match="ffn2.w_2.weight"):
+        Engine(cfg, sd, None, None)
