@@ -4,6 +4,8 @@
 // Why fp32 CUDA cores here: the parity bar is bit-exact arg-max tokens against the reference's fp32
 // CPU path (BASELINE.json north_star); every GEMM on the path feeds an arg-max within a few layers.
 // This kernel is the exact-precision baseline; the tcgen05 path (kernels_umma.cu) is opt-in per GEMM.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -52,8 +54,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// gridDim.z > 1: split-K.  Slice z accumulates k-tiles [z*tiles_per_split, (z+1)*tiles_per_split) and stores the raw
+// partial sums to ws[z][M][N]; splitk_epilogue_kernel then reduces the slices in a fixed order and applies the epilogue.
 template <int BM, int BN, bool CONV>
-__global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restrict__ W, int M, int N, int K, Epilogue ep) {
+__global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restrict__ W, int M, int N, int K, Epilogue ep,
+                                                  int tiles_per_split, float* __restrict__ ws) {
   constexpr int TM = BM / 16;
   constexpr int TN = BN / 16;
   constexpr int A_F4 = BM * BK / 4;  // float4 loads per A tile
@@ -114,13 +119,15 @@ __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restri
     }
   };
 
-  const int nk = (K + BK - 1) / BK;
-  gload(0);
+  const int nk_all = (K + BK - 1) / BK;
+  const int kt0 = blockIdx.z * tiles_per_split;
+  const int nk = min(nk_all, kt0 + tiles_per_split) - kt0;
+  gload(kt0 * BK);
   sstore(0);
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < nk) gload((kt + 1) * BK);
+    if (kt + 1 < nk) gload((kt0 + kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float av[TM], bv[TN];
@@ -139,6 +146,20 @@ __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restri
     }
   }
 
+  if (ws != nullptr) {  // split-K: raw partial sums
+    float* wz = ws + (int64_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      int m = m0 + ty * TM + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int n = n0 + tx * TN + j;
+        if (n < N) wz[(int64_t)m * N + n] = acc[i][j];
+      }
+    }
+    return;
+  }
   // ---- epilogue
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -182,13 +203,81 @@ __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restri
   }
 }
 
+__global__ void splitk_epilogue_kernel(const float* __restrict__ ws, int splits, int M, int N, int L_rows, Epilogue ep) {
+  const int ncols = ep.glu ? N / 2 : N;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * ncols) return;
+  int m = idx / ncols, oc = idx - m * ncols;
+  int64_t orow = m;
+  if (ep.out_L > 0) {
+    int b = m / L_rows;
+    int t = m - b * L_rows;
+    orow = (int64_t)b * ep.out_L + (int64_t)t * ep.out_row_stride + ep.out_row_offset;
+  }
+  float y;
+  if (ep.glu) {
+    int n = 2 * oc;
+    float av_ = 0.f, gv = 0.f;
+    for (int z = 0; z < splits; ++z) {
+      const float* p = ws + ((int64_t)z * M + m) * N + n;
+      av_ += p[0];
+      gv += p[1];
+    }
+    if (ep.bias) {
+      av_ += ep.bias[n];
+      gv += ep.bias[n + 1];
+    }
+    y = ep.alpha * (av_ * (1.0f / (1.0f + expf(-gv))));
+  } else {
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += ws[((int64_t)z * M + m) * N + oc];
+    if (ep.bias) acc += ep.bias[oc];
+    y = ep.alpha * apply_act(acc, ep.act);
+  }
+  float* op = ep.out + orow * ep.ldo + oc;
+  if (ep.residual) y += ep.res_scale * ep.residual[orow * ep.ldo + oc];
+  if (ep.accumulate) y += *op;
+  *op = y;
+}
+
+// scratch for split-K partial sums (one per process; all launches of a handle are stream-ordered)
+float* g_splitk_ws = nullptr;
+size_t g_splitk_cap = 0;
+constexpr size_t SPLITK_WS_BYTES = 32u << 20;
+
 template <int BM, int BN>
 void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue& ep, bool conv, cudaStream_t st) {
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  const long ctas = (long)grid.x * grid.y;
+  const int nk = (K + BK - 1) / BK;
+  int splits = 1;
+  if (ctas < 96 && nk >= 8) {
+    splits = (int)std::min<long>((148 + ctas - 1) / ctas, nk / 4);  // >= 4 k-tiles (64 columns) per slice
+    if ((size_t)splits * M * N * sizeof(float) > SPLITK_WS_BYTES) splits = 1;
+  }
+  float* ws = nullptr;
+  int tiles = nk;
+  if (splits > 1) {
+    if (!g_splitk_ws) {
+      if (cudaMalloc((void**)&g_splitk_ws, SPLITK_WS_BYTES) != cudaSuccess) { g_splitk_ws = nullptr; splits = 1; }
+      else g_splitk_cap = SPLITK_WS_BYTES;
+    }
+  }
+  if (splits > 1) {
+    tiles = (nk + splits - 1) / splits;
+    splits = (nk + tiles - 1) / tiles;
+    grid.z = splits;
+    ws = g_splitk_ws;
+  }
   if (conv)
-    gemm_kernel<BM, BN, true><<<grid, NT, 0, st>>>(a, W, M, N, K, ep);
+    gemm_kernel<BM, BN, true><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);
   else
-    gemm_kernel<BM, BN, false><<<grid, NT, 0, st>>>(a, W, M, N, K, ep);
+    gemm_kernel<BM, BN, false><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);
+  if (splits > 1) {
+    ++g_launches;
+    int total = M * (ep.glu ? N / 2 : N);
+    splitk_epilogue_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, splits, M, N, a.L_rows, ep);
+  }
 }
 
 }  // namespace

