@@ -40,12 +40,12 @@ def shard_utterances(n_utts: int, rank: int, world: int):
     return [i for i in range(n_utts) if i % world == rank]
 
 
-def agent_args(device_index=0):
+def agent_args(device_index=0, encoder_mode="cached"):
     return argparse.Namespace(model_path="synthetic", vocoder="synthetic", vocoder_cfg=None, data_bin=".", config_yaml=None,
                               multitask_config_yaml=None, sample_rate=SAMPLE_RATE, max_len=200, force_finish=False,
                               dur_prediction=True, lagging_k1=0, lagging_k2=0, segment_size=CHUNK_MS, stride_n=1, stride_n2=1,
                               unit_per_subword=15, source_segment_size=CHUNK_MS, vocoder_context="receptive-field",
-                              device_index=device_index)
+                              device_index=device_index, encoder_mode=encoder_mode)
 
 
 class ClockSampler:
@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--encoder-mode", type=str, default="cached", choices=["cached", "recompute"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -188,7 +189,7 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    agent = StreamSpeechS2STAgent(agent_args(local))
+    agent = StreamSpeechS2STAgent(agent_args(local, args.encoder_mode))
     eng = agent.engine
     if world > 1:
         # the one collective of the path: initial weight broadcast over NVLink.  Every rank built the
@@ -271,7 +272,7 @@ def main():
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic 16 kHz audio + seeded random-init weights of the StreamSpeech architecture (calibrated token rates, see DESIGN.md)",
             "config": {"workload": WORKLOAD, "utterance_s": UTT_SECONDS, "chunk_ms": CHUNK_MS, "policy_calls_per_step": int(UTT_SECONDS * 1000 // CHUNK_MS) + 1,
-                       "l2": "256 MiB flush between timed steps", "parallelism": f"utterance-sharded x{world}",
+                       "l2": "256 MiB flush between timed steps", "encoder_mode": args.encoder_mode, "parallelism": f"utterance-sharded x{world}",
                        "output_audio_s_per_step": out_res / args.steps / SAMPLE_RATE},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(UTT_SECONDS * SAMPLE_RATE * 4),
                     "d2h_bytes_per_step": int(out_e2e / args.steps * 4), "ms_per_step": ms_e2e / args.steps},

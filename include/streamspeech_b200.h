@@ -88,6 +88,16 @@ int64_t ss_encoder_out_frames(int64_t n_fbank_frames);
 int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const int32_t* lengths_host, int B, int F,
                        float* out_dev);
 
+/* Streaming form of the same encoder for ONE utterance per handle (what the reference agent recomputes from sample 0
+ * on every policy() call, agent:433): frames of completed chunk groups are final, so only the rows
+ * [T_final_prev, T) are computed; per-layer K/V and conv-module inputs of the final rows are cached in the handle.
+ * feats_dev [F][feat_dim] = ALL fbank frames so far; enc_out_dev = caller-owned persistent buffer [>= T][enc_dim]
+ * whose rows < T_final_prev are left untouched.  *T_out = ss_encoder_out_frames(F); *T_final_out = rows now final.
+ * Requires attn_chunk > 0.  enqueue only */
+int ss_encoder_stream_reset(ss_engine* h);
+int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, int F, float* enc_out_dev, int32_t* T_out,
+                           int32_t* T_final_out);
+
 /* ---- C1: CTCDecoder.generate (agent/ctc_decoder.py:40-111): Linear -> log_softmax -> mask pad,unk -> argmax -> collapse.
  * head 0 = source_unigram (ASR), 1 = ctc_target_unigram (ST).  enc_dev [rows][enc_dim] of ONE utterance.
  * argmax_dev[rows] int64; tokens_dev[rows] int64 / index_dev[rows] int32 hold *count_dev collapsed entries. enqueue only */

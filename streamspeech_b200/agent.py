@@ -117,6 +117,16 @@ class _EngineAgentMixin:
         self.feat_cache = torch.zeros(6000, cfg.feat_dim, dtype=torch.float32, device=self.torch_device)
         self.n_feat = 0
         self._resident = None
+        self.encoder_mode = getattr(args, "encoder_mode", "cached")
+        self.enc_buf = torch.zeros(getattr(args, "max_enc_frames", 1024), cfg.enc_dim, dtype=torch.float32, device=self.torch_device)
+
+    def _encode(self, feature: torch.Tensor) -> torch.Tensor:
+        """forward_encoder (agent:433).  "cached": only the rows of the not yet final chunk group are recomputed
+        (ss_encoder_stream_step); "recompute": the whole prefix every call, like the reference."""
+        if self.encoder_mode == "recompute":
+            return self.engine.encoder(feature.unsqueeze(0))[0]
+        T, _ = self.engine.encoder_stream_step(feature, self.enc_buf)
+        return self.enc_buf[:T]
 
     def step_resident(self, audio_dev: torch.Tensor, n_valid: int, finished: bool):
         """Device-resident variant of pushpop(): the first `n_valid` samples of `audio_dev` (fp32, on the engine's
@@ -135,6 +145,7 @@ class _EngineAgentMixin:
         if hasattr(self, "audio"):
             self.audio.n = 0
             self.n_feat = 0
+            self.engine.encoder_stream_reset()
 
     def _features(self):
         """OnlineFeatureExtractor.__call__ (agent:66-87) with a per-frame cache."""
@@ -214,6 +225,7 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
         parser.add_argument("--output-asr-translation", type=bool, default=False)
         parser.add_argument("--vocoder-context", type=str, default="receptive-field", choices=["receptive-field", "full"])
         parser.add_argument("--device-index", type=int, default=0)
+        parser.add_argument("--encoder-mode", type=str, default="cached", choices=["cached", "recompute"])
 
     def reset(self):  # agent:328-347
         self.src_seg_num = 0
@@ -251,7 +263,7 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
         feature = self._features()
         if feature.size(0) == 0 and not self.states.source_finished:
             return READ
-        enc = eng.encoder(feature.unsqueeze(0))[0]  # [T, 256]
+        enc = self._encode(feature)  # [T, 256]
         self.encoder_out = enc
         src_ctc_indices, _ = self._ctc(0, enc)
         tgt_ctc_indices, _ = self._ctc(1, enc)
@@ -379,7 +391,7 @@ class StreamSpeechASRAgent(_EngineAgentMixin, SpeechToTextAgent):
         feature = self._features()
         if feature.size(0) == 0 and not self.states.source_finished:
             return ReadAction()
-        enc = self.engine.encoder(feature.unsqueeze(0))[0]
+        enc = self._encode(feature)
         toks, _ = self._ctc(0, enc)
         self.trace = {"asr_tokens": toks}
         text = " ".join(self.dict["source_unigram"][t] for t in toks)  # :419-425

@@ -138,6 +138,11 @@ struct ss_engine {
   float* voc_unit_emb = nullptr;  // [Ucap][emb]
   int* voc_cumsum = nullptr;      // [Ucap+1]
   int voc_ucap = 0, voc_U = 0;
+  // streaming encoder state (one utterance per handle)
+  int st_T_final = 0;
+  float* st_k = nullptr;    // [enc_layers][Tpos][enc_dim]
+  float* st_v = nullptr;
+  float* st_glu = nullptr;  // conv-module GLU outputs (depthwise-conv inputs)
   int* lengths_dev = nullptr;     // [Bcap]
   int lengths_cap = 0;
 

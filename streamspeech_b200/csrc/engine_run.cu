@@ -219,7 +219,8 @@ int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const
     // x = x + self_attn(LN(x))
     layer_norm(x, D, y, D, L.attn_ln.g, L.attn_ln.b, (int)rows, D, st);
     linear(y, D, (int)rows, L.qkv, ep_out(qkv, 3 * D), st);
-    relpos_attention(qkv, L.pos_proj, h->Tpos, L.pos_u, L.pos_v, att, B, T, c.enc_heads, D, h->attn_chunk, len_dev, st);
+    relpos_attention(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, L.pos_proj, h->Tpos, L.pos_u, L.pos_v, att, B, T, 0, T, c.enc_heads, D,
+                     h->attn_chunk, len_dev, st);
     linear(att, D, (int)rows, L.attn_out, ep_residual(x, D), st);
     // x = x + conv_module(x)
     layer_norm(x, D, y, D, L.conv_ln.g, L.conv_ln.b, (int)rows, D, st);
@@ -228,7 +229,7 @@ int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const
       ep.glu = 1;
       linear(y, D, (int)rows, L.pw1, ep, st);
     }
-    depthwise_bn_silu(glu, D, L.dw_w, L.bn_scale, L.bn_shift, dw, D, B, T, D, c.dw_kernel, cc, nullptr, st);
+    depthwise_bn_silu(glu, D, L.dw_w, L.bn_scale, L.bn_shift, dw, D, B, T, 0, T, D, c.dw_kernel, cc, st);
     linear(dw, D, (int)rows, L.pw2, ep_residual(x, D), st);
     // x = LN(x + 0.5 * ffn2(x))
     layer_norm(x, D, y, D, L.ffn2_ln.g, L.ffn2_ln.b, (int)rows, D, st);
@@ -237,6 +238,97 @@ int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const
     layer_norm(x, D, x, D, L.final_ln.g, L.final_ln.b, (int)rows, D, st);
   }
   return check_launch(h, "ss_encoder_forward");
+}
+
+int ss_encoder_stream_reset(ss_engine* h) {
+  if (!h) return SS_ERR_INVALID;
+  h->st_T_final = 0;
+  return SS_OK;
+}
+
+int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, int F, float* enc_out_dev, int32_t* T_out, int32_t* T_final_out) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (h->attn_chunk <= 0 || h->conv_chunk <= 0) return h->fail(SS_ERR_STATE, "streaming encoder needs a chunked model (ss_set_chunk)");
+  const ss_config& c = h->cfg;
+  cudaStream_t st = S(stream);
+  const int D = c.enc_dim;
+  if (F <= 0) {
+    if (T_out) *T_out = 0;
+    if (T_final_out) *T_final_out = h->st_T_final;
+    return SS_OK;
+  }
+  const int T1 = (F - 1) / 2 + 1, T = (T1 - 1) / 2 + 1;
+  if (T > h->Tpos) return h->fail(SS_ERR_CAPACITY, "encoder sequence longer than max_enc_frames");
+  const int G = std::max(h->attn_chunk, h->conv_chunk);  // rows of a group are final once 4*G*(i+1) fbank frames exist
+  const int a0 = std::min(h->st_T_final, T);
+  const int nA = T - a0;
+  if (T_out) *T_out = T;
+  const int cc = h->conv_chunk;
+  if (nA > 0) {
+    const int t1_lo = std::max(0, 2 * a0 - (c.conv_kernel / 2));
+    const int n1 = T1 - t1_lo;
+    size_t need = ((size_t)n1 * (c.conv_channels / 2) + (size_t)nA * (size_t)(6 * D + c.enc_ffn) + 4096) * sizeof(float) + 16 * 256;
+    if (!ws_begin(h, need)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+    float* c1 = h->ws.f32((size_t)n1 * (c.conv_channels / 2));
+    float* x0 = h->ws.f32((size_t)nA * D);
+    float* y = h->ws.f32((size_t)nA * D);
+    float* hid = h->ws.f32((size_t)nA * c.enc_ffn);
+    float* qb = h->ws.f32((size_t)nA * D);
+    float* att = h->ws.f32((size_t)nA * D);
+    float* dw = h->ws.f32((size_t)nA * D);
+    if (!c1 || !x0 || !y || !hid || !qb || !att || !dw) return h->fail(SS_ERR_CUDA, "workspace too small");
+    float* x = enc_out_dev + (size_t)a0 * D;
+    {
+      ConvA a;
+      a.x = feats_dev; a.B = 1; a.L_in = F; a.L_rows = n1; a.C_in = c.feat_dim; a.ldx = c.feat_dim;
+      a.ksize = c.conv_kernel; a.stride = 2; a.pad_left = c.conv_kernel / 2; a.chunk = cc; a.t_offset = t1_lo;
+      Epilogue ep = ep_out(c1, c.conv_channels / 2);
+      ep.bias = h->sub_conv[0].b; ep.glu = 1;
+      gemm_conv(a, h->sub_conv[0].w, h->sub_conv[0].N, ep, st);
+      ConvA a2;
+      a2.x = c1; a2.B = 1; a2.L_in = T1; a2.L_rows = nA; a2.C_in = c.conv_channels / 2; a2.ldx = c.conv_channels / 2;
+      a2.ksize = c.conv_kernel; a2.stride = 2; a2.pad_left = c.conv_kernel / 2; a2.chunk = cc;
+      a2.t_offset = a0; a2.x_row0 = t1_lo; a2.x_rows = n1;
+      Epilogue ep2 = ep_out(x0, D);
+      ep2.bias = h->sub_conv[1].b; ep2.glu = 1; ep2.alpha = sqrtf((float)D);
+      gemm_conv(a2, h->sub_conv[1].w, h->sub_conv[1].N, ep2, st);
+    }
+    linear(x0, D, nA, h->enc_linear, ep_out(x, D), st);
+    for (int i = 0; i < c.enc_layers; ++i) {
+      const ConformerLayerW& L = h->enc[i];
+      float* kc = h->st_k + (size_t)i * h->Tpos * D;
+      float* vc = h->st_v + (size_t)i * h->Tpos * D;
+      float* gc = h->st_glu + (size_t)i * h->Tpos * D;
+      layer_norm(x, D, y, D, L.ffn1_ln.g, L.ffn1_ln.b, nA, D, st);
+      linear(y, D, nA, L.ffn1_w1, ep_out(hid, c.enc_ffn, ACT_SILU), st);
+      linear(hid, c.enc_ffn, nA, L.ffn1_w2, ep_residual(x, D, 0.5f), st);
+      layer_norm(x, D, y, D, L.attn_ln.g, L.attn_ln.b, nA, D, st);
+      Linear lq = L.qkv, lk = L.qkv, lv = L.qkv;  // row slices of the fused [3D][D] projection
+      lq.N = lk.N = lv.N = D;
+      lk.w += (size_t)D * D; lk.b += D;
+      lv.w += (size_t)2 * D * D; lv.b += 2 * D;
+      linear(y, D, nA, lq, ep_out(qb, D), st);
+      linear(y, D, nA, lk, ep_out(kc + (size_t)a0 * D, D), st);  // provisional tail rows are overwritten next call
+      linear(y, D, nA, lv, ep_out(vc + (size_t)a0 * D, D), st);
+      relpos_attention(qb, D, kc, D, vc, D, L.pos_proj, h->Tpos, L.pos_u, L.pos_v, att, 1, nA, a0, T, c.enc_heads, D, h->attn_chunk, nullptr, st);
+      linear(att, D, nA, L.attn_out, ep_residual(x, D), st);
+      layer_norm(x, D, y, D, L.conv_ln.g, L.conv_ln.b, nA, D, st);
+      {
+        Epilogue ep = ep_out(gc + (size_t)a0 * D, D);
+        ep.glu = 1;
+        linear(y, D, nA, L.pw1, ep, st);
+      }
+      depthwise_bn_silu(gc, D, L.dw_w, L.bn_scale, L.bn_shift, dw, D, 1, T, a0, nA, D, c.dw_kernel, cc, st);
+      linear(dw, D, nA, L.pw2, ep_residual(x, D), st);
+      layer_norm(x, D, y, D, L.ffn2_ln.g, L.ffn2_ln.b, nA, D, st);
+      linear(y, D, nA, L.ffn2_w1, ep_out(hid, c.enc_ffn, ACT_SILU), st);
+      linear(hid, c.enc_ffn, nA, L.ffn2_w2, ep_residual(x, D, 0.5f), st);
+      layer_norm(x, D, x, D, L.final_ln.g, L.final_ln.b, nA, D, st);
+    }
+  }
+  h->st_T_final = std::max(h->st_T_final, std::min(T, (F / (4 * G)) * G));
+  if (T_final_out) *T_final_out = h->st_T_final;
+  return check_launch(h, "ss_encoder_stream_step");
 }
 
 int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev, int64_t* tokens_dev,
@@ -317,25 +409,48 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
   int fed = 0;  // rows in the KV cache
   int n_tok = start;  // hypothesis length so far (without eos)
   for (int i = 0; i < start; ++i) tokens_out_host[i] = prefix_host[i];
-  for (int step = start; step <= max_len; ++step) {
-    // feed tokens[fed .. step]  (first iteration: the whole prefix; afterwards one token)
-    int n = step + 1 - fed;
-    mt_forward(h, fed, n, T, nullptr, feats_out_dev + (size_t)fed * dim, s, x, st);
-    fed = step + 1;
-    if (step >= max_len) break;  // eos is forced here (sequence_generator.py:362-364): no need for the logits
-    linear(feats_out_dev + (size_t)step * dim, dim, 1, outp, ep_out(logits, c.tgt_vocab), st);
-    // lprobs[pad] = -inf; eos banned while step < min_len (=1)
-    if (step < 1)
-      argmax_rows(logits, c.tgt_vocab, 1, c.tgt_vocab, h->mask_pad_eos, 2, h->mt_next_dev, nullptr, st);
-    else
-      argmax_rows(logits, c.tgt_vocab, 1, c.tgt_vocab, h->mask_pad_unk, 1, h->mt_next_dev, nullptr, st);
-    cudaMemcpyAsync(h->mt_next_pinned, h->mt_next_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-    // also append the chosen token to the device token buffer for the next step
-    cudaMemcpyAsync(h->mt_tok_dev + step + 1, h->mt_next_dev, sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return h->fail(SS_ERR_CUDA, std::string("ss_mt_greedy: ") + cudaGetErrorString(cudaGetLastError()));
-    int64_t next = h->mt_next_pinned[0];
-    if (next == c.eos) break;
-    tokens_out_host[n_tok++] = next;
+  // The arg-max of step s is written straight into the device token buffer at s+1, so consecutive steps need no host
+  // round trip.  Steps are enqueued in bursts; the host reads the burst's tokens back once and stops at the first eos
+  // (steps enqueued past an eos only produce rows that are never read).
+  const int burst = (max_new_tokens >= 0) ? std::max(1, max_new_tokens) : 16;
+  int step = start;
+  bool done = false;
+  while (!done) {
+    const int burst_first = step;
+    int enq = 0;
+    for (; step <= max_len && enq < burst; ++step, ++enq) {
+      // feed tokens[fed .. step]  (first iteration: the whole prefix; afterwards one token)
+      int n = step + 1 - fed;
+      mt_forward(h, fed, n, T, nullptr, feats_out_dev + (size_t)fed * dim, s, x, st);
+      fed = step + 1;
+      if (step >= max_len) {  // eos is forced here (sequence_generator.py:362-364): no need for the logits
+        done = true;
+        ++step;
+        break;
+      }
+      linear(feats_out_dev + (size_t)step * dim, dim, 1, outp, ep_out(logits, c.tgt_vocab), st);
+      // lprobs[pad] = -inf; eos banned while step < min_len (=1)
+      if (step < 1)
+        argmax_rows(logits, c.tgt_vocab, 1, c.tgt_vocab, h->mask_pad_eos, 2, h->mt_tok_dev + step + 1, nullptr, st);
+      else
+        argmax_rows(logits, c.tgt_vocab, 1, c.tgt_vocab, h->mask_pad_unk, 1, h->mt_tok_dev + step + 1, nullptr, st);
+    }
+    // tokens produced by this burst live at mt_tok_dev[burst_first+1 .. ]; the forced-eos step produced none
+    int produced = step - burst_first - (done ? 1 : 0);
+    if (produced > 0) {
+      cudaMemcpyAsync(h->mt_next_pinned, h->mt_tok_dev + burst_first + 1, produced * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess)
+        return h->fail(SS_ERR_CUDA, std::string("ss_mt_greedy: ") + cudaGetErrorString(cudaGetLastError()));
+      for (int i = 0; i < produced; ++i) {
+        int64_t next = h->mt_next_pinned[i];
+        if (next == c.eos) {
+          done = true;
+          break;
+        }
+        tokens_out_host[n_tok++] = next;
+      }
+    }
+    if (step > max_len) done = true;
   }
   *n_out = n_tok;
   return check_launch(h, "ss_mt_greedy");

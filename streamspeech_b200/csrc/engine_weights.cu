@@ -253,6 +253,12 @@ void finalize_impl(ss_engine* h) {
     L.pw2 = pw2.lin;
     L.final_ln = make_ln(h, p + ".final_layer_norm", D);
   }
+  {
+    size_t n = (size_t)c.enc_layers * h->Tpos * D;
+    h->st_k = dev_alloc<float>(h, n);
+    h->st_v = dev_alloc<float>(h, n);
+    h->st_glu = dev_alloc<float>(h, n);
+  }
   // ---- CTC heads
   h->ctc_head[0] = make_linear(h, "source_unigram_decoder.proj", c.src_vocab, D);
   h->ctc_head[1] = make_linear(h, "ctc_target_unigram_decoder.proj", c.tgt_vocab, D);
@@ -273,7 +279,7 @@ void finalize_impl(ss_engine* h) {
     h->mt_self_v = dev_alloc<float>(h, cache);
     h->mt_tok_dev = dev_alloc<int64_t>(h, c.max_mt_positions + 8);
     h->mt_next_dev = dev_alloc<int64_t>(h, 8);
-    cudaMallocHost((void**)&h->mt_next_pinned, 8 * sizeof(int64_t));
+    cudaMallocHost((void**)&h->mt_next_pinned, (size_t)(c.max_mt_positions + 8) * sizeof(int64_t));
   }
   // ---- T2U encoder + unit decoder
   for (int i = 0; i < c.t2u_layers; ++i)

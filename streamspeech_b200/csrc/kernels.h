@@ -28,6 +28,11 @@ struct ConvA {
   int chunk = 0;           // >0: chunk-causal masking (ChunkCausalConv1d semantics)
   float pre_lrelu = 1.0f;  // leaky-relu slope applied while loading A (1 = identity)
   const int* lengths = nullptr;  // optional per-batch valid length of x rows (rows >= length read as zero)
+  // windowed (streaming) use: GEMM row 0 is logical output position t_offset, and buffer row 0 of x is logical
+  // input position x_row0 (x holds x_rows rows per batch element; 0 = L_in).  Masks use logical positions.
+  int t_offset = 0;
+  int x_row0 = 0;
+  int x_rows = 0;
 };
 
 struct Epilogue {
@@ -59,10 +64,12 @@ void fbank_cmvn(const float* samples, int64_t n_samples, int f0, int nf, const f
                 const float* cmvn_std, float* out /*[nf][80]*/, cudaStream_t st);
 
 // Relative-position self-attention of the chunk-Conformer (espnet_multihead_attention.py:154-209).
-// qkv: [B*T][3*D] (q|k|v), pos: [2*Tpos-1][D] rows indexed by (i-j) + Tpos-1, out: [B*T][D]
-void relpos_attention(const float* qkv, const float* pos, int Tpos, const float* bias_u, const float* bias_v,
-                      float* out, int B, int T, int H, int D, int chunk /*0 = full*/, const int* lengths_dev,
-                      cudaStream_t st);
+// q: [B*nQ][ldq] rows for absolute query positions q_offset .. q_offset+nQ-1; k, v: [B*T][ld] rows for absolute
+// key positions 0..T-1; pos: [2*Tpos-1][D] rows indexed by (i-j) + Tpos-1; out: [B*nQ][D].
+// Full recompute: q = qkv, k = qkv + D, v = qkv + 2D, ld* = 3D, q_offset = 0, nQ = T.
+void relpos_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* pos, int Tpos,
+                      const float* bias_u, const float* bias_v, float* out, int B, int nQ, int q_offset, int T, int H, int D,
+                      int chunk /*0 = full*/, const int* lengths_dev, cudaStream_t st);
 
 // Standard multi-head attention, head_dim 64.  q rows = b*Tq + t.  kv_len[b] (device, optional) masks keys >= len.
 // causal: key j visible to query i iff j <= i + causal_offset.
@@ -70,10 +77,10 @@ void mha_attention(const float* q, int ldq, const float* k, int ldk, const float
                    int Tq, int Tk, int H, float scale, int causal, int causal_offset, const int* kv_len_dev,
                    cudaStream_t st);
 
-// depthwise chunk-causal conv (k taps, left context (k-1)/2) + folded BatchNorm + SiLU, channels-last [B*T][C]
+// depthwise chunk-causal conv (k taps, left context (k-1)/2) + folded BatchNorm + SiLU, channels-last.
+// x: [B*T][C] (absolute positions 0..T-1); computes positions t0..t0+n-1 into y rows 0..n-1 per batch element.
 void depthwise_bn_silu(const float* x, int ldx, const float* w /*[k][C]*/, const float* scale, const float* shift,
-                       float* y, int ldy, int B, int T, int C, int k, int chunk, const int* lengths_dev,
-                       cudaStream_t st);
+                       float* y, int ldy, int B, int T, int t0, int n, int C, int k, int chunk, cudaStream_t st);
 
 // misc elementwise / gather kernels
 void scale_rows(float* x, int64_t n, float s, cudaStream_t st);

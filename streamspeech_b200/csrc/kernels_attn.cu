@@ -75,50 +75,49 @@ __device__ __forceinline__ void pv_store(const float* S, int ld, int nq, const i
   *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
-__global__ void __launch_bounds__(ATT_NT) relpos_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ pos,
-                                                                  int Tpos, const float* __restrict__ bias_u,
-                                                                  const float* __restrict__ bias_v, float* __restrict__ out,
-                                                                  int T, int H, int D, int chunk,
-                                                                  const int* __restrict__ lengths, int ldS) {
+__global__ void __launch_bounds__(ATT_NT) relpos_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+                                                                  int ldk, const float* __restrict__ v, int ldv,
+                                                                  const float* __restrict__ pos, int Tpos,
+                                                                  const float* __restrict__ bias_u, const float* __restrict__ bias_v,
+                                                                  float* __restrict__ out, int nQ, int q_offset, int T, int H, int D,
+                                                                  int chunk, const int* __restrict__ lengths, int ldS) {
   extern __shared__ __align__(16) float smem[];
   float* Qu = smem;                 // [QT][64]
   float* Qv = Qu + QT * HD;         // [QT][64]
   float* S = Qv + QT * HD;          // [QT][ldS]
   __shared__ int nvis[QT];
-  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QT;
-  const int nq = min(QT, T - i0);
+  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * QT;  // r0: first query row of the tile (buffer-relative)
+  const int nq = min(QT, nQ - r0);
   const int len = lengths ? min(lengths[b], T) : T;
-  const int64_t ld3 = 3 * (int64_t)D;
-  const float* qb = qkv + ((int64_t)b * T) * ld3 + h * HD;
-  const float* kb = qb + D;
-  const float* vb = qb + 2 * D;
+  const float* qb = q + ((int64_t)b * nQ) * ldq + h * HD;
+  const float* kb = k + ((int64_t)b * T) * ldk + h * HD;
+  const float* vb = v + ((int64_t)b * T) * ldv + h * HD;
   for (int e = threadIdx.x; e < QT * HD; e += ATT_NT) {
-    int q = e / HD, d = e % HD;
-    float v = (q < nq) ? qb[(int64_t)(i0 + q) * ld3 + d] : 0.f;
-    Qu[e] = v + bias_u[h * HD + d];
-    Qv[e] = v + bias_v[h * HD + d];
+    int qq = e / HD, d = e % HD;
+    float val = (qq < nq) ? qb[(int64_t)(r0 + qq) * ldq + d] : 0.f;
+    Qu[e] = val + bias_u[h * HD + d];
+    Qv[e] = val + bias_v[h * HD + d];
   }
   if (threadIdx.x < QT) {
-    int i = i0 + threadIdx.x;
+    int i = q_offset + r0 + threadIdx.x;                           // absolute query position
     int lim = chunk > 0 ? min((i / chunk + 1) * chunk, T) : T;   // chunk mask (s2t_conformer.py:195-213)
     nvis[threadIdx.x] = max(1, min(lim, len));                   // key padding mask (forward_attention)
-    if (len <= 0) nvis[threadIdx.x] = lim;
   }
   __syncthreads();
   const int kmax = nvis[nq - 1];  // limits are non-decreasing in i
   const float* pb = pos + h * HD;
   for (int e = threadIdx.x; e < nq * kmax; e += ATT_NT) {
-    int q = e / kmax, j = e - q * kmax;
-    if (j >= nvis[q]) continue;
-    int i = i0 + q;
-    float ac = dot64(Qu + q * HD, kb + (int64_t)j * ld3);
-    float bd = dot64(Qv + q * HD, pb + (int64_t)(i - j + Tpos - 1) * D);
-    S[q * ldS + j] = (ac + bd) * 0.125f;  // / sqrt(d_k), d_k = 64
+    int qq = e / kmax, j = e - qq * kmax;
+    if (j >= nvis[qq]) continue;
+    int i = q_offset + r0 + qq;
+    float ac = dot64(Qu + qq * HD, kb + (int64_t)j * ldk);
+    float bd = dot64(Qv + qq * HD, pb + (int64_t)(i - j + Tpos - 1) * D);
+    S[qq * ldS + j] = (ac + bd) * 0.125f;  // / sqrt(d_k), d_k = 64
   }
   __syncthreads();
   softmax_rows(S, ldS, nq, nvis);
   __syncthreads();
-  pv_store(S, ldS, nq, nvis, vb, ld3, out + ((int64_t)b * T) * D + h * HD, D, i0);
+  pv_store(S, ldS, nq, nvis, vb, ldv, out + ((int64_t)b * nQ) * D + h * HD, D, r0);
 }
 
 __global__ void __launch_bounds__(ATT_NT) mha_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
@@ -161,10 +160,11 @@ __global__ void __launch_bounds__(ATT_NT) mha_attention_kernel(const float* __re
 
 }  // namespace
 
-void relpos_attention(const float* qkv, const float* pos, int Tpos, const float* bias_u, const float* bias_v, float* out,
-                      int B, int T, int H, int D, int chunk, const int* lengths_dev, cudaStream_t st) {
+void relpos_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* pos, int Tpos,
+                      const float* bias_u, const float* bias_v, float* out, int B, int nQ, int q_offset, int T, int H, int D,
+                      int chunk, const int* lengths_dev, cudaStream_t st) {
   ++g_launches;
-  if (B <= 0 || T <= 0) return;
+  if (B <= 0 || T <= 0 || nQ <= 0) return;
   int ldS = (T + 3) & ~3;
   size_t smem = (size_t)(2 * QT * HD + QT * ldS) * sizeof(float);
   static size_t configured = 0;
@@ -172,8 +172,9 @@ void relpos_attention(const float* qkv, const float* pos, int Tpos, const float*
     cudaFuncSetAttribute(relpos_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dim3 grid((T + QT - 1) / QT, H, B);
-  relpos_attention_kernel<<<grid, ATT_NT, smem, st>>>(qkv, pos, Tpos, bias_u, bias_v, out, T, H, D, chunk, lengths_dev, ldS);
+  dim3 grid((nQ + QT - 1) / QT, H, B);
+  relpos_attention_kernel<<<grid, ATT_NT, smem, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, bias_u, bias_v, out, nQ, q_offset, T, H, D,
+                                                      chunk, lengths_dev, ldS);
 }
 
 void mha_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int B,

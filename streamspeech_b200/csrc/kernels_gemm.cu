@@ -23,7 +23,7 @@ __device__ __forceinline__ float4 load_a4(const ConvA& a, int m, int kk, int M, 
   const float* p;
   if (CONV) {
     int b = m / a.L_rows;
-    int t = m - b * a.L_rows;
+    int t = m - b * a.L_rows + a.t_offset;
     int tap = kk / a.C_in;
     int ci = kk - tap * a.C_in;
     int center = t * a.stride;
@@ -31,7 +31,10 @@ __device__ __forceinline__ float4 load_a4(const ConvA& a, int m, int kk, int M, 
     if (pos < 0 || pos >= a.L_in) return v;
     if (a.chunk > 0 && pos >= (center / a.chunk + 1) * a.chunk) return v;
     if (a.lengths != nullptr && pos >= a.lengths[b]) return v;
-    p = a.x + ((int64_t)b * a.L_in + pos) * a.ldx + ci;
+    int xr = a.x_rows > 0 ? a.x_rows : a.L_in;
+    int pr = pos - a.x_row0;
+    if (pr < 0 || pr >= xr) return v;
+    p = a.x + ((int64_t)b * xr + pr) * a.ldx + ci;
   } else {
     p = a.x + (int64_t)m * a.ldx + kk;
   }
@@ -288,7 +291,7 @@ void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaSt
   const int K = a.ksize * a.C_in;
   if (M <= 0 || N <= 0) return;
   const bool conv = !(a.ksize == 1 && a.stride == 1 && a.pad_left == 0 && a.chunk == 0 && a.lengths == nullptr &&
-                      a.L_in == a.L_rows);
+                      a.L_in == a.L_rows && a.t_offset == 0 && a.x_row0 == 0 && a.x_rows == 0);
   auto ctas = [&](int bm, int bn) { return (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
   const long target = 148;  // one wave of SMs
   if (N <= 16 && !ep.glu) {

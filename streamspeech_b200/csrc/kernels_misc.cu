@@ -43,14 +43,13 @@ __global__ void layer_norm_kernel(const float* __restrict__ x, int ldx, float* _
 
 __global__ void depthwise_bn_silu_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                          const float* __restrict__ scale, const float* __restrict__ shift,
-                                         float* __restrict__ y, int ldy, int T, int C, int k, int chunk,
-                                         const int* __restrict__ lengths) {
-  int row = blockIdx.x;  // b*T + t
-  int b = row / T, t = row - b * T;
+                                         float* __restrict__ y, int ldy, int T, int t0, int n, int C, int k, int chunk) {
+  int row = blockIdx.x;  // b*n + r
+  int b = row / n, t = t0 + (row - b * n);
   int half = (k - 1) >> 1;
   int lim = T;
   if (chunk > 0) lim = min(T, (t / chunk + 1) * chunk);  // future beyond the chunk end is zero (chunk_causal_conv1d.py:40-62)
-  (void)lengths;  // the reference convolves over padded frames too (padding is only masked in attention)
+  // NB: the reference convolves over padded frames too (padding is only masked in attention)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
     for (int j = 0; j < k; ++j) {
@@ -242,10 +241,10 @@ void layer_norm(const float* x, int ldx, float* y, int ldy, const float* gamma, 
 }
 
 void depthwise_bn_silu(const float* x, int ldx, const float* w, const float* scale, const float* shift, float* y, int ldy,
-                       int B, int T, int C, int k, int chunk, const int* lengths_dev, cudaStream_t st) {
+                       int B, int T, int t0, int n, int C, int k, int chunk, cudaStream_t st) {
   ++g_launches;
-  if (B * T <= 0) return;
-  depthwise_bn_silu_kernel<<<B * T, 256, 0, st>>>(x, ldx, w, scale, shift, y, ldy, T, C, k, chunk, lengths_dev);
+  if (B * n <= 0) return;
+  depthwise_bn_silu_kernel<<<B * n, 256, 0, st>>>(x, ldx, w, scale, shift, y, ldy, T, t0, n, C, k, chunk);
 }
 
 void scale_rows(float* x, int64_t n, float s, cudaStream_t st) {

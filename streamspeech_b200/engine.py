@@ -66,6 +66,8 @@ def load_library() -> ctypes.CDLL:
     lib.ss_encoder_out_frames.restype = i64
     lib.ss_fbank.argtypes = [vp, vp, vp, i64, i64, i64, vp]
     lib.ss_encoder_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    lib.ss_encoder_stream_reset.argtypes = [vp]
+    lib.ss_encoder_stream_step.argtypes = [vp, vp, vp, i32, vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.ss_ctc_greedy.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
     lib.ss_mt_greedy.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, i32, ctypes.POINTER(i32), vp]
     lib.ss_mt_features.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp]
@@ -84,7 +86,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
-    "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_ctc_greedy", "ss_mt_greedy",
+    "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_mt_greedy",
     "ss_mt_features", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
     "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_layer_norm", "ss_launch_count",
 ]
@@ -237,6 +239,18 @@ class Engine:
             lens = (ctypes.c_int32 * B)(*[int(x) for x in lengths])
         self._check(self.lib.ss_encoder_forward(self._h, self._stream(), feats.data_ptr(), lens, B, F, out.data_ptr()))
         return out
+
+    def encoder_stream_reset(self):
+        self._check(self.lib.ss_encoder_stream_reset(self._h))
+
+    def encoder_stream_step(self, feats: torch.Tensor, out_buf: torch.Tensor) -> Tuple[int, int]:
+        """feats [F, 80] = all fbank frames of the utterance so far; out_buf [>= T, enc_dim] persistent.  Returns (T, T_final)."""
+        assert feats.is_cuda and feats.is_contiguous() and out_buf.is_cuda and out_buf.is_contiguous()
+        T, Tf = ctypes.c_int32(0), ctypes.c_int32(0)
+        assert out_buf.shape[0] >= self.encoder_out_frames(feats.shape[0])
+        self._check(self.lib.ss_encoder_stream_step(self._h, self._stream(), feats.data_ptr(), feats.shape[0], out_buf.data_ptr(),
+                                                    ctypes.byref(T), ctypes.byref(Tf)))
+        return T.value, Tf.value
 
     def ctc_greedy(self, head: int, enc: torch.Tensor):
         """enc [T, enc_dim] of one utterance -> dict of device tensors (argmax, tokens, index, count)."""

@@ -166,6 +166,29 @@ def test_encoder_streaming_prefix_invariance(full):
     assert d < 1e-4, d
 
 
+@pytest.mark.parametrize("seg_ms,attn,conv", [(160, 4, 8), (320, 8, 8), (640, 16, 16), (160, 4, 4)])
+def test_encoder_streaming_cache_equals_recompute(full, seg_ms, attn, conv):
+    """ss_encoder_stream_step (K/V + conv-input caches, only the open chunk group recomputed) must reproduce the
+    full-prefix recompute that the reference performs on every policy() call, at every call."""
+    cfg, e, o = full
+    e.set_chunk(attn, conv)
+    feats = e.fbank(cuda(synth.make_audio(5.0, seed=31)))
+    buf = torch.zeros(1024, cfg.enc_dim, device="cuda")
+    e.encoder_stream_reset()
+    step = seg_ms // 10
+    worst, calls = 0.0, 0
+    ends = list(range(step - 2, feats.shape[0], step)) + [feats.shape[0]]  # fbank lags the audio by 1.5 frames
+    for F in ends:
+        T, Tf = e.encoder_stream_step(feats[:F].contiguous(), buf)
+        ref = e.encoder(feats[:F].unsqueeze(0).contiguous())[0]
+        assert T == ref.shape[0] and Tf <= T
+        worst = max(worst, maxdiff(buf[:T], ref))
+        calls += 1
+    report(f"encoder_stream_cache_c{attn}_cc{conv}", maxdiff=worst, calls=calls)
+    assert worst < 2e-5, worst
+    e.set_chunk(8, 8)
+
+
 def test_encoder_full_size_vs_oracle(full):
     cfg, e, o = full
     from oracle.streamspeech_oracle import online_features
@@ -276,8 +299,8 @@ def agent_args(**kw):
     return argparse.Namespace(**d)
 
 
-@pytest.mark.parametrize("seconds,seed", [(4.0, 1234), (6.4, 77)])
-def test_streaming_s2st_agent_vs_oracle(seconds, seed):
+@pytest.mark.parametrize("seconds,seed,mode", [(4.0, 1234, "cached"), (6.4, 77, "cached"), (3.0, 1234, "recompute")])
+def test_streaming_s2st_agent_vs_oracle(seconds, seed, mode):
     """Config 2 shape (chunk 320 ms, batch 1): every policy() call must reproduce the oracle agent's action,
     token sequences bit-exactly and the emitted waveform within 1e-3."""
     from oracle.agent_oracle import OracleS2STAgent
@@ -288,7 +311,7 @@ def test_streaming_s2st_agent_vs_oracle(seconds, seed):
     cfg = ModelConfig()
     o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), synth.make_vocoder_state_dict(cfg.vocoder, 1), synth.make_gcmvn(cfg))
     ref = OracleS2STAgent(o, 320)
-    agent = StreamSpeechS2STAgent(agent_args())
+    agent = StreamSpeechS2STAgent(agent_args(encoder_mode=mode, vocoder_context="full" if mode == "recompute" else "receptive-field"))
     wav = synth.make_audio(seconds, seed=seed)
     n = 5120
     worst, writes = 0.0, 0
@@ -308,7 +331,7 @@ def test_streaming_s2st_agent_vs_oracle(seconds, seed):
             if len(a_ref.wav):
                 worst = max(worst, float(np.abs(np.array(seg.content) - np.array(a_ref.wav)).max()))
                 writes += 1
-    report("s2st_streaming", seconds=seconds, wav_maxdiff=worst, writes=writes)
+    report("s2st_streaming_" + mode, seconds=seconds, wav_maxdiff=worst, writes=writes)
     assert writes >= 1 and worst < WAV_TOL, (writes, worst)
     agent.engine.close()
 
