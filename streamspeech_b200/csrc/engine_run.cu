@@ -23,7 +23,10 @@ void linear(const float* x, int ldx, int M, const Linear& l, Epilogue ep, cudaSt
   ConvA a;
   a.x = x; a.B = 1; a.L_in = M; a.L_rows = M; a.C_in = l.K; a.ldx = ldx;
   ep.bias = l.b;
-  gemm_conv(a, l.w, l.N, ep, st);
+  if (skinny_gemm_supported(M, l.N, l.K, ep) && (ldx & 3) == 0)
+    skinny_gemm(x, ldx, l.w, M, l.N, l.K, ep, st);
+  else
+    gemm_conv(a, l.w, l.N, ep, st);
 }
 Epilogue ep_out(float* out, int ldo, int act = ACT_NONE) {
   Epilogue e;

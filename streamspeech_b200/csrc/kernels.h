@@ -54,6 +54,10 @@ struct Epilogue {
 // C[M,N] = epilogue( A[M,K] * W[N,K]^T ), K = ksize*C_in, W row-major with K contiguous.
 void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaStream_t st);
 
+// Weight-streaming GEMM for M <= 64 rows (plain row-major A): one warp per output column, see kernels_skinny.cu.
+bool skinny_gemm_supported(int M, int N, int K, const Epilogue& ep);
+void skinny_gemm(const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st);
+
 // y[r] = LayerNorm(x[r]) * gamma + beta, rows of length C (C <= 1024, multiple of 32)
 void layer_norm(const float* x, int ldx, float* y, int ldy, const float* gamma, const float* beta, int rows, int C,
                 cudaStream_t st);

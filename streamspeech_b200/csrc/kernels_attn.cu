@@ -158,6 +158,100 @@ __global__ void __launch_bounds__(ATT_NT) mha_attention_kernel(const float* __re
   pv_store(S, ldS, nq, nvis, vb, ldv, out + ((int64_t)b * Tq) * ldo + h * HD, ldo, i0);
 }
 
+// ---- one CTA per (query row, head, batch): used when there are too few query tiles to fill the GPU (streaming steps)
+__device__ __forceinline__ float block_max128(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+}
+__device__ __forceinline__ float block_sum128(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// softmax over S[0..n) by the whole CTA, then out[d] = sum_j S[j] * V[j][d]
+__device__ __forceinline__ void row_softmax_pv(float* S, int n, const float* __restrict__ vb, int64_t ldv, float* __restrict__ op,
+                                               float* red, float* part) {
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += ATT_NT) mx = fmaxf(mx, S[j]);
+  mx = block_max128(mx, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < n; j += ATT_NT) {
+    float e = expf(S[j] - mx);
+    S[j] = e;
+    sum += e;
+  }
+  sum = block_sum128(sum, red);
+  __syncthreads();
+  const int d = threadIdx.x & 63, half = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (int j = half; j < n; j += 2) acc = fmaf(S[j] / sum, vb[(int64_t)j * ldv + d], acc);
+  if (half == 1) part[d] = acc;
+  __syncthreads();
+  if (half == 0) op[d] = acc + part[d];
+}
+
+__global__ void __launch_bounds__(ATT_NT) relpos_attention_row_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+                                                                      int ldk, const float* __restrict__ v, int ldv,
+                                                                      const float* __restrict__ pos, int Tpos,
+                                                                      const float* __restrict__ bias_u, const float* __restrict__ bias_v,
+                                                                      float* __restrict__ out, int nQ, int q_offset, int T, int D,
+                                                                      int chunk, const int* __restrict__ lengths) {
+  extern __shared__ __align__(16) float smem[];
+  float* S = smem;  // [T]
+  __shared__ __align__(16) float qu[HD], qv[HD], part[HD];
+  __shared__ float red[4];
+  const int r = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int i = q_offset + r;
+  const int len = lengths ? min(lengths[b], T) : T;
+  const int lim = chunk > 0 ? min((i / chunk + 1) * chunk, T) : T;
+  const int n = max(1, min(lim, len));
+  const float* qb = q + ((int64_t)b * nQ + r) * ldq + h * HD;
+  const float* kb = k + ((int64_t)b * T) * ldk + h * HD;
+  const float* vb = v + ((int64_t)b * T) * ldv + h * HD;
+  if (threadIdx.x < HD) {
+    float val = qb[threadIdx.x];
+    qu[threadIdx.x] = val + bias_u[h * HD + threadIdx.x];
+    qv[threadIdx.x] = val + bias_v[h * HD + threadIdx.x];
+  }
+  __syncthreads();
+  const float* pb = pos + h * HD;
+  for (int j = threadIdx.x; j < n; j += ATT_NT) {
+    float ac = dot64(qu, kb + (int64_t)j * ldk);
+    float bd = dot64(qv, pb + (int64_t)(i - j + Tpos - 1) * D);
+    S[j] = (ac + bd) * 0.125f;
+  }
+  __syncthreads();
+  row_softmax_pv(S, n, vb, ldv, out + ((int64_t)b * nQ + r) * D + h * HD, red, part);
+}
+
+__global__ void __launch_bounds__(ATT_NT) mha_attention_row_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                                   const float* __restrict__ v, int ldv, float* __restrict__ out, int ldo,
+                                                                   int Tq, int Tk, float scale, int causal, int causal_offset,
+                                                                   const int* __restrict__ kv_len) {
+  extern __shared__ __align__(16) float smem[];
+  float* S = smem;
+  __shared__ __align__(16) float qs[HD], part[HD];
+  __shared__ float red[4];
+  const int r = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int len = kv_len ? min(kv_len[b], Tk) : Tk;
+  const int lim = causal ? min(r + causal_offset + 1, Tk) : Tk;
+  const int n = max(1, min(lim, len));
+  const float* qb = q + ((int64_t)b * Tq + r) * ldq + h * HD;
+  const float* kb = k + ((int64_t)b * Tk) * ldk + h * HD;
+  const float* vb = v + ((int64_t)b * Tk) * ldv + h * HD;
+  if (threadIdx.x < HD) qs[threadIdx.x] = qb[threadIdx.x] * scale;
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += ATT_NT) S[j] = dot64(qs, kb + (int64_t)j * ldk);
+  __syncthreads();
+  row_softmax_pv(S, n, vb, ldv, out + ((int64_t)b * Tq + r) * ldo + h * HD, red, part);
+}
+
 }  // namespace
 
 void relpos_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* pos, int Tpos,
@@ -165,6 +259,17 @@ void relpos_attention(const float* q, int ldq, const float* k, int ldk, const fl
                       int chunk, const int* lengths_dev, cudaStream_t st) {
   ++g_launches;
   if (B <= 0 || T <= 0 || nQ <= 0) return;
+  if ((long)((nQ + QT - 1) / QT) * H * B < 96 && (size_t)T * sizeof(float) <= 160 * 1024) {  // too few tiles: one CTA per query row
+    size_t smem_row = (size_t)((T + 3) & ~3) * sizeof(float);
+    static size_t configured_row = 0;
+    if (smem_row > 48 * 1024 && smem_row > configured_row) {
+      cudaFuncSetAttribute(relpos_attention_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      configured_row = 160 * 1024;
+    }
+    relpos_attention_row_kernel<<<dim3(nQ, H, B), ATT_NT, smem_row, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, bias_u, bias_v, out, nQ, q_offset,
+                                                                          T, D, chunk, lengths_dev);
+    return;
+  }
   int ldS = (T + 3) & ~3;
   size_t smem = (size_t)(2 * QT * HD + QT * ldS) * sizeof(float);
   static size_t configured = 0;
@@ -182,6 +287,17 @@ void mha_attention(const float* q, int ldq, const float* k, int ldk, const float
                    cudaStream_t st) {
   ++g_launches;
   if (B <= 0 || Tq <= 0 || Tk <= 0) return;
+  if ((long)((Tq + QT - 1) / QT) * H * B < 96 && (size_t)Tk * sizeof(float) <= 160 * 1024) {
+    size_t smem_row = (size_t)((Tk + 3) & ~3) * sizeof(float);
+    static size_t configured_row = 0;
+    if (smem_row > 48 * 1024 && smem_row > configured_row) {
+      cudaFuncSetAttribute(mha_attention_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      configured_row = 160 * 1024;
+    }
+    mha_attention_row_kernel<<<dim3(Tq, H, B), ATT_NT, smem_row, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, scale, causal, causal_offset,
+                                                                       kv_len_dev);
+    return;
+  }
   int ldS = (Tk + 3) & ~3;
   size_t smem = (size_t)(QT * HD + QT * ldS) * sizeof(float);
   static size_t configured = 0;
