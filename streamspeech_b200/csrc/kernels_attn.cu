@@ -1,164 +1,176 @@
-// Attention kernels (fp32, head_dim 64).  One CTA per (query tile, head, batch element); the score
-// tile lives in shared memory, softmax uses warp-shuffle reductions.
+// Attention kernels (fp32, head_dim 64).
 //   relpos_attention: RelPositionMultiHeadedAttention.forward with the rel_shift folded into the index
 //                     bd[i][j] = (q_i + v) . P[i - j]   (uni_unity/modules/espnet_multihead_attention.py:133-209)
 //   mha_attention   : fairseq MultiheadAttention slow path (ctc_unity/modules/multihead_attention.py:555-784)
+// Two kernel shapes per op:
+//   * tile kernel: one CTA per (16 queries, head, batch); K / V (/ P) tiles of 64 keys are staged in shared memory with
+//     coalesced 128-bit loads and consumed with an online softmax (running max / sum), so K and V are read once per
+//     query tile and nothing of size T x T ever exists;
+//   * row kernel: one CTA per (query, head, batch) for streaming steps with a handful of queries, keys split over the
+//     CTA's threads so that many loads are in flight.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ss {
 namespace {
 
-constexpr int QT = 16;    // queries per CTA
+constexpr int QT = 16;      // queries per CTA (tile kernel)
+constexpr int KT = 64;      // keys per shared-memory tile
 constexpr int ATT_NT = 128;
-constexpr int HD = 64;    // head dim
+constexpr int HD = 64;      // head dim
+constexpr int LDK = HD + 4; // padded row stride of the K/V/P tiles (bank-conflict-free 128-bit reads)
 
-__device__ __forceinline__ float dot64(const float* __restrict__ a_smem, const float* __restrict__ b_gmem) {
+__device__ __forceinline__ float dot64(const float* __restrict__ a, const float* __restrict__ b) {
   float acc = 0.f;
 #pragma unroll
   for (int d = 0; d < HD; d += 4) {
-    float4 b = *reinterpret_cast<const float4*>(b_gmem + d);
-    acc = fmaf(a_smem[d + 0], b.x, acc);
-    acc = fmaf(a_smem[d + 1], b.y, acc);
-    acc = fmaf(a_smem[d + 2], b.z, acc);
-    acc = fmaf(a_smem[d + 3], b.w, acc);
+    float4 x = *reinterpret_cast<const float4*>(a + d);
+    float4 y = *reinterpret_cast<const float4*>(b + d);
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+    acc = fmaf(x.z, y.z, acc);
+    acc = fmaf(x.w, y.w, acc);
   }
   return acc;
 }
 
-// softmax over S[q][0..n) for every query row of the tile; rows are handled one warp at a time
-__device__ __forceinline__ void softmax_rows(float* S, int ld, int nq, const int* nvis) {
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int q = warp; q < nq; q += ATT_NT / 32) {
-    float* row = S + q * ld;
-    int n = nvis[q];
-    float mx = -INFINITY;
-    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, row[j]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < n; j += 32) {
-      float e = expf(row[j] - mx);
-      row[j] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    for (int j = lane; j < n; j += 32) row[j] = row[j] / sum;
+// cooperative copy of `rows` rows of 64 floats (global row stride ld) into a padded smem tile; rows >= valid are zero
+__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int64_t ld, int rows, int valid) {
+  for (int e = threadIdx.x; e < rows * (HD / 4); e += ATT_NT) {
+    int r = e >> 4, c = (e & 15) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < valid) v = *reinterpret_cast<const float4*>(src + (int64_t)r * ld + c);
+    *reinterpret_cast<float4*>(dst + r * LDK + c) = v;
   }
 }
 
-// out[q][d] = sum_j S[q][j] * V[j][d]; thread -> (q = tid/8, 8 dims starting at (tid%8)*8)
-__device__ __forceinline__ void pv_store(const float* S, int ld, int nq, const int* nvis, const float* __restrict__ vbase,
-                                         int64_t ldv, float* __restrict__ obase, int64_t ldo, int i0) {
-  int q = threadIdx.x >> 3, d0 = (threadIdx.x & 7) * 8;
-  if (q >= nq) return;
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  int n = nvis[q];
-  const float* row = S + q * ld;
-  for (int j = 0; j < n; ++j) {
-    float p = row[j];
-    const float* vp = vbase + (int64_t)j * ldv + d0;
-    float4 a = *reinterpret_cast<const float4*>(vp);
-    float4 b = *reinterpret_cast<const float4*>(vp + 4);
-    acc[0] = fmaf(p, a.x, acc[0]);
-    acc[1] = fmaf(p, a.y, acc[1]);
-    acc[2] = fmaf(p, a.z, acc[2]);
-    acc[3] = fmaf(p, a.w, acc[3]);
-    acc[4] = fmaf(p, b.x, acc[4]);
-    acc[5] = fmaf(p, b.y, acc[5]);
-    acc[6] = fmaf(p, b.z, acc[6]);
-    acc[7] = fmaf(p, b.w, acc[7]);
-  }
-  float* op = obase + (int64_t)(i0 + q) * ldo + d0;
-  *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-}
-
-__global__ void __launch_bounds__(ATT_NT) relpos_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
-                                                                  int ldk, const float* __restrict__ v, int ldv,
-                                                                  const float* __restrict__ pos, int Tpos,
-                                                                  const float* __restrict__ bias_u, const float* __restrict__ bias_v,
-                                                                  float* __restrict__ out, int nQ, int q_offset, int T, int H, int D,
-                                                                  int chunk, const int* __restrict__ lengths, int ldS) {
+// Tile kernel.  RELPOS: queries carry two biased copies (q+u for content, q+v for position) and the score adds
+// (q+v).P[i-j]; otherwise plain scaled dot product.  nvis(i) = number of visible keys of query i (a prefix).
+template <bool RELPOS>
+__global__ void __launch_bounds__(ATT_NT) attn_tile_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                           const float* __restrict__ v, int ldv, const float* __restrict__ pos, int Tpos,
+                                                           int ldp, const float* __restrict__ bias_u, const float* __restrict__ bias_v,
+                                                           float* __restrict__ out, int ldo, int nQ, int q_offset, int T, float scale,
+                                                           int chunk, int causal, int causal_offset, const int* __restrict__ lengths) {
   extern __shared__ __align__(16) float smem[];
-  float* Qu = smem;                 // [QT][64]
-  float* Qv = Qu + QT * HD;         // [QT][64]
-  float* S = Qv + QT * HD;          // [QT][ldS]
+  float* Qa = smem;                          // [QT][LDK]  (q+u) or scaled q
+  float* Qb = Qa + QT * LDK;                 // [QT][LDK]  (q+v)           (RELPOS only)
+  float* Ks = Qb + (RELPOS ? QT * LDK : 0);  // [KT][LDK]
+  float* Vs = Ks + KT * LDK;                 // [KT][LDK]
+  float* Ps = Vs + KT * LDK;                 // [KT+QT-1][LDK]             (RELPOS only)
+  float* Sc = Ps + (RELPOS ? (KT + QT - 1) * LDK : 0);  // [QT][KT+1] probabilities of the current tile
   __shared__ int nvis[QT];
-  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * QT;  // r0: first query row of the tile (buffer-relative)
+  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * QT;
   const int nq = min(QT, nQ - r0);
   const int len = lengths ? min(lengths[b], T) : T;
   const float* qb = q + ((int64_t)b * nQ) * ldq + h * HD;
   const float* kb = k + ((int64_t)b * T) * ldk + h * HD;
   const float* vb = v + ((int64_t)b * T) * ldv + h * HD;
   for (int e = threadIdx.x; e < QT * HD; e += ATT_NT) {
-    int qq = e / HD, d = e % HD;
+    int qq = e >> 6, d = e & 63;
     float val = (qq < nq) ? qb[(int64_t)(r0 + qq) * ldq + d] : 0.f;
-    Qu[e] = val + bias_u[h * HD + d];
-    Qv[e] = val + bias_v[h * HD + d];
+    if (RELPOS) {
+      Qa[qq * LDK + d] = val + bias_u[h * HD + d];
+      Qb[qq * LDK + d] = val + bias_v[h * HD + d];
+    } else {
+      Qa[qq * LDK + d] = val * scale;  // q *= scaling (multihead_attention.py:573)
+    }
   }
   if (threadIdx.x < QT) {
-    int i = q_offset + r0 + threadIdx.x;                           // absolute query position
-    int lim = chunk > 0 ? min((i / chunk + 1) * chunk, T) : T;   // chunk mask (s2t_conformer.py:195-213)
-    nvis[threadIdx.x] = max(1, min(lim, len));                   // key padding mask (forward_attention)
-  }
-  __syncthreads();
-  const int kmax = nvis[nq - 1];  // limits are non-decreasing in i
-  const float* pb = pos + h * HD;
-  for (int e = threadIdx.x; e < nq * kmax; e += ATT_NT) {
-    int qq = e / kmax, j = e - qq * kmax;
-    if (j >= nvis[qq]) continue;
-    int i = q_offset + r0 + qq;
-    float ac = dot64(Qu + qq * HD, kb + (int64_t)j * ldk);
-    float bd = dot64(Qv + qq * HD, pb + (int64_t)(i - j + Tpos - 1) * D);
-    S[qq * ldS + j] = (ac + bd) * 0.125f;  // / sqrt(d_k), d_k = 64
-  }
-  __syncthreads();
-  softmax_rows(S, ldS, nq, nvis);
-  __syncthreads();
-  pv_store(S, ldS, nq, nvis, vb, ldv, out + ((int64_t)b * nQ) * D + h * HD, D, r0);
-}
-
-__global__ void __launch_bounds__(ATT_NT) mha_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
-                                                               int ldk, const float* __restrict__ v, int ldv,
-                                                               float* __restrict__ out, int ldo, int Tq, int Tk, float scale,
-                                                               int causal, int causal_offset,
-                                                               const int* __restrict__ kv_len, int ldS) {
-  extern __shared__ __align__(16) float smem[];
-  float* Q = smem;            // [QT][64]
-  float* S = Q + QT * HD;     // [QT][ldS]
-  __shared__ int nvis[QT];
-  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * QT;
-  const int nq = min(QT, Tq - i0);
-  const int len = kv_len ? min(kv_len[b], Tk) : Tk;
-  const float* qb = q + ((int64_t)b * Tq) * ldq + h * HD;
-  const float* kb = k + ((int64_t)b * Tk) * ldk + h * HD;
-  const float* vb = v + ((int64_t)b * Tk) * ldv + h * HD;
-  for (int e = threadIdx.x; e < QT * HD; e += ATT_NT) {
-    int qq = e / HD, d = e % HD;
-    Q[e] = (qq < nq) ? qb[(int64_t)(i0 + qq) * ldq + d] * scale : 0.f;  // q *= scaling (multihead_attention.py:573)
-  }
-  if (threadIdx.x < QT) {
-    int i = i0 + threadIdx.x;
-    int lim = causal ? min(i + causal_offset + 1, Tk) : Tk;
-    nvis[threadIdx.x] = max(1, min(lim, len));
+    int i = q_offset + r0 + threadIdx.x;  // absolute query position
+    int lim;
+    if (RELPOS) lim = chunk > 0 ? min((i / chunk + 1) * chunk, T) : T;  // chunk mask (s2t_conformer.py:195-213)
+    else lim = causal ? min(i + causal_offset + 1, T) : T;
+    nvis[threadIdx.x] = threadIdx.x < nq ? max(1, min(lim, len)) : 0;
   }
   __syncthreads();
   int kmax = 0;
   for (int qq = 0; qq < nq; ++qq) kmax = max(kmax, nvis[qq]);
-  for (int e = threadIdx.x; e < nq * kmax; e += ATT_NT) {
-    int qq = e / kmax, j = e - qq * kmax;
-    if (j >= nvis[qq]) continue;
-    S[qq * ldS + j] = dot64(Q + qq * HD, kb + (int64_t)j * ldk);
+  const int tq = threadIdx.x >> 3;        // query owned by this thread (8 threads per query)
+  const int tg = threadIdx.x & 7;         // key phase / dim group
+  const int my_nvis = nvis[tq];
+  const int i_abs = q_offset + r0 + tq;
+  float m_run = -INFINITY, l_run = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int j0 = 0; j0 < kmax; j0 += KT) {
+    const int nk = min(KT, kmax - j0);
+    __syncthreads();  // previous tile fully consumed
+    load_tile(Ks, kb + (int64_t)j0 * ldk, ldk, KT, nk);
+    load_tile(Vs, vb + (int64_t)j0 * ldv, ldv, KT, nk);
+    const int rel_lo = (q_offset + r0) - (j0 + KT - 1);  // smallest relative position (i - j) touched by this tile
+    if (RELPOS) {
+      const float* pb = pos + h * HD;
+      for (int e = threadIdx.x; e < (KT + QT - 1) * (HD / 4); e += ATT_NT) {
+        int r = e >> 4, c = (e & 15) << 2;
+        int rel = rel_lo + r;
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rel > -Tpos && rel < Tpos) pv = *reinterpret_cast<const float4*>(pb + (int64_t)(rel + Tpos - 1) * ldp + c);
+        *reinterpret_cast<float4*>(Ps + r * LDK + c) = pv;
+      }
+    }
+    __syncthreads();
+    // scores of this thread: keys jj = tg + 8*i
+    float sc[8];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int jj = tg + 8 * i;
+      int j = j0 + jj;
+      float s = -INFINITY;
+      if (j < my_nvis) {
+        s = dot64(Qa + tq * LDK, Ks + jj * LDK);
+        if (RELPOS) s = (s + dot64(Qb + tq * LDK, Ps + ((i_abs - j) - rel_lo) * LDK)) * 0.125f;  // / sqrt(d_k), d_k = 64
+      }
+      sc[i] = s;
+      tmax = fmaxf(tmax, s);
+    }
+    // row max / sum across the 8 threads of the query (they are 8 consecutive lanes of one warp)
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    const float m_new = fmaxf(m_run, tmax);
+    const float corr = (m_new == -INFINITY) ? 1.f : expf(m_run - m_new);
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float p = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - m_new);
+      Sc[tq * (KT + 1) + tg + 8 * i] = p;
+      tsum += p;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+    l_run = l_run * corr + tsum;
+    m_run = m_new;
+    __syncwarp();  // the Sc row of a query is written and read by lanes of the same warp
+    const int d0 = tg * 4;  // this thread owns dims [d0, d0+4) and [32+d0, 32+d0+4): conflict-free 128-bit reads of V
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= corr;
+    const float* prow = Sc + tq * (KT + 1);
+#pragma unroll 4
+    for (int jj = 0; jj < nk; ++jj) {
+      float p = prow[jj];
+      float4 a = *reinterpret_cast<const float4*>(Vs + jj * LDK + d0);
+      float4 c4 = *reinterpret_cast<const float4*>(Vs + jj * LDK + 32 + d0);
+      acc[0] = fmaf(p, a.x, acc[0]);
+      acc[1] = fmaf(p, a.y, acc[1]);
+      acc[2] = fmaf(p, a.z, acc[2]);
+      acc[3] = fmaf(p, a.w, acc[3]);
+      acc[4] = fmaf(p, c4.x, acc[4]);
+      acc[5] = fmaf(p, c4.y, acc[5]);
+      acc[6] = fmaf(p, c4.z, acc[6]);
+      acc[7] = fmaf(p, c4.w, acc[7]);
+    }
   }
-  __syncthreads();
-  softmax_rows(S, ldS, nq, nvis);
-  __syncthreads();
-  pv_store(S, ldS, nq, nvis, vb, ldv, out + ((int64_t)b * Tq) * ldo + h * HD, ldo, i0);
+  if (tq < nq) {
+    float inv = 1.0f / l_run;
+    float* op = out + ((int64_t)b * nQ + r0 + tq) * ldo + h * HD + tg * 4;
+    *reinterpret_cast<float4*>(op) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<float4*>(op + 32) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  }
 }
 
-// ---- one CTA per (query row, head, batch): used when there are too few query tiles to fill the GPU (streaming steps)
+// ---- row kernel: one CTA per (query row, head, batch)
 __device__ __forceinline__ float block_max128(float v, float* red) {
   v = warp_max(v);
   __syncthreads();
@@ -174,11 +186,44 @@ __device__ __forceinline__ float block_sum128(float v, float* red) {
   return (red[0] + red[1]) + (red[2] + red[3]);
 }
 
-// softmax over S[0..n) by the whole CTA, then out[d] = sum_j S[j] * V[j][d]
-__device__ __forceinline__ void row_softmax_pv(float* S, int n, const float* __restrict__ vb, int64_t ldv, float* __restrict__ op,
-                                               float* red, float* part) {
+template <bool RELPOS>
+__global__ void __launch_bounds__(ATT_NT) attn_row_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                          const float* __restrict__ v, int ldv, const float* __restrict__ pos, int Tpos,
+                                                          int ldp, const float* __restrict__ bias_u, const float* __restrict__ bias_v,
+                                                          float* __restrict__ out, int ldo, int nQ, int q_offset, int T, float scale,
+                                                          int chunk, int causal, int causal_offset, const int* __restrict__ lengths) {
+  extern __shared__ __align__(16) float smem[];
+  float* S = smem;  // [T]
+  __shared__ __align__(16) float qa[HD], qb2[HD];
+  __shared__ __align__(16) float part[4][HD];
+  __shared__ float red[4];
+  const int r = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int i = q_offset + r;
+  const int len = lengths ? min(lengths[b], T) : T;
+  int lim;
+  if (RELPOS) lim = chunk > 0 ? min((i / chunk + 1) * chunk, T) : T;
+  else lim = causal ? min(r + causal_offset + 1, T) : T;
+  const int n = max(1, min(lim, len));
+  const float* qp = q + ((int64_t)b * nQ + r) * ldq + h * HD;
+  const float* kb = k + ((int64_t)b * T) * ldk + h * HD;
+  const float* vb = v + ((int64_t)b * T) * ldv + h * HD;
+  if (threadIdx.x < HD) {
+    float val = qp[threadIdx.x];
+    if (RELPOS) {
+      qa[threadIdx.x] = val + bias_u[h * HD + threadIdx.x];
+      qb2[threadIdx.x] = val + bias_v[h * HD + threadIdx.x];
+    } else {
+      qa[threadIdx.x] = val * scale;
+    }
+  }
+  __syncthreads();
   float mx = -INFINITY;
-  for (int j = threadIdx.x; j < n; j += ATT_NT) mx = fmaxf(mx, S[j]);
+  for (int j = threadIdx.x; j < n; j += ATT_NT) {
+    float s = dot64(qa, kb + (int64_t)j * ldk);
+    if (RELPOS) s = (s + dot64(qb2, pos + (int64_t)(i - j + Tpos - 1) * ldp + h * HD)) * 0.125f;
+    S[j] = s;
+    mx = fmaxf(mx, s);
+  }
   mx = block_max128(mx, red);
   float sum = 0.f;
   for (int j = threadIdx.x; j < n; j += ATT_NT) {
@@ -188,68 +233,49 @@ __device__ __forceinline__ void row_softmax_pv(float* S, int n, const float* __r
   }
   sum = block_sum128(sum, red);
   __syncthreads();
-  const int d = threadIdx.x & 63, half = threadIdx.x >> 6;
-  float acc = 0.f;
-  for (int j = half; j < n; j += 2) acc = fmaf(S[j] / sum, vb[(int64_t)j * ldv + d], acc);
-  if (half == 1) part[d] = acc;
+  // out[d] = sum_j p_j V[j][d]: warp w takes keys j = w (mod 4); lane owns dims 2*lane, 2*lane+1 (coalesced 256 B rows)
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+  for (int j = w; j < n; j += 4) {
+    float p = S[j];
+    float2 vv = *reinterpret_cast<const float2*>(vb + (int64_t)j * ldv + 2 * lane);
+    a0 = fmaf(p, vv.x, a0);
+    a1 = fmaf(p, vv.y, a1);
+  }
+  part[w][2 * lane] = a0;
+  part[w][2 * lane + 1] = a1;
   __syncthreads();
-  if (half == 0) op[d] = acc + part[d];
-}
-
-__global__ void __launch_bounds__(ATT_NT) relpos_attention_row_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
-                                                                      int ldk, const float* __restrict__ v, int ldv,
-                                                                      const float* __restrict__ pos, int Tpos,
-                                                                      const float* __restrict__ bias_u, const float* __restrict__ bias_v,
-                                                                      float* __restrict__ out, int nQ, int q_offset, int T, int D,
-                                                                      int chunk, const int* __restrict__ lengths) {
-  extern __shared__ __align__(16) float smem[];
-  float* S = smem;  // [T]
-  __shared__ __align__(16) float qu[HD], qv[HD], part[HD];
-  __shared__ float red[4];
-  const int r = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int i = q_offset + r;
-  const int len = lengths ? min(lengths[b], T) : T;
-  const int lim = chunk > 0 ? min((i / chunk + 1) * chunk, T) : T;
-  const int n = max(1, min(lim, len));
-  const float* qb = q + ((int64_t)b * nQ + r) * ldq + h * HD;
-  const float* kb = k + ((int64_t)b * T) * ldk + h * HD;
-  const float* vb = v + ((int64_t)b * T) * ldv + h * HD;
   if (threadIdx.x < HD) {
-    float val = qb[threadIdx.x];
-    qu[threadIdx.x] = val + bias_u[h * HD + threadIdx.x];
-    qv[threadIdx.x] = val + bias_v[h * HD + threadIdx.x];
+    float t = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
+    out[((int64_t)b * nQ + r) * ldo + h * HD + threadIdx.x] = t / sum;
   }
-  __syncthreads();
-  const float* pb = pos + h * HD;
-  for (int j = threadIdx.x; j < n; j += ATT_NT) {
-    float ac = dot64(qu, kb + (int64_t)j * ldk);
-    float bd = dot64(qv, pb + (int64_t)(i - j + Tpos - 1) * D);
-    S[j] = (ac + bd) * 0.125f;
-  }
-  __syncthreads();
-  row_softmax_pv(S, n, vb, ldv, out + ((int64_t)b * nQ + r) * D + h * HD, red, part);
 }
 
-__global__ void __launch_bounds__(ATT_NT) mha_attention_row_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
-                                                                   const float* __restrict__ v, int ldv, float* __restrict__ out, int ldo,
-                                                                   int Tq, int Tk, float scale, int causal, int causal_offset,
-                                                                   const int* __restrict__ kv_len) {
-  extern __shared__ __align__(16) float smem[];
-  float* S = smem;
-  __shared__ __align__(16) float qs[HD], part[HD];
-  __shared__ float red[4];
-  const int r = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int len = kv_len ? min(kv_len[b], Tk) : Tk;
-  const int lim = causal ? min(r + causal_offset + 1, Tk) : Tk;
-  const int n = max(1, min(lim, len));
-  const float* qb = q + ((int64_t)b * Tq + r) * ldq + h * HD;
-  const float* kb = k + ((int64_t)b * Tk) * ldk + h * HD;
-  const float* vb = v + ((int64_t)b * Tk) * ldv + h * HD;
-  if (threadIdx.x < HD) qs[threadIdx.x] = qb[threadIdx.x] * scale;
-  __syncthreads();
-  for (int j = threadIdx.x; j < n; j += ATT_NT) S[j] = dot64(qs, kb + (int64_t)j * ldk);
-  __syncthreads();
-  row_softmax_pv(S, n, vb, ldv, out + ((int64_t)b * Tq + r) * ldo + h * HD, red, part);
+template <bool RELPOS>
+void launch_attn(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* pos, int Tpos, int ldp,
+                 const float* bias_u, const float* bias_v, float* out, int ldo, int B, int nQ, int q_offset, int T, int H, float scale,
+                 int chunk, int causal, int causal_offset, const int* lengths, cudaStream_t st) {
+  const long tiles = (long)((nQ + QT - 1) / QT) * H * B;
+  if (tiles < 96 && (size_t)T * sizeof(float) <= 160 * 1024) {
+    size_t smem_row = (size_t)((T + 3) & ~3) * sizeof(float);
+    static size_t configured_row = 0;
+    if (smem_row > 40 * 1024 && smem_row > configured_row) {
+      cudaFuncSetAttribute(attn_row_kernel<RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      configured_row = 160 * 1024;
+    }
+    attn_row_kernel<RELPOS><<<dim3(nQ, H, B), ATT_NT, smem_row, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo, nQ,
+                                                                      q_offset, T, scale, chunk, causal, causal_offset, lengths);
+    return;
+  }
+  size_t smem = (size_t)((RELPOS ? 2 : 1) * QT * LDK + 2 * KT * LDK + (RELPOS ? (KT + QT - 1) * LDK : 0) + QT * (KT + 1)) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attn_tile_kernel<RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  attn_tile_kernel<RELPOS><<<dim3((nQ + QT - 1) / QT, H, B), ATT_NT, smem, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo,
+                                                                                 nQ, q_offset, T, scale, chunk, causal, causal_offset, lengths);
 }
 
 }  // namespace
@@ -259,27 +285,7 @@ void relpos_attention(const float* q, int ldq, const float* k, int ldk, const fl
                       int chunk, const int* lengths_dev, cudaStream_t st) {
   ++g_launches;
   if (B <= 0 || T <= 0 || nQ <= 0) return;
-  if ((long)((nQ + QT - 1) / QT) * H * B < 96 && (size_t)T * sizeof(float) <= 160 * 1024) {  // too few tiles: one CTA per query row
-    size_t smem_row = (size_t)((T + 3) & ~3) * sizeof(float);
-    static size_t configured_row = 0;
-    if (smem_row > 48 * 1024 && smem_row > configured_row) {
-      cudaFuncSetAttribute(relpos_attention_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      configured_row = 160 * 1024;
-    }
-    relpos_attention_row_kernel<<<dim3(nQ, H, B), ATT_NT, smem_row, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, bias_u, bias_v, out, nQ, q_offset,
-                                                                          T, D, chunk, lengths_dev);
-    return;
-  }
-  int ldS = (T + 3) & ~3;
-  size_t smem = (size_t)(2 * QT * HD + QT * ldS) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(relpos_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  dim3 grid((nQ + QT - 1) / QT, H, B);
-  relpos_attention_kernel<<<grid, ATT_NT, smem, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, bias_u, bias_v, out, nQ, q_offset, T, H, D,
-                                                      chunk, lengths_dev, ldS);
+  launch_attn<true>(q, ldq, k, ldk, v, ldv, pos, Tpos, D, bias_u, bias_v, out, D, B, nQ, q_offset, T, H, 0.125f, chunk, 0, 0, lengths_dev, st);
 }
 
 void mha_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int B,
@@ -287,27 +293,8 @@ void mha_attention(const float* q, int ldq, const float* k, int ldk, const float
                    cudaStream_t st) {
   ++g_launches;
   if (B <= 0 || Tq <= 0 || Tk <= 0) return;
-  if ((long)((Tq + QT - 1) / QT) * H * B < 96 && (size_t)Tk * sizeof(float) <= 160 * 1024) {
-    size_t smem_row = (size_t)((Tk + 3) & ~3) * sizeof(float);
-    static size_t configured_row = 0;
-    if (smem_row > 48 * 1024 && smem_row > configured_row) {
-      cudaFuncSetAttribute(mha_attention_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      configured_row = 160 * 1024;
-    }
-    mha_attention_row_kernel<<<dim3(Tq, H, B), ATT_NT, smem_row, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, scale, causal, causal_offset,
-                                                                       kv_len_dev);
-    return;
-  }
-  int ldS = (Tk + 3) & ~3;
-  size_t smem = (size_t)(QT * HD + QT * ldS) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(mha_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  dim3 grid((Tq + QT - 1) / QT, H, B);
-  mha_attention_kernel<<<grid, ATT_NT, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, scale, causal, causal_offset,
-                                                   kv_len_dev, ldS);
+  launch_attn<false>(q, ldq, k, ldk, v, ldv, nullptr, 0, 0, nullptr, nullptr, out, ldo, B, Tq, 0, Tk, H, scale, 0, causal, causal_offset,
+                     kv_len_dev, st);
 }
 
 }  // namespace ss

@@ -254,7 +254,7 @@ void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue&
   const long ctas = (long)grid.x * grid.y;
   const int nk = (K + BK - 1) / BK;
   int splits = 1;
-  if (ctas < 96 && nk >= 8) {
+  if (ctas < 148 && nk >= 8) {
     splits = (int)std::min<long>((148 + ctas - 1) / ctas, nk / 4);  // >= 4 k-tiles (64 columns) per slice
     if ((size_t)splits * M * N * sizeof(float) > SPLITK_WS_BYTES) splits = 1;
   }
@@ -304,9 +304,13 @@ void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaSt
     else launch<32, 32>(a, W, M, N, K, ep, conv, st);
     return;
   }
+  // Prefer the largest tile that still fills the GPU once split-K (slices of >= 8 k-tiles, at most 8 slices) is counted:
+  // a long K walked by few small CTAs is latency-bound (r1_launches_v0: 42 us per 32x32-tile launch).
+  const int nk = (K + BK - 1) / BK;
+  const long max_splits = std::max(1, std::min(8, nk / 8));
   if (ctas(128, 64) >= 2 * target) launch<128, 64>(a, W, M, N, K, ep, conv, st);
-  else if (ctas(64, 64) >= target) launch<64, 64>(a, W, M, N, K, ep, conv, st);
-  else if (ctas(32, 64) >= target) launch<32, 64>(a, W, M, N, K, ep, conv, st);
+  else if (ctas(64, 64) * max_splits >= target) launch<64, 64>(a, W, M, N, K, ep, conv, st);
+  else if (ctas(32, 64) * max_splits >= target) launch<32, 64>(a, W, M, N, K, ep, conv, st);
   else launch<32, 32>(a, W, M, N, K, ep, conv, st);
 }
 

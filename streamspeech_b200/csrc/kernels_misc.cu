@@ -155,19 +155,44 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int
 
 __global__ void ctc_collapse_kernel(const int64_t* __restrict__ am, int n, int blank, int pad, int64_t* __restrict__ toks,
                                     int* __restrict__ index, int* __restrict__ count) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one CTA of 1024 threads; thread t owns the contiguous slice [t*per, (t+1)*per); block-wide exclusive scan of the keep counts
+  __shared__ int wsum[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, t * per), hi = min(n, lo + per);
   int c = 0;
-  for (int i = 0; i < n; ++i) {
+  for (int i = lo; i < hi; ++i) {
     int64_t v = am[i];
-    if (i == 0 || v != am[i - 1]) {
-      if (v != blank && v != pad) {
-        toks[c] = v;
-        if (index) index[c] = i;
-        ++c;
-      }
+    c += ((i == 0 || v != am[i - 1]) && v != blank && v != pad) ? 1 : 0;
+  }
+  int inc = c;  // inclusive scan inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int s = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    wsum[lane] = s;
+  }
+  __syncthreads();
+  int base = (w > 0 ? wsum[w - 1] : 0) + inc - c;
+  for (int i = lo; i < hi; ++i) {
+    int64_t v = am[i];
+    if ((i == 0 || v != am[i - 1]) && v != blank && v != pad) {
+      toks[base] = v;
+      if (index) index[base] = i;
+      ++base;
     }
   }
-  *count = c;
+  if (t == 1023) *count = wsum[31];
 }
 
 __global__ void gather_rows_kernel(const int64_t* __restrict__ idx, int idx_offset, const float* __restrict__ table, int C,
@@ -282,7 +307,7 @@ void argmax_rows(const float* logits, int ld, int rows, int V, const int* masked
 void ctc_collapse(const int64_t* argmax, int n, int blank, int pad, int64_t* out_tokens, int* out_index, int* out_count,
                   cudaStream_t st) {
   ++g_launches;
-  ctc_collapse_kernel<<<1, 32, 0, st>>>(argmax, n, blank, pad, out_tokens, out_index, out_count);
+  ctc_collapse_kernel<<<1, 1024, 0, st>>>(argmax, n, blank, pad, out_tokens, out_index, out_count);
 }
 
 void gather_rows(const int64_t* idx, int n, int idx_offset, const float* table, int C, float* out, cudaStream_t st) {

@@ -1,9 +1,12 @@
 // Skinny GEMM for the streaming regime (M <= 64 rows: cached encoder step M = 16, MT decode step M = 1):
 //   out[m][n] = epilogue( sum_k A[m][k] * W[n][k] ),  A row-major [M][K], W row-major [N][K].
 // These GEMMs are weight-streaming problems (2 MB of W for 16 rows), so the kernel is organised around memory-level
-// parallelism instead of tiles: one warp per output column, lanes stride K with 128-bit loads (a whole W row is in
-// flight at once), A staged once per CTA in shared memory, M accumulators per lane, shuffle reduction, fused epilogue
-// (bias / ReLU / SiLU / GLU / residual).  Deterministic summation order.  HBM/L2-bound by construction.
+// parallelism instead of tiles:
+//   * one warp per (output column, K-slice); lanes stride K with 128-bit loads, so a whole slice of the W row is in
+//     flight at once; W is read exactly once (streaming, L1 no-allocate), A (<= 128 KB) is re-read through L1/L2;
+//   * the KS K-slices of a column live in one CTA and are combined through shared memory in a fixed order
+//     (deterministic results), then the epilogue (bias / ReLU / SiLU / GLU / residual) runs one row per lane.
+// HBM/L2-bound by construction: algorithmic bytes = N*K*4 (weights) + M*K*4 + M*N*4.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -11,6 +14,7 @@ namespace ss {
 namespace {
 
 constexpr int SK_WARPS = 8;
+constexpr int SK_MR = 16;  // rows per pass (accumulators per lane)
 
 __device__ __forceinline__ float sk_act(float x, int act) {
   switch (act) {
@@ -21,80 +25,116 @@ __device__ __forceinline__ float sk_act(float x, int act) {
   }
 }
 
-// MR = rows handled per pass (accumulators per lane)
-template <int MR>
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// KS = K-slices per column (warps cooperating on one column), CPT = columns per task (2 for GLU pairs)
+template <int MR, int KS, int CPT>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                                     int M, int N, int K, Epilogue ep) {
-  extern __shared__ __align__(16) float As[];  // [M][K]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // stage A (coalesced 128-bit loads)
-  const int kv = K >> 2;
-  for (int i = tid; i < M * kv; i += SK_WARPS * 32) {
-    int m = i / kv, k4 = i - m * kv;
-    reinterpret_cast<float4*>(As)[i] = *reinterpret_cast<const float4*>(A + (int64_t)m * lda + (k4 << 2));
-  }
-  __syncthreads();
-  const int cols_per_task = ep.glu ? 2 : 1;
-  const int ntasks = N / cols_per_task;
-  for (int task = blockIdx.x * SK_WARPS + warp; task < ntasks; task += gridDim.x * SK_WARPS) {
-    const int n0 = task * cols_per_task;
+  constexpr int TASKS_PER_CTA = SK_WARPS / KS;
+  __shared__ float part[SK_WARPS][CPT][MR];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slice = warp % KS, tslot = warp / KS;
+  const int ntasks = N / CPT;
+  const int kslice = K / KS;  // multiple of 128 (checked by the host)
+  const int k_lo = slice * kslice, k_hi = k_lo + kslice;
+  for (int tbase = blockIdx.x * TASKS_PER_CTA; tbase < ntasks; tbase += gridDim.x * TASKS_PER_CTA) {
+    const int task = tbase + tslot;
+    const bool active = task < ntasks;
+    const int n0 = task * CPT;
     for (int mb = 0; mb < M; mb += MR) {
-      float acc0[MR], acc1[MR];
+      float acc[CPT][MR];
 #pragma unroll
-      for (int r = 0; r < MR; ++r) acc0[r] = acc1[r] = 0.f;
-      const float* w0 = W + (int64_t)n0 * K;
-      const float* w1 = w0 + K;
-#pragma unroll 4
-      for (int k = lane * 4; k < K; k += 128) {
-        float4 a0 = *reinterpret_cast<const float4*>(w0 + k);
-        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cols_per_task == 2) a1 = *reinterpret_cast<const float4*>(w1 + k);
+      for (int c = 0; c < CPT; ++c)
 #pragma unroll
-        for (int r = 0; r < MR; ++r) {
-          if (mb + r < M) {
-            float4 x = *reinterpret_cast<const float4*>(As + (mb + r) * K + k);
-            acc0[r] = fmaf(x.x, a0.x, acc0[r]);
-            acc0[r] = fmaf(x.y, a0.y, acc0[r]);
-            acc0[r] = fmaf(x.z, a0.z, acc0[r]);
-            acc0[r] = fmaf(x.w, a0.w, acc0[r]);
-            if (cols_per_task == 2) {
-              acc1[r] = fmaf(x.x, a1.x, acc1[r]);
-              acc1[r] = fmaf(x.y, a1.y, acc1[r]);
-              acc1[r] = fmaf(x.z, a1.z, acc1[r]);
-              acc1[r] = fmaf(x.w, a1.w, acc1[r]);
+        for (int r = 0; r < MR; ++r) acc[c][r] = 0.f;
+      if (active) {
+        const float* w0 = W + (int64_t)n0 * K;
+#pragma unroll 2
+        for (int k = k_lo + lane * 4; k < k_hi; k += 128) {
+          float4 wv[CPT];
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) wv[c] = ld_stream(w0 + (int64_t)c * K + k);
+#pragma unroll
+          for (int r = 0; r < MR; ++r) {
+            if (mb + r < M) {
+              float4 x = *reinterpret_cast<const float4*>(A + (int64_t)(mb + r) * lda + k);
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) {
+                acc[c][r] = fmaf(x.x, wv[c].x, acc[c][r]);
+                acc[c][r] = fmaf(x.y, wv[c].y, acc[c][r]);
+                acc[c][r] = fmaf(x.z, wv[c].z, acc[c][r]);
+                acc[c][r] = fmaf(x.w, wv[c].w, acc[c][r]);
+              }
             }
           }
         }
       }
+      // lane r ends up holding the warp total of row r
+      float mine[CPT];
 #pragma unroll
-      for (int r = 0; r < MR; ++r) {
-        acc0[r] = warp_sum(acc0[r]);
-        if (cols_per_task == 2) acc1[r] = warp_sum(acc1[r]);
-      }
-      if (lane == 0) {
+      for (int c = 0; c < CPT; ++c) {
+        mine[c] = 0.f;
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
-          int m = mb + r;
-          if (m >= M) break;
-          float y;
-          int oc;
-          if (ep.glu) {
-            float av = acc0[r] + (ep.bias ? ep.bias[n0] : 0.f);
-            float gv = acc1[r] + (ep.bias ? ep.bias[n0 + 1] : 0.f);
-            y = ep.alpha * (av * (1.0f / (1.0f + expf(-gv))));
-            oc = n0 >> 1;
-          } else {
-            y = ep.alpha * sk_act(acc0[r] + (ep.bias ? ep.bias[n0] : 0.f), ep.act);
-            oc = n0;
-          }
-          int64_t o = (int64_t)m * ep.ldo + oc;
-          if (ep.residual) y += ep.res_scale * ep.residual[o];
-          if (ep.accumulate) y += ep.out[o];
-          ep.out[o] = y;
+          float t = warp_sum(acc[c][r]);
+          if (lane == r) mine[c] = t;
         }
       }
+      if (KS > 1) {
+        if (lane < MR) {
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) part[warp][c][lane] = mine[c];
+        }
+        __syncthreads();
+        if (slice == 0 && lane < MR) {
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            float t = part[warp][c][lane];
+#pragma unroll
+            for (int s = 1; s < KS; ++s) t += part[warp + s][c][lane];
+            mine[c] = t;
+          }
+        }
+      }
+      const int m = mb + lane;
+      if (active && slice == 0 && lane < MR && m < M) {
+        float y;
+        int oc;
+        if (CPT == 2) {
+          float av = mine[0] + (ep.bias ? ep.bias[n0] : 0.f);
+          float gv = mine[CPT - 1] + (ep.bias ? ep.bias[n0 + 1] : 0.f);
+          y = ep.alpha * (av * (1.0f / (1.0f + expf(-gv))));
+          oc = n0 >> 1;
+        } else {
+          y = ep.alpha * sk_act(mine[0] + (ep.bias ? ep.bias[n0] : 0.f), ep.act);
+          oc = n0;
+        }
+        int64_t o = (int64_t)m * ep.ldo + oc;
+        if (ep.residual) y += ep.res_scale * ep.residual[o];
+        if (ep.accumulate) y += ep.out[o];
+        ep.out[o] = y;
+      }
+      if (KS > 1) __syncthreads();  // `part` is reused by the next pass / task
     }
   }
+}
+
+template <int MR, int KS>
+void launch_skinny(const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+  const int cpt = ep.glu ? 2 : 1;
+  const int ntasks = N / cpt;
+  const int per_cta = SK_WARPS / KS;
+  int grid = (ntasks + per_cta - 1) / per_cta;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (ep.glu)
+    skinny_gemm_kernel<MR, KS, 2><<<grid, SK_WARPS * 32, 0, st>>>(A, lda, W, M, N, K, ep);
+  else
+    skinny_gemm_kernel<MR, KS, 1><<<grid, SK_WARPS * 32, 0, st>>>(A, lda, W, M, N, K, ep);
 }
 
 }  // namespace
@@ -102,27 +142,37 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
 bool skinny_gemm_supported(int M, int N, int K, const Epilogue& ep) {
   if (M < 1 || M > 64 || (K & 127) != 0 || ep.out_L > 0) return false;
   if (ep.glu && (N & 1)) return false;
-  return (size_t)M * K * sizeof(float) <= 200 * 1024;
+  return true;
 }
 
 void skinny_gemm(const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
   ++g_launches;
-  const size_t smem = (size_t)M * K * sizeof(float);
+  // K-slices per column: enough warp-tasks to cover 148 SMs x 16 warps, every slice a multiple of 128 columns
   const int ntasks = ep.glu ? N / 2 : N;
-  int grid = (ntasks + SK_WARPS - 1) / SK_WARPS;
-  const int max_grid = smem > 100 * 1024 ? 148 : 148 * 4;
-  if (grid > max_grid) grid = max_grid;
-  static size_t configured[3] = {0, 0, 0};
-  auto launch = [&](auto kernel, int slot) {
-    if (smem > 48 * 1024 && smem > configured[slot]) {
-      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      configured[slot] = 200 * 1024;
+  int ks = 1;
+  while (ks < 8 && (long)ntasks * ks < 2400 && K % (ks * 2 * 128) == 0) ks *= 2;
+  if (M == 1) {
+    switch (ks) {
+      case 1: launch_skinny<1, 1>(A, lda, W, M, N, K, ep, st); break;
+      case 2: launch_skinny<1, 2>(A, lda, W, M, N, K, ep, st); break;
+      case 4: launch_skinny<1, 4>(A, lda, W, M, N, K, ep, st); break;
+      default: launch_skinny<1, 8>(A, lda, W, M, N, K, ep, st); break;
     }
-    kernel<<<grid, SK_WARPS * 32, smem, st>>>(A, lda, W, M, N, K, ep);
-  };
-  if (M == 1) launch(skinny_gemm_kernel<1>, 0);
-  else if (M <= 8) launch(skinny_gemm_kernel<8>, 1);
-  else launch(skinny_gemm_kernel<16>, 2);
+  } else if (M <= 8) {
+    switch (ks) {
+      case 1: launch_skinny<8, 1>(A, lda, W, M, N, K, ep, st); break;
+      case 2: launch_skinny<8, 2>(A, lda, W, M, N, K, ep, st); break;
+      case 4: launch_skinny<8, 4>(A, lda, W, M, N, K, ep, st); break;
+      default: launch_skinny<8, 8>(A, lda, W, M, N, K, ep, st); break;
+    }
+  } else {
+    switch (ks) {
+      case 1: launch_skinny<SK_MR, 1>(A, lda, W, M, N, K, ep, st); break;
+      case 2: launch_skinny<SK_MR, 2>(A, lda, W, M, N, K, ep, st); break;
+      case 4: launch_skinny<SK_MR, 4>(A, lda, W, M, N, K, ep, st); break;
+      default: launch_skinny<SK_MR, 8>(A, lda, W, M, N, K, ep, st); break;
+    }
+  }
 }
 
 }  // namespace ss
