@@ -28,6 +28,46 @@ void linear(const float* x, int ldx, int M, const Linear& l, Epilogue ep, cudaSt
   else
     gemm_conv(a, l.w, l.N, ep, st);
 }
+// out = epilogue(LayerNorm(x) @ W^T).  The LN is fused into the skinny kernel's A load when the shape allows it,
+// otherwise it is a separate launch into `scratch` [M][K].
+void ln_linear(const float* x, int ldx, int M, const LNorm& ln, const Linear& l, Epilogue ep, float* scratch, cudaStream_t st) {
+  ep.bias = l.b;
+  Epilogue fused = ep;
+  fused.ln_gamma = ln.g;
+  fused.ln_beta = ln.b;
+  if (ln.C == l.K && (ldx & 3) == 0 && skinny_gemm_supported(M, l.N, l.K, fused)) {
+    skinny_gemm(x, ldx, l.w, M, l.N, l.K, fused, st);
+    return;
+  }
+  layer_norm(x, ldx, scratch, l.K, ln.g, ln.b, M, l.K, st);
+  linear(scratch, l.K, M, l, ep, st);
+}
+
+// q | k | v = LayerNorm(x) @ Wqkv^T with the three column blocks routed to their own buffers (query scratch, K cache
+// rows, V cache rows).  One launch on the skinny path; LN + three GEMMs otherwise.
+void ln_qkv_routed(const float* x, int ldx, int M, const LNorm& ln, const Linear& qkv, int dim, float* q, int ldq, float* k, int ldk,
+                   float* v, int ldv, float* scratch, cudaStream_t st) {
+  Epilogue ep;
+  ep.out = q; ep.ldo = ldq; ep.out2 = k; ep.ldo2 = ldk; ep.out3 = v; ep.ldo3 = ldv; ep.split_n = dim;
+  ep.bias = qkv.b; ep.ln_gamma = ln.g; ep.ln_beta = ln.b;
+  if (ln.C == qkv.K && (ldx & 3) == 0 && skinny_gemm_supported(M, qkv.N, qkv.K, ep)) {
+    skinny_gemm(x, ldx, qkv.w, M, qkv.N, qkv.K, ep, st);
+    return;
+  }
+  layer_norm(x, ldx, scratch, qkv.K, ln.g, ln.b, M, qkv.K, st);
+  Linear part = qkv;
+  part.N = dim;
+  float* outs[3] = {q, k, v};
+  int lds[3] = {ldq, ldk, ldv};
+  for (int p = 0; p < 3; ++p) {
+    part.w = qkv.w + (size_t)p * dim * qkv.K;
+    part.b = qkv.b + p * dim;
+    Epilogue e;
+    e.out = outs[p]; e.ldo = lds[p];
+    linear(scratch, qkv.K, M, part, e, st);
+  }
+}
+
 Epilogue ep_out(float* out, int ldo, int act = ACT_NONE) {
   Epilogue e;
   e.out = out; e.ldo = ldo; e.act = act;
@@ -55,27 +95,22 @@ void dec_layer(const DecLayerW& L, float* x, int n, int dim, int ffn, int heads,
                const int* self_kv_len_dev, float* cache_k, float* cache_v, int past, const float* cross_kv, int Tk,
                const int* cross_len_dev, DecScratch& s, cudaStream_t st) {
   const float scale = 0.125f;  // head_dim ** -0.5, head_dim = 64
-  layer_norm(x, dim, s.y, dim, L.self_ln.g, L.self_ln.b, n, dim, st);
   if (cache_k) {
-    linear(s.y, dim, n, L.q, ep_out(s.q, dim), st);
-    linear(s.y, dim, n, L.k, ep_out(cache_k + (size_t)past * dim, dim), st);
-    linear(s.y, dim, n, L.v, ep_out(cache_v + (size_t)past * dim, dim), st);
+    ln_qkv_routed(x, dim, n, L.self_ln, L.qkv, dim, s.q, dim, cache_k + (size_t)past * dim, dim, cache_v + (size_t)past * dim, dim, s.y, st);
     mha_attention(s.q, dim, cache_k, dim, cache_v, dim, s.attn, dim, 1, n, past + n, heads, scale, 1, past, self_kv_len_dev, st);
   } else {
-    linear(s.y, dim, n, L.qkv, ep_out(s.qkv, 3 * dim), st);
+    ln_linear(x, dim, n, L.self_ln, L.qkv, ep_out(s.qkv, 3 * dim), s.y, st);
     mha_attention(s.qkv, 3 * dim, s.qkv + dim, 3 * dim, s.qkv + 2 * dim, 3 * dim, s.attn, dim, 1, n, n, heads, scale,
                   causal ? 1 : 0, 0, self_kv_len_dev, st);
   }
   (void)self_kv_len_limit;
   linear(s.attn, dim, n, L.out, ep_residual(x, dim), st);
   if (L.has_cross) {
-    layer_norm(x, dim, s.y, dim, L.cross_ln.g, L.cross_ln.b, n, dim, st);
-    linear(s.y, dim, n, L.cq, ep_out(s.q, dim), st);
+    ln_linear(x, dim, n, L.cross_ln, L.cq, ep_out(s.q, dim), s.y, st);
     mha_attention(s.q, dim, cross_kv, 2 * dim, cross_kv + dim, 2 * dim, s.attn, dim, 1, n, Tk, heads, scale, 0, 0, cross_len_dev, st);
     linear(s.attn, dim, n, L.cout, ep_residual(x, dim), st);
   }
-  layer_norm(x, dim, s.y, dim, L.final_ln.g, L.final_ln.b, n, dim, st);
-  linear(s.y, dim, n, L.fc1, ep_out(s.hid, ffn, ACT_RELU), st);
+  ln_linear(x, dim, n, L.final_ln, L.fc1, ep_out(s.hid, ffn, ACT_RELU), s.y, st);
   linear(s.hid, ffn, n, L.fc2, ep_residual(x, dim), st);
 }
 
@@ -302,29 +337,20 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
       float* kc = h->st_k + (size_t)i * h->Tpos * D;
       float* vc = h->st_v + (size_t)i * h->Tpos * D;
       float* gc = h->st_glu + (size_t)i * h->Tpos * D;
-      layer_norm(x, D, y, D, L.ffn1_ln.g, L.ffn1_ln.b, nA, D, st);
-      linear(y, D, nA, L.ffn1_w1, ep_out(hid, c.enc_ffn, ACT_SILU), st);
+      ln_linear(x, D, nA, L.ffn1_ln, L.ffn1_w1, ep_out(hid, c.enc_ffn, ACT_SILU), y, st);
       linear(hid, c.enc_ffn, nA, L.ffn1_w2, ep_residual(x, D, 0.5f), st);
-      layer_norm(x, D, y, D, L.attn_ln.g, L.attn_ln.b, nA, D, st);
-      Linear lq = L.qkv, lk = L.qkv, lv = L.qkv;  // row slices of the fused [3D][D] projection
-      lq.N = lk.N = lv.N = D;
-      lk.w += (size_t)D * D; lk.b += D;
-      lv.w += (size_t)2 * D * D; lv.b += 2 * D;
-      linear(y, D, nA, lq, ep_out(qb, D), st);
-      linear(y, D, nA, lk, ep_out(kc + (size_t)a0 * D, D), st);  // provisional tail rows are overwritten next call
-      linear(y, D, nA, lv, ep_out(vc + (size_t)a0 * D, D), st);
+      // q -> scratch, k / v -> cache rows a0.. (provisional tail rows are overwritten next call)
+      ln_qkv_routed(x, D, nA, L.attn_ln, L.qkv, D, qb, D, kc + (size_t)a0 * D, D, vc + (size_t)a0 * D, D, y, st);
       relpos_attention(qb, D, kc, D, vc, D, L.pos_proj, h->Tpos, L.pos_u, L.pos_v, att, 1, nA, a0, T, c.enc_heads, D, h->attn_chunk, nullptr, st);
       linear(att, D, nA, L.attn_out, ep_residual(x, D), st);
-      layer_norm(x, D, y, D, L.conv_ln.g, L.conv_ln.b, nA, D, st);
       {
         Epilogue ep = ep_out(gc + (size_t)a0 * D, D);
         ep.glu = 1;
-        linear(y, D, nA, L.pw1, ep, st);
+        ln_linear(x, D, nA, L.conv_ln, L.pw1, ep, y, st);
       }
       depthwise_bn_silu(gc, D, L.dw_w, L.bn_scale, L.bn_shift, dw, D, 1, T, a0, nA, D, c.dw_kernel, cc, st);
       linear(dw, D, nA, L.pw2, ep_residual(x, D), st);
-      layer_norm(x, D, y, D, L.ffn2_ln.g, L.ffn2_ln.b, nA, D, st);
-      linear(y, D, nA, L.ffn2_w1, ep_out(hid, c.enc_ffn, ACT_SILU), st);
+      ln_linear(x, D, nA, L.ffn2_ln, L.ffn2_w1, ep_out(hid, c.enc_ffn, ACT_SILU), y, st);
       linear(hid, c.enc_ffn, nA, L.ffn2_w2, ep_residual(x, D, 0.5f), st);
       layer_norm(x, D, x, D, L.final_ln.g, L.final_ln.b, nA, D, st);
     }

@@ -49,6 +49,16 @@ struct Epilogue {
   int out_L = 0;
   int out_row_stride = 1;
   int out_row_offset = 0;
+  // ---- skinny-GEMM-only fusions (engine checks skinny_gemm_supported before setting them)
+  // A := LayerNorm(A) over the K columns (eps 1e-5) applied while loading A; K must be the full row width
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  // column routing: columns [p*split_n, (p+1)*split_n) go to out / out2 / out3 (fused Q|K|V projections writing
+  // straight into the query buffer and the K / V caches)
+  int split_n = 0;
+  float* out2 = nullptr;
+  float* out3 = nullptr;
+  int ldo2 = 0, ldo3 = 0;
 };
 
 // C[M,N] = epilogue( A[M,K] * W[N,K]^T ), K = ksize*C_in, W row-major with K contiguous.

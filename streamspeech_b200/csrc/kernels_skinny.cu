@@ -37,7 +37,29 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
                                                                     int M, int N, int K, Epilogue ep) {
   constexpr int TASKS_PER_CTA = SK_WARPS / KS;
   __shared__ float part[SK_WARPS][CPT][MR];
+  __shared__ float ln_mean[64], ln_rstd[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool fuse_ln = ep.ln_gamma != nullptr;
+  if (fuse_ln) {
+    // row statistics with the same operation order as layer_norm_kernel (two-pass, lane-strided, shuffle tree)
+    for (int m = warp; m < M; m += SK_WARPS) {
+      const float* xr = A + (int64_t)m * lda;
+      float s = 0.f;
+      for (int c = lane; c < K; c += 32) s += xr[c];
+      float mean = warp_sum(s) / (float)K;
+      float ss_ = 0.f;
+      for (int c = lane; c < K; c += 32) {
+        float d = xr[c] - mean;
+        ss_ = fmaf(d, d, ss_);
+      }
+      float var = warp_sum(ss_) / (float)K;
+      if (lane == 0) {
+        ln_mean[m] = mean;
+        ln_rstd[m] = 1.0f / sqrtf(var + 1e-5f);
+      }
+    }
+    __syncthreads();
+  }
   const int slice = warp % KS, tslot = warp / KS;
   const int ntasks = N / CPT;
   const int kslice = K / KS;  // multiple of 128 (checked by the host)
@@ -59,10 +81,22 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
           float4 wv[CPT];
 #pragma unroll
           for (int c = 0; c < CPT; ++c) wv[c] = ld_stream(w0 + (int64_t)c * K + k);
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (fuse_ln) {
+            g4 = *reinterpret_cast<const float4*>(ep.ln_gamma + k);
+            b4 = *reinterpret_cast<const float4*>(ep.ln_beta + k);
+          }
 #pragma unroll
           for (int r = 0; r < MR; ++r) {
             if (mb + r < M) {
               float4 x = *reinterpret_cast<const float4*>(A + (int64_t)(mb + r) * lda + k);
+              if (fuse_ln) {
+                const float mu = ln_mean[mb + r], rs = ln_rstd[mb + r];
+                x.x = (x.x - mu) * rs * g4.x + b4.x;
+                x.y = (x.y - mu) * rs * g4.y + b4.y;
+                x.z = (x.z - mu) * rs * g4.z + b4.z;
+                x.w = (x.w - mu) * rs * g4.w + b4.w;
+              }
 #pragma unroll
               for (int c = 0; c < CPT; ++c) {
                 acc[c][r] = fmaf(x.x, wv[c].x, acc[c][r]);
@@ -114,10 +148,18 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
           y = ep.alpha * sk_act(mine[0] + (ep.bias ? ep.bias[n0] : 0.f), ep.act);
           oc = n0;
         }
-        int64_t o = (int64_t)m * ep.ldo + oc;
+        float* obase = ep.out;
+        int ld = ep.ldo;
+        if (ep.split_n > 0) {  // fused Q|K|V: route the column block to its own buffer
+          int p = oc / ep.split_n;
+          oc -= p * ep.split_n;
+          if (p == 1) { obase = ep.out2; ld = ep.ldo2; }
+          else if (p == 2) { obase = ep.out3; ld = ep.ldo3; }
+        }
+        int64_t o = (int64_t)m * ld + oc;
         if (ep.residual) y += ep.res_scale * ep.residual[o];
-        if (ep.accumulate) y += ep.out[o];
-        ep.out[o] = y;
+        if (ep.accumulate) y += obase[o];
+        obase[o] = y;
       }
       if (KS > 1) __syncthreads();  // `part` is reused by the next pass / task
     }
@@ -141,6 +183,7 @@ void launch_skinny(const float* A, int lda, const float* W, int M, int N, int K,
 
 bool skinny_gemm_supported(int M, int N, int K, const Epilogue& ep) {
   if (M < 1 || M > 64 || (K & 127) != 0 || ep.out_L > 0) return false;
+  if (ep.ln_gamma && K > 1024) return false;
   if (ep.glu && (N & 1)) return false;
   return true;
 }
