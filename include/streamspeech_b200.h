@@ -144,6 +144,11 @@ int ss_vocoder_receptive_field(const ss_engine* h);
 /* ---- single ops exported for the parity tests (same kernels the entry points above launch) ------------- */
 int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N,
                  int act, float* out_dev);
+/* same GEMM on the tcgen05 tensor-core kernel (bf16 operand splitting, pieces = 2 or 3); parity-test hook */
+int ss_op_linear_umma(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N,
+                      int act, int pieces, float* out_dev);
+/* engine options: "umma_vocoder" / "umma_linear" = 0 (fp32 CUDA cores), 2 or 3 (tcgen05, bf16 pieces per operand) */
+int ss_set_option(ss_engine* h, const char* name, int value);
 int ss_op_layer_norm(ss_engine* h, void* stream, const float* x_dev, int rows, int C, const float* g_dev, const float* b_dev,
                      float* out_dev);
 

@@ -84,6 +84,8 @@ struct ss_engine {
   std::string err;
   bool finalized = false;
   int attn_chunk = 8, conv_chunk = 8;
+  int umma_vocoder = 0;   // 0 = fp32 CUDA-core convs, 2 / 3 = tcgen05 with that many bf16 pieces per operand
+  int umma_linear = 0;    // same for large-M linears (unit decoder, T2U, MT prefill, full-prefix encoder)
   std::map<std::string, ss::HostTensor> host;  // loaded tensors by key
   std::vector<void*> dev_allocs;
 

@@ -18,6 +18,18 @@ int check_launch(ss_engine* h, const char* where) {
   return SS_OK;
 }
 
+// tensor-core routing of the current entry point (set from the handle at the top of each entry point)
+thread_local int g_umma_linear = 0;
+thread_local int g_umma_conv = 0;
+
+// conv-as-GEMM dispatch: tcgen05 split-bf16 kernel for large tiles when enabled, fp32 CUDA-core kernel otherwise
+void conv_gemm(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaStream_t st) {
+  if (g_umma_conv >= 2 && a.B * a.L_rows >= 128 && umma_gemm_supported(a, N, ep))
+    umma_gemm_conv(a, W, N, ep, g_umma_conv, st);
+  else
+    gemm_conv(a, W, N, ep, st);
+}
+
 // plain linear: out[M][N] = epilogue(x[M][K] @ W^T)
 void linear(const float* x, int ldx, int M, const Linear& l, Epilogue ep, cudaStream_t st) {
   ConvA a;
@@ -25,6 +37,8 @@ void linear(const float* x, int ldx, int M, const Linear& l, Epilogue ep, cudaSt
   ep.bias = l.b;
   if (skinny_gemm_supported(M, l.N, l.K, ep) && (ldx & 3) == 0)
     skinny_gemm(x, ldx, l.w, M, l.N, l.K, ep, st);
+  else if (g_umma_linear >= 2 && M >= 128 && (ldx & 3) == 0 && umma_gemm_supported(a, l.N, ep))
+    umma_gemm_conv(a, l.w, l.N, ep, g_umma_linear, st);
   else
     gemm_conv(a, l.w, l.N, ep, st);
 }
@@ -187,6 +201,7 @@ int ss_fbank(ss_engine* h, void* stream, const float* samples_dev, int64_t n_sam
 }
 
 int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const int32_t* lengths_host, int B, int F, float* out_dev) {
+  if (h) g_umma_linear = h->umma_linear;
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   if (B <= 0 || F <= 0) return h->fail(SS_ERR_INVALID, "empty encoder input");
   const ss_config& c = h->cfg;
@@ -285,6 +300,7 @@ int ss_encoder_stream_reset(ss_engine* h) {
 }
 
 int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, int F, float* enc_out_dev, int32_t* T_out, int32_t* T_final_out) {
+  if (h) g_umma_linear = h->umma_linear;
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   if (h->attn_chunk <= 0 || h->conv_chunk <= 0) return h->fail(SS_ERR_STATE, "streaming encoder needs a chunked model (ss_set_chunk)");
   const ss_config& c = h->cfg;
@@ -362,6 +378,7 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
 
 int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev, int64_t* tokens_dev,
                   int32_t* index_dev, int32_t* count_dev) {
+  if (h) g_umma_linear = h->umma_linear;
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   if (head < 0 || head > 1 || rows <= 0) return h->fail(SS_ERR_INVALID, "bad ctc head / rows");
   const Linear& l = h->ctc_head[head];
@@ -376,6 +393,7 @@ int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, in
 
 int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* tokens_host, int n, float* feats_out_dev,
                    float* logits_last_dev) {
+  if (h) g_umma_linear = h->umma_linear;
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   const ss_config& c = h->cfg;
   if (n <= 0 || n > c.max_mt_positions || T <= 0) return h->fail(SS_ERR_INVALID, "bad MT sequence length");
@@ -409,6 +427,7 @@ int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, cons
 
 int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* prefix_host, int n_prefix, int max_new_tokens,
                  int max_len_b, int64_t* tokens_out_host, int max_out, int* n_out, float* feats_out_dev) {
+  if (h) g_umma_linear = h->umma_linear;
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   const ss_config& c = h->cfg;
   cudaStream_t st = S(stream);
@@ -487,6 +506,7 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
 
 int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, int Slen, int n_pad_tail, int mask_eos, int64_t* argmax_dev,
                        int64_t* units_dev, int32_t* count_dev, float* t2u_out_dev, float* logits_dev) {
+  if (h) g_umma_linear = h->umma_linear;
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   const ss_config& c = h->cfg;
   cudaStream_t st = S(stream);
@@ -587,6 +607,7 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
   if (n_frames <= 0 || frame0 < 0 || frame0 + n_frames != total_frames) return h->fail(SS_ERR_INVALID, "vocoder frame range must be the tail of the sequence");
   const ss_config& c = h->cfg;
   cudaStream_t st = S(stream);
+  g_umma_conv = h->umma_vocoder;
   int ctx = left_context < 0 ? h->receptive_field : left_context;
   ctx = std::min(ctx, frame0);
   const int f_lo = frame0 - ctx;
@@ -621,7 +642,7 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
     a.x = frames; a.B = 1; a.L_in = N; a.L_rows = N; a.C_in = c.voc_in_dim; a.ldx = c.voc_in_dim; a.ksize = 7; a.pad_left = 3;
     Epilogue e = ep_out(bufX, c.voc_init_channels);
     e.bias = h->conv_pre.lin.b;
-    gemm_conv(a, h->conv_pre.lin.w, c.voc_init_channels, e, st);
+    conv_gemm(a, h->conv_pre.lin.w, c.voc_init_channels, e, st);
   }
   int L = N, ch = c.voc_init_channels;
   for (int i = 0; i < c.voc_n_ups; ++i) {
@@ -639,7 +660,7 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
       Epilogue e = ep_out(bufY, U.cout);
       e.bias = U.bias;
       e.out_L = Lout; e.out_row_stride = U.u; e.out_row_offset = q0 * U.u + phi - U.pad;
-      gemm_conv(a, U.phase_w[phi].w, U.cout, e, st);
+      conv_gemm(a, U.phase_w[phi].w, U.cout, e, st);
     }
     L = Lout;
     ch = U.cout;
@@ -656,7 +677,7 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
         a1.pad_left = (w1.ksize * w1.dil - w1.dil) / 2; a1.pre_lrelu = 0.1f;
         Epilogue e1 = ep_out(bufT, ch);
         e1.bias = w1.lin.b;
-        gemm_conv(a1, w1.lin.w, ch, e1, st);
+        conv_gemm(a1, w1.lin.w, ch, e1, st);
         ConvA a2;
         a2.x = bufT; a2.B = 1; a2.L_in = L; a2.L_rows = L; a2.C_in = ch; a2.ldx = ch; a2.ksize = w2.ksize; a2.dil = 1;
         a2.pad_left = (w2.ksize - 1) / 2; a2.pre_lrelu = 0.1f;
@@ -676,7 +697,7 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
           e2.accumulate = (j > 0);
         }
         // NB: residual and out must not alias for the accumulate form; cur is bufY/bufA/bufB, out is bufX or the other ping-pong
-        gemm_conv(a2, w2.lin.w, ch, e2, st);
+        conv_gemm(a2, w2.lin.w, ch, e2, st);
         cur = e2.out;
       }
     }
@@ -685,6 +706,27 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
   conv_post_tanh(bufX, L, ch, h->conv_post_w, h->conv_post_b, h->conv_post_k, 0.01f, wav, st);
   copy_f32(wav + (size_t)ctx * h->hop, wav_out_dev, (int64_t)n_frames * h->hop, st);
   return check_launch(h, "ss_vocoder_generate");
+}
+
+int ss_set_option(ss_engine* h, const char* name, int value) {
+  if (!h || !name) return SS_ERR_INVALID;
+  std::string n(name);
+  if (n == "umma_vocoder") h->umma_vocoder = value;
+  else if (n == "umma_linear") h->umma_linear = value;
+  else return h->fail(SS_ERR_INVALID, "unknown option " + n);
+  return SS_OK;
+}
+
+int ss_op_linear_umma(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N, int act,
+                      int pieces, float* out_dev) {
+  if (!h) return SS_ERR_INVALID;
+  ConvA a;
+  a.x = x_dev; a.B = 1; a.L_in = M; a.L_rows = M; a.C_in = K; a.ldx = K;
+  Epilogue ep = ep_out(out_dev, N, act);
+  ep.bias = bias_dev;
+  if (!umma_gemm_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 GEMM");
+  umma_gemm_conv(a, w_dev, N, ep, pieces, S(stream));
+  return check_launch(h, "ss_op_linear_umma");
 }
 
 int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N, int act,

@@ -64,6 +64,11 @@ struct Epilogue {
 // C[M,N] = epilogue( A[M,K] * W[N,K]^T ), K = ksize*C_in, W row-major with K contiguous.
 void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaStream_t st);
 
+// tcgen05 tensor-core GEMM with bf16 operand splitting (pieces = 2: 3 MMAs, ~2^-16 relative; pieces = 3: 6 MMAs,
+// ~fp32), same ConvA / Epilogue contract as gemm_conv.  See kernels_umma.cu.
+bool umma_gemm_supported(const ConvA& a, int N, const Epilogue& ep);
+void umma_gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, int pieces, cudaStream_t st);
+
 // Weight-streaming GEMM for M <= 64 rows (plain row-major A): one warp per output column, see kernels_skinny.cu.
 bool skinny_gemm_supported(int M, int N, int K, const Epilogue& ep);
 void skinny_gemm(const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st);

@@ -77,6 +77,8 @@ def load_library() -> ctypes.CDLL:
     lib.ss_vocoder_hop.argtypes = [vp]
     lib.ss_vocoder_receptive_field.argtypes = [vp]
     lib.ss_op_linear.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, vp]
+    lib.ss_op_linear_umma.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, vp]
+    lib.ss_set_option.argtypes = [vp, ctypes.c_char_p, i32]
     lib.ss_op_layer_norm.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     lib.ss_launch_count.argtypes = [vp]
     lib.ss_launch_count.restype = i64
@@ -88,7 +90,7 @@ EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_mt_greedy",
     "ss_mt_features", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
-    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_layer_norm", "ss_launch_count",
+    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_set_option", "ss_op_layer_norm", "ss_launch_count",
 ]
 
 
@@ -317,6 +319,16 @@ class Engine:
         out = self._f32(M, N)
         self._check(self.lib.ss_op_linear(self._h, self._stream(), x.data_ptr(), M, K, w.data_ptr(), self._ptr(b), N, act, out.data_ptr()))
         return out
+
+    def op_linear_umma(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: int = 0, pieces: int = 3) -> torch.Tensor:
+        M, K = x.shape
+        N = w.shape[0]
+        out = self._f32(M, N)
+        self._check(self.lib.ss_op_linear_umma(self._h, self._stream(), x.data_ptr(), M, K, w.data_ptr(), self._ptr(b), N, act, pieces, out.data_ptr()))
+        return out
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.ss_set_option(self._h, name.encode(), int(value)))
 
     def op_layer_norm(self, x: torch.Tensor, g: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         out = torch.empty_like(x)
