@@ -64,6 +64,10 @@ struct Epilogue {
 // C[M,N] = epilogue( A[M,K] * W[N,K]^T ), K = ksize*C_in, W row-major with K contiguous.
 void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaStream_t st);
 
+// split-K scratch (one per process; launches of a handle are stream-ordered) and its fixed-order reduce + epilogue
+float* splitk_workspace(size_t bytes);
+void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, const Epilogue& ep, cudaStream_t st);
+
 // tcgen05 tensor-core GEMM with bf16 operand splitting (pieces = 2: 3 MMAs, ~2^-16 relative; pieces = 3: 6 MMAs,
 // ~fp32), same ConvA / Epilogue contract as gemm_conv.  See kernels_umma.cu.
 bool umma_gemm_supported(const ConvA& a, int N, const Epilogue& ep);

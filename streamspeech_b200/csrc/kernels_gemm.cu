@@ -248,6 +248,28 @@ float* g_splitk_ws = nullptr;
 size_t g_splitk_cap = 0;
 constexpr size_t SPLITK_WS_BYTES = 32u << 20;
 
+}  // namespace
+
+float* splitk_workspace(size_t bytes) {
+  if (bytes > SPLITK_WS_BYTES) return nullptr;
+  if (!g_splitk_ws) {
+    if (cudaMalloc((void**)&g_splitk_ws, SPLITK_WS_BYTES) != cudaSuccess) {
+      g_splitk_ws = nullptr;
+      return nullptr;
+    }
+    g_splitk_cap = SPLITK_WS_BYTES;
+  }
+  return g_splitk_ws;
+}
+
+void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, const Epilogue& ep, cudaStream_t st) {
+  ++g_launches;
+  int total = M * (ep.glu ? N / 2 : N);
+  splitk_epilogue_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, splits, M, N, L_rows, ep);
+}
+
+namespace {
+
 template <int BM, int BN>
 void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue& ep, bool conv, cudaStream_t st) {
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);

@@ -20,6 +20,8 @@
 // Two smem stages are used so that the gather of tile k+1 overlaps the MMAs of tile k.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -28,7 +30,7 @@ namespace {
 
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;
-constexpr int UM_NT = 128;
+constexpr int UM_NT = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -126,8 +128,11 @@ __device__ __forceinline__ float4 load_a4_conv(const ConvA& a, int m, int kk, in
 }
 
 // NP = bf16 pieces per operand (2 -> 3 MMAs, 3 -> 6 MMAs)
+// gridDim.z > 1: split-K, slice z covers k-tiles [z*tiles_per_split, ...) and stores raw partial sums to ws[z][M][N]
+// (reduced in a fixed order by splitk_epilogue, which also bounds the length of each tensor-core accumulation chain).
 template <int BN, int NP>
-__global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* __restrict__ W, int M, int N, int K, Epilogue ep) {
+__global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* __restrict__ W, int M, int N, int K, Epilogue ep,
+                                                          int tiles_per_split, float* __restrict__ ws) {
   constexpr int A_TILE = UM_BM * UM_BK * 2;  // bytes of one bf16 piece of the A tile
   constexpr int B_TILE = BN * UM_BK * 2;
   constexpr int STAGE = NP * (A_TILE + B_TILE);
@@ -154,8 +159,14 @@ __global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* 
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = make_idesc(BN);
 
-  const int nk = (K + UM_BK - 1) / UM_BK;
+  const int nk_all = (K + UM_BK - 1) / UM_BK;
+  const int kt0 = blockIdx.z * tiles_per_split;
+  const int nk = min(nk_all, kt0 + tiles_per_split) - kt0;
   uint32_t phase[2] = {0, 0};
+  // per-thread staging assignment is the same for every k-tile: rows r = (tid>>3) + 32*i, quad q = tid&7
+  constexpr int A_IT = UM_BM * (UM_BK / 4) / UM_NT;  // 4
+  constexpr int B_IT = (BN * (UM_BK / 4) + UM_NT - 1) / UM_NT;
+  const int q = tid & 7;
   for (int kt = 0; kt < nk; ++kt) {
     const int st = kt & 1;
     unsigned char* sbase = smem + st * STAGE;
@@ -170,23 +181,30 @@ __global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* 
       a_piece[p] = sbase + p * A_TILE;
       b_piece[p] = sbase + NP * A_TILE + p * B_TILE;
     }
-    const int k0 = kt * UM_BK;
-    // ---- stage A: 128 rows x 8 quads
-#pragma unroll 4
-    for (int i = tid; i < UM_BM * (UM_BK / 4); i += UM_NT) {
-      int r = i >> 3, q = i & 7;
-      float4 v = load_a4_conv(a, m0 + r, k0 + q * 4, M, K);
-      uint32_t off = (uint32_t)(((q >> 1) * (UM_BM / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (q & 1) * 8);
-      split_store<NP>(v, a_piece, off);
-    }
-    // ---- stage W: BN rows x 8 quads
-#pragma unroll 4
-    for (int i = tid; i < BN * (UM_BK / 4); i += UM_NT) {
-      int r = i >> 3, q = i & 7;
+    const int k0 = (kt0 + kt) * UM_BK;
+    // ---- issue all global loads of this tile first (A_IT + B_IT independent 128-bit loads per thread in flight)
+    float4 va[A_IT], vb[B_IT];
+#pragma unroll
+    for (int i = 0; i < A_IT; ++i) va[i] = load_a4_conv(a, m0 + (tid >> 3) + 32 * i, k0 + q * 4, M, K);
+#pragma unroll
+    for (int i = 0; i < B_IT; ++i) {
+      int r = (tid >> 3) + 32 * i;
       int n = n0 + r, kk = k0 + q * 4;
-      float4 v = (n < N && kk < K) ? *reinterpret_cast<const float4*>(W + (int64_t)n * K + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
-      uint32_t off = (uint32_t)(((q >> 1) * (BN / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (q & 1) * 8);
-      split_store<NP>(v, b_piece, off);
+      vb[i] = (r < BN && n < N && kk < K) ? *reinterpret_cast<const float4*>(W + (int64_t)n * K + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < A_IT; ++i) {
+      int r = (tid >> 3) + 32 * i;
+      uint32_t off = (uint32_t)(((q >> 1) * (UM_BM / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (q & 1) * 8);
+      split_store<NP>(va[i], a_piece, off);
+    }
+#pragma unroll
+    for (int i = 0; i < B_IT; ++i) {
+      int r = (tid >> 3) + 32 * i;
+      if (r < BN) {
+        uint32_t off = (uint32_t)(((q >> 1) * (BN / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (q & 1) * 8);
+        split_store<NP>(vb[i], b_piece, off);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
@@ -221,8 +239,13 @@ __global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* 
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue: thread (warp, lane) owns output row m0 + 32*warp + lane
-  const int m = m0 + warp * 32 + lane;
+  // ---- epilogue: warp w reads TMEM lane quadrant (w & 3) = output rows m0 + 32*(w&3) + lane; the two warpgroups
+  // split the columns
+  const int quad = warp & 3;
+  const int m = m0 + quad * 32 + lane;
+  constexpr int COLS_PER_GROUP = BN >= 32 ? BN / 2 : BN;
+  const int c_begin = (BN >= 32) ? (warp >> 2) * COLS_PER_GROUP : 0;
+  const bool epi_active = (BN >= 32) || warp < 4;
   int64_t orow = m;
   if (ep.out_L > 0 && m < M) {
     int b = m / a.L_rows;
@@ -230,9 +253,9 @@ __global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* 
     orow = (int64_t)b * ep.out_L + (int64_t)t * ep.out_row_stride + ep.out_row_offset;
   }
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 16) {
+  for (int c0 = c_begin; epi_active && c0 < c_begin + COLS_PER_GROUP; c0 += 16) {
     uint32_t r[16];
-    uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
@@ -240,6 +263,17 @@ __global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* 
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (ws != nullptr) {  // split-K: raw partial sums
+      if (m < M) {
+        float* wz = ws + ((int64_t)blockIdx.z * M + m) * N;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int n = n0 + c0 + j;
+          if (n < N) wz[n] = __uint_as_float(r[j]);
+        }
+      }
+      continue;
+    }
     if (m < M) {
       float* orow_p = ep.out + orow * ep.ldo;
       const float* rrow_p = ep.residual ? ep.residual + orow * ep.ldo : nullptr;
@@ -286,7 +320,25 @@ void launch_umma(const ConvA& a, const float* W, int M, int N, int K, const Epil
     configured = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + UM_BM - 1) / UM_BM);
-  umma_gemm_kernel<BN, NP><<<grid, UM_NT, smem, st>>>(a, W, M, N, K, ep);
+  const long ctas = (long)grid.x * grid.y;
+  const int nk = (K + UM_BK - 1) / UM_BK;
+  int splits = 1;
+  float* ws = nullptr;
+  if (ctas < 148 && nk >= 8) {
+    splits = (int)std::min<long>((148 + ctas - 1) / ctas, nk / 4);
+    ws = splitk_workspace((size_t)splits * M * N * sizeof(float));
+    if (!ws) splits = 1;
+  }
+  int tiles = nk;
+  if (splits > 1) {
+    tiles = (nk + splits - 1) / splits;
+    splits = (nk + tiles - 1) / tiles;
+    grid.z = splits;
+  } else {
+    ws = nullptr;
+  }
+  umma_gemm_kernel<BN, NP><<<grid, UM_NT, smem, st>>>(a, W, M, N, K, ep, tiles, ws);
+  if (splits > 1) splitk_epilogue(ws, splits, M, N, a.L_rows, ep, st);
 }
 
 }  // namespace

@@ -25,7 +25,7 @@ for (M, K, N, act) in [(128, 32, 16, 0), (128, 64, 128, 0), (256, 96, 32, 1), (3
         got = e.op_linear_umma(x.cuda(), w.cuda(), b.cuda(), act, pieces).cpu()
         d = float((got - ref).abs().max()); d32 = float((f32 - ref).abs().max())
         res[f"gemm_{M}x{K}x{N}_act{act}_p{pieces}"] = {"umma_maxdiff": d, "fp32_simt_maxdiff": d32}
-        tol = 3e-5 if pieces == 3 else 2e-3
+        tol = 2e-4 if pieces == 3 else 2e-3
         if not d < tol:
             ok = False
         print(M, K, N, act, "pieces", pieces, "maxdiff", d, "(fp32 SIMT:", d32, ")", "OK" if d < tol else "FAIL")
