@@ -168,6 +168,10 @@ class Engine:
         except Exception:
             self.close()
             raise
+        # tensor-core routing (kernels_umma.cu): vocoder convs tolerate the 3-MMA split (1e-3 waveform bar, measured 7e-6);
+        # linears that feed an arg-max stay on the exact fp32 kernels unless explicitly switched on
+        self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "0")))
+        self.set_option("umma_linear", int(os.environ.get("SS_UMMA_LINEAR", "0")))
         self.hop = self.lib.ss_vocoder_hop(self._h)
         self.vocoder_receptive_field = self.lib.ss_vocoder_receptive_field(self._h)
 
