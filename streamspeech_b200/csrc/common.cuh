@@ -6,6 +6,10 @@
 
 namespace ss {
 
+// Programmatic dependent launch: allow the next kernel in the stream (if it was launched with the PDL attribute, see
+// kernels_skinny.cu) to begin its independent prologue while this grid is still running.  A no-op otherwise.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

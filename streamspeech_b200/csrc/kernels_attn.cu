@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_tile_kernel(const float* __restri
                                                            float* __restrict__ out, int ldo, int nQ, int q_offset, int T, float scale,
                                                            int chunk, int causal, int causal_offset, const int* __restrict__ lengths) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   float* Qa = smem;                          // [QT][LDK]  (q+u) or scaled q
   float* Qb = Qa + QT * LDK;                 // [QT][LDK]  (q+v)           (RELPOS only)
   float* Ks = Qb + (RELPOS ? QT * LDK : 0);  // [KT][LDK]
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_row_kernel(const float* __restric
                                                           float* __restrict__ out, int ldo, int nQ, int q_offset, int T, float scale,
                                                           int chunk, int causal, int causal_offset, const int* __restrict__ lengths) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   float* S = smem;  // [T]
   __shared__ __align__(16) float qa[HD], qb2[HD];
   __shared__ __align__(16) float part[4][HD];

@@ -13,6 +13,7 @@ template <int N>  // N = C / 32
 __global__ void layer_norm_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
   constexpr int C = N * 32;
+  pdl_trigger();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -44,6 +45,7 @@ __global__ void layer_norm_kernel(const float* __restrict__ x, int ldx, float* _
 __global__ void depthwise_bn_silu_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                          float* __restrict__ y, int ldy, int T, int t0, int n, int C, int k, int chunk) {
+  pdl_trigger();
   int row = blockIdx.x;  // b*n + r
   int b = row / n, t = t0 + (row - b * n);
   int half = (k - 1) >> 1;
@@ -75,6 +77,7 @@ __global__ void copy_kernel(const float* __restrict__ s, float* __restrict__ d, 
 __global__ void embed_tokens_pos_kernel(const int64_t* __restrict__ tokens, const int* __restrict__ positions, int pos_offset,
                                         const float* __restrict__ emb, const float* __restrict__ pos_table, float scale,
                                         float* __restrict__ out, int rows, int C, int pad_idx) {
+  pdl_trigger();
   int r = blockIdx.x;
   int64_t tok = tokens[r];
   // make_positions (fairseq/utils.py:256-266) for sequences whose pads are trailing:

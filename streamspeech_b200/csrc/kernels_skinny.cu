@@ -40,6 +40,26 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
   __shared__ float ln_mean[64], ln_rstd[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool fuse_ln = ep.ln_gamma != nullptr;
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue now, and fetch this
+  // warp's first slice of W (weights do not depend on the previous kernel) BEFORE waiting for the previous kernel's
+  // results -- the weight-fetch latency of GEMM i+1 hides behind the execution of GEMM i.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  constexpr int PF = 2;  // prefetched 128-bit W loads per column and lane
+  float4 wpre[CPT][PF];
+  {
+    const int slice_ = warp % KS, tslot_ = warp / KS;
+    const int kslice_ = K / KS;
+    const int task_ = blockIdx.x * (SK_WARPS / KS) + tslot_;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        int k = slice_ * kslice_ + lane * 4 + i * 128;
+        wpre[c][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (task_ < N / CPT && k < (slice_ + 1) * kslice_) wpre[c][i] = ld_stream(W + ((int64_t)task_ * CPT + c) * K + k);
+      }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (fuse_ln) {
     // row statistics with the same operation order as layer_norm_kernel (two-pass, lane-strided, shuffle tree)
     for (int m = warp; m < M; m += SK_WARPS) {
@@ -76,11 +96,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
         for (int r = 0; r < MR; ++r) acc[c][r] = 0.f;
       if (active) {
         const float* w0 = W + (int64_t)n0 * K;
-#pragma unroll 2
-        for (int k = k_lo + lane * 4; k < k_hi; k += 128) {
-          float4 wv[CPT];
-#pragma unroll
-          for (int c = 0; c < CPT; ++c) wv[c] = ld_stream(w0 + (int64_t)c * K + k);
+        const bool first = (tbase == blockIdx.x * TASKS_PER_CTA) && mb == 0;
+        auto step = [&](int k, const float4* wv) {
           float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (fuse_ln) {
             g4 = *reinterpret_cast<const float4*>(ep.ln_gamma + k);
@@ -106,6 +123,23 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
               }
             }
           }
+        };
+        int k = k_lo + lane * 4;
+#pragma unroll
+        for (int i = 0; i < PF; ++i, k += 128) {
+          if (k < k_hi) {
+            float4 wv[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) wv[c] = first ? wpre[c][i] : ld_stream(w0 + (int64_t)c * K + k);
+            step(k, wv);
+          }
+        }
+#pragma unroll 2
+        for (; k < k_hi; k += 128) {
+          float4 wv[CPT];
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) wv[c] = ld_stream(w0 + (int64_t)c * K + k);
+          step(k, wv);
         }
       }
       // lane r ends up holding the warp total of row r
@@ -173,10 +207,20 @@ void launch_skinny(const float* A, int lda, const float* W, int M, int N, int K,
   const int per_cta = SK_WARPS / KS;
   int grid = (ntasks + per_cta - 1) / per_cta;
   if (grid > 148 * 8) grid = 148 * 8;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(SK_WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (ep.glu)
-    skinny_gemm_kernel<MR, KS, 2><<<grid, SK_WARPS * 32, 0, st>>>(A, lda, W, M, N, K, ep);
+    cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<MR, KS, 2>, A, lda, W, M, N, K, ep);
   else
-    skinny_gemm_kernel<MR, KS, 1><<<grid, SK_WARPS * 32, 0, st>>>(A, lda, W, M, N, K, ep);
+    cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<MR, KS, 1>, A, lda, W, M, N, K, ep);
 }
 
 }  // namespace
