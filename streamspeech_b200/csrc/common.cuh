@@ -9,6 +9,26 @@ namespace ss {
 // Programmatic dependent launch: allow the next kernel in the stream (if it was launched with the PDL attribute, see
 // kernels_skinny.cu) to begin its independent prologue while this grid is still running.  A no-op otherwise.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ... and the matching wait: everything the previous kernels of the stream wrote is visible after it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// launch with programmatic stream serialization: the grid may be scheduled while its predecessor is still running; every
+// kernel launched this way calls pdl_wait() before it touches memory (so semantics equal a normal launch, minus the
+// launch / scheduling latency that now overlaps the predecessor)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

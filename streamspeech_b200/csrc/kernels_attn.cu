@@ -52,8 +52,9 @@ __global__ void __launch_bounds__(ATT_NT) attn_tile_kernel(const float* __restri
                                                            int ldp, const float* __restrict__ bias_u, const float* __restrict__ bias_v,
                                                            float* __restrict__ out, int ldo, int nQ, int q_offset, int T, float scale,
                                                            int chunk, int causal, int causal_offset, const int* __restrict__ lengths) {
-  extern __shared__ __align__(16) float smem[];
   pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
   float* Qa = smem;                          // [QT][LDK]  (q+u) or scaled q
   float* Qb = Qa + QT * LDK;                 // [QT][LDK]  (q+v)           (RELPOS only)
   float* Ks = Qb + (RELPOS ? QT * LDK : 0);  // [KT][LDK]
@@ -193,8 +194,9 @@ __global__ void __launch_bounds__(ATT_NT) attn_row_kernel(const float* __restric
                                                           int ldp, const float* __restrict__ bias_u, const float* __restrict__ bias_v,
                                                           float* __restrict__ out, int ldo, int nQ, int q_offset, int T, float scale,
                                                           int chunk, int causal, int causal_offset, const int* __restrict__ lengths) {
-  extern __shared__ __align__(16) float smem[];
   pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];
   float* S = smem;  // [T]
   __shared__ __align__(16) float qa[HD], qb2[HD];
   __shared__ __align__(16) float part[4][HD];
@@ -266,7 +268,7 @@ void launch_attn(const float* q, int ldq, const float* k, int ldk, const float* 
       cudaFuncSetAttribute(attn_row_kernel<RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       configured_row = 160 * 1024;
     }
-    attn_row_kernel<RELPOS><<<dim3(nQ, H, B), ATT_NT, smem_row, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo, nQ,
+    launch_pdl(attn_row_kernel<RELPOS>, dim3(dim3(nQ, H, B)), dim3(ATT_NT), smem_row, st, q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo, nQ,
                                                                       q_offset, T, scale, chunk, causal, causal_offset, lengths);
     return;
   }
@@ -276,7 +278,7 @@ void launch_attn(const float* q, int ldq, const float* k, int ldk, const float* 
     cudaFuncSetAttribute(attn_tile_kernel<RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  attn_tile_kernel<RELPOS><<<dim3((nQ + QT - 1) / QT, H, B), ATT_NT, smem, st>>>(q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo,
+  launch_pdl(attn_tile_kernel<RELPOS>, dim3(dim3((nQ + QT - 1) / QT, H, B)), dim3(ATT_NT), smem, st, q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo,
                                                                                  nQ, q_offset, T, scale, chunk, causal, causal_offset, lengths);
 }
 

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ sa
                                                     const float* __restrict__ mel_bank, const float* __restrict__ window,
                                                     const float* __restrict__ cmvn_mean, const float* __restrict__ cmvn_std,
                                                     float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float re[NFFT], im[NFFT];
   __shared__ float twc[NFFT / 2], tws[NFFT / 2];
   __shared__ float frame[FRAME];
@@ -87,7 +89,7 @@ void fbank_cmvn(const float* samples, int64_t n_samples, int f0, int nf, const f
                 const float* cmvn_mean, const float* /*unused*/, const float* cmvn_std, float* out, cudaStream_t st) {
   ++g_launches;
   if (nf <= 0) return;
-  fbank_kernel<<<nf, 256, 0, st>>>(samples, n_samples, f0, mel_bank, window, cmvn_mean, cmvn_std, out);
+  launch_pdl(fbank_kernel, dim3(nf), dim3(256), 0, st, samples, n_samples, f0, mel_bank, window, cmvn_mean, cmvn_std, out);
 }
 
 }  // namespace ss

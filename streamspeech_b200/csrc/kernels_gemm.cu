@@ -62,6 +62,8 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 template <int BM, int BN, bool CONV>
 __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restrict__ W, int M, int N, int K, Epilogue ep,
                                                   int tiles_per_split, float* __restrict__ ws) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int TM = BM / 16;
   constexpr int TN = BN / 16;
   constexpr int A_F4 = BM * BK / 4;  // float4 loads per A tile
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restri
 }
 
 __global__ void splitk_epilogue_kernel(const float* __restrict__ ws, int splits, int M, int N, int L_rows, Epilogue ep) {
+  pdl_trigger();
+  pdl_wait();
   const int ncols = ep.glu ? N / 2 : N;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * ncols) return;
@@ -265,7 +269,7 @@ float* splitk_workspace(size_t bytes) {
 void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, const Epilogue& ep, cudaStream_t st) {
   ++g_launches;
   int total = M * (ep.glu ? N / 2 : N);
-  splitk_epilogue_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, splits, M, N, L_rows, ep);
+  launch_pdl(splitk_epilogue_kernel, dim3((total + 255) / 256), dim3(256), 0, st, ws, splits, M, N, L_rows, ep);
 }
 
 namespace {
@@ -295,13 +299,13 @@ void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue&
     ws = g_splitk_ws;
   }
   if (conv)
-    gemm_kernel<BM, BN, true><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);
+    launch_pdl(gemm_kernel<BM, BN, true>, dim3(grid), dim3(NT), 0, st, a, W, M, N, K, ep, tiles, ws);
   else
-    gemm_kernel<BM, BN, false><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);
+    launch_pdl(gemm_kernel<BM, BN, false>, dim3(grid), dim3(NT), 0, st, a, W, M, N, K, ep, tiles, ws);
   if (splits > 1) {
     ++g_launches;
     int total = M * (ep.glu ? N / 2 : N);
-    splitk_epilogue_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, splits, M, N, a.L_rows, ep);
+    launch_pdl(splitk_epilogue_kernel, dim3((total + 255) / 256), dim3(256), 0, st, ws, splits, M, N, a.L_rows, ep);
   }
 }
 

@@ -12,8 +12,9 @@ namespace {
 template <int N>  // N = C / 32
 __global__ void layer_norm_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
-  constexpr int C = N * 32;
   pdl_trigger();
+  pdl_wait();
+  constexpr int C = N * 32;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -46,6 +47,7 @@ __global__ void depthwise_bn_silu_kernel(const float* __restrict__ x, int ldx, c
                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                          float* __restrict__ y, int ldy, int T, int t0, int n, int C, int k, int chunk) {
   pdl_trigger();
+  pdl_wait();
   int row = blockIdx.x;  // b*n + r
   int b = row / n, t = t0 + (row - b * n);
   int half = (k - 1) >> 1;
@@ -65,11 +67,15 @@ __global__ void depthwise_bn_silu_kernel(const float* __restrict__ x, int ldx, c
 }
 
 __global__ void scale_kernel(float* x, int64_t n, float s) {
+  pdl_trigger();
+  pdl_wait();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] *= s;
 }
 
 __global__ void copy_kernel(const float* __restrict__ s, float* __restrict__ d, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = s[i];
 }
@@ -78,6 +84,7 @@ __global__ void embed_tokens_pos_kernel(const int64_t* __restrict__ tokens, cons
                                         const float* __restrict__ emb, const float* __restrict__ pos_table, float scale,
                                         float* __restrict__ out, int rows, int C, int pad_idx) {
   pdl_trigger();
+  pdl_wait();
   int r = blockIdx.x;
   int64_t tok = tokens[r];
   // make_positions (fairseq/utils.py:256-266) for sequences whose pads are trailing:
@@ -89,6 +96,8 @@ __global__ void embed_tokens_pos_kernel(const int64_t* __restrict__ tokens, cons
 
 __global__ void repeat_rows_add_kernel(const float* __restrict__ x, int S, int R, int C, const float* __restrict__ addvec,
                                        float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   int r = blockIdx.x;  // output row s*R + rr
   int s = r / R;
   const float* xr = x + (int64_t)s * C;
@@ -101,6 +110,8 @@ __global__ void repeat_rows_add_kernel(const float* __restrict__ x, int S, int R
 // (CTCDecoder.generate, agent/ctc_decoder.py:53-62; F.log_softmax = (x - max) - log(sum(exp(x - max))))
 __global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ masked, int n_masked,
                                    int64_t* __restrict__ out_idx, float* __restrict__ out_lprob) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   __shared__ float sval[32];
   __shared__ int sidx[32];
@@ -158,6 +169,8 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int
 
 __global__ void ctc_collapse_kernel(const int64_t* __restrict__ am, int n, int blank, int pad, int64_t* __restrict__ toks,
                                     int* __restrict__ index, int* __restrict__ count) {
+  pdl_trigger();
+  pdl_wait();
   // one CTA of 1024 threads; thread t owns the contiguous slice [t*per, (t+1)*per); block-wide exclusive scan of the keep counts
   __shared__ int wsum[32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -200,12 +213,16 @@ __global__ void ctc_collapse_kernel(const int64_t* __restrict__ am, int n, int b
 
 __global__ void gather_rows_kernel(const int64_t* __restrict__ idx, int idx_offset, const float* __restrict__ table, int C,
                                    float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   int r = blockIdx.x;
   int64_t t = idx[r] + idx_offset;
   for (int c = threadIdx.x; c < C; c += blockDim.x) out[(int64_t)r * C + c] = table[t * C + c];
 }
 
 __global__ void duration_kernel(const float* __restrict__ logdur, int n, int64_t* __restrict__ dur, int* __restrict__ cumsum) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int acc = 0;
   cumsum[0] = 0;
@@ -223,6 +240,8 @@ __global__ void duration_kernel(const float* __restrict__ logdur, int n, int64_t
 
 __global__ void expand_frames_kernel(const float* __restrict__ emb, const int* __restrict__ cumsum, int U, int f0, int C,
                                      float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   int f = f0 + blockIdx.x;
   int lo = 0, hi = U;  // find u with cumsum[u] <= f < cumsum[u+1]
   while (hi - lo > 1) {
@@ -234,6 +253,8 @@ __global__ void expand_frames_kernel(const float* __restrict__ emb, const int* _
 
 __global__ void conv_post_tanh_kernel(const float* __restrict__ x, int L, int C, const float* __restrict__ w, float bias, int k,
                                       float pre_slope, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L) return;
   int half = (k - 1) >> 1;
@@ -260,10 +281,10 @@ void layer_norm(const float* x, int ldx, float* y, int ldy, const float* gamma, 
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
   switch (C) {
-    case 128: layer_norm_kernel<4><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
-    case 256: layer_norm_kernel<8><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
-    case 512: layer_norm_kernel<16><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
-    case 1024: layer_norm_kernel<32><<<grid, wpb * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows); break;
+    case 128: launch_pdl(layer_norm_kernel<4>, dim3(grid), dim3(wpb * 32), 0, st, x, ldx, y, ldy, gamma, beta, rows); break;
+    case 256: launch_pdl(layer_norm_kernel<8>, dim3(grid), dim3(wpb * 32), 0, st, x, ldx, y, ldy, gamma, beta, rows); break;
+    case 512: launch_pdl(layer_norm_kernel<16>, dim3(grid), dim3(wpb * 32), 0, st, x, ldx, y, ldy, gamma, beta, rows); break;
+    case 1024: launch_pdl(layer_norm_kernel<32>, dim3(grid), dim3(wpb * 32), 0, st, x, ldx, y, ldy, gamma, beta, rows); break;
     default: break;  // engine validates C at finalize
   }
 }
@@ -272,69 +293,69 @@ void depthwise_bn_silu(const float* x, int ldx, const float* w, const float* sca
                        int B, int T, int t0, int n, int C, int k, int chunk, cudaStream_t st) {
   ++g_launches;
   if (B * n <= 0) return;
-  depthwise_bn_silu_kernel<<<B * n, 256, 0, st>>>(x, ldx, w, scale, shift, y, ldy, T, t0, n, C, k, chunk);
+  launch_pdl(depthwise_bn_silu_kernel, dim3(B * n), dim3(256), 0, st, x, ldx, w, scale, shift, y, ldy, T, t0, n, C, k, chunk);
 }
 
 void scale_rows(float* x, int64_t n, float s, cudaStream_t st) {
   ++g_launches;
   if (n <= 0) return;
-  scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s);
+  launch_pdl(scale_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, n, s);
 }
 
 void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st) {
   ++g_launches;
   if (n <= 0) return;
-  copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+  launch_pdl(copy_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, src, dst, n);
 }
 
 void embed_tokens_pos(const int64_t* tokens, const int* positions_or_null, int pos_offset, const float* emb,
                       const float* pos_table, float scale, float* out, int rows, int C, int pad_idx, cudaStream_t st) {
   ++g_launches;
   if (rows <= 0) return;
-  embed_tokens_pos_kernel<<<rows, 128, 0, st>>>(tokens, positions_or_null, pos_offset, emb, pos_table, scale, out, rows, C, pad_idx);
+  launch_pdl(embed_tokens_pos_kernel, dim3(rows), dim3(128), 0, st, tokens, positions_or_null, pos_offset, emb, pos_table, scale, out, rows, C, pad_idx);
 }
 
 void repeat_rows_add(const float* x, int S, int R, int C, const float* addvec_or_null, float* out, cudaStream_t st) {
   ++g_launches;
   if (S * R <= 0) return;
-  repeat_rows_add_kernel<<<S * R, 128, 0, st>>>(x, S, R, C, addvec_or_null, out);
+  launch_pdl(repeat_rows_add_kernel, dim3(S * R), dim3(128), 0, st, x, S, R, C, addvec_or_null, out);
 }
 
 void argmax_rows(const float* logits, int ld, int rows, int V, const int* masked_cols, int n_masked, int64_t* out_idx,
                  float* out_lprob_or_null, cudaStream_t st) {
   ++g_launches;
   if (rows <= 0) return;
-  argmax_rows_kernel<<<rows, 256, 0, st>>>(logits, ld, V, masked_cols, n_masked, out_idx, out_lprob_or_null);
+  launch_pdl(argmax_rows_kernel, dim3(rows), dim3(256), 0, st, logits, ld, V, masked_cols, n_masked, out_idx, out_lprob_or_null);
 }
 
 void ctc_collapse(const int64_t* argmax, int n, int blank, int pad, int64_t* out_tokens, int* out_index, int* out_count,
                   cudaStream_t st) {
   ++g_launches;
-  ctc_collapse_kernel<<<1, 1024, 0, st>>>(argmax, n, blank, pad, out_tokens, out_index, out_count);
+  launch_pdl(ctc_collapse_kernel, dim3(1), dim3(1024), 0, st, argmax, n, blank, pad, out_tokens, out_index, out_count);
 }
 
 void gather_rows(const int64_t* idx, int n, int idx_offset, const float* table, int C, float* out, cudaStream_t st) {
   ++g_launches;
   if (n <= 0) return;
-  gather_rows_kernel<<<n, 128, 0, st>>>(idx, idx_offset, table, C, out);
+  launch_pdl(gather_rows_kernel, dim3(n), dim3(128), 0, st, idx, idx_offset, table, C, out);
 }
 
 void duration_from_log(const float* logdur, int n, int64_t* dur, int* cumsum, cudaStream_t st) {
   ++g_launches;
-  duration_kernel<<<1, 32, 0, st>>>(logdur, n, dur, cumsum);
+  launch_pdl(duration_kernel, dim3(1), dim3(32), 0, st, logdur, n, dur, cumsum);
 }
 
 void expand_frames(const float* emb, const int* cumsum, int U, int f0, int nf, int C, float* out, cudaStream_t st) {
   ++g_launches;
   if (nf <= 0) return;
-  expand_frames_kernel<<<nf, 128, 0, st>>>(emb, cumsum, U, f0, C, out);
+  launch_pdl(expand_frames_kernel, dim3(nf), dim3(128), 0, st, emb, cumsum, U, f0, C, out);
 }
 
 void conv_post_tanh(const float* x, int L, int C, const float* w, float bias, int k, float pre_slope, float* out,
                     cudaStream_t st) {
   ++g_launches;
   if (L <= 0) return;
-  conv_post_tanh_kernel<<<(L + 127) / 128, 128, 0, st>>>(x, L, C, w, bias, k, pre_slope, out);
+  launch_pdl(conv_post_tanh_kernel, dim3((L + 127) / 128), dim3(128), 0, st, x, L, C, w, bias, k, pre_slope, out);
 }
 
 }  // namespace ss
