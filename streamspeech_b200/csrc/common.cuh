@@ -24,7 +24,10 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  // only small grids launch early: CTAs of a large dependent grid would sit on shared memory / registers that the
+  // (multi-wave) predecessor still needs (measured: vocoder convs 35 ms -> 48 ms with unconditional PDL)
+  const unsigned long long ctas = (unsigned long long)grid.x * grid.y * grid.z;
+  attr[0].val.programmaticStreamSerializationAllowed = ctas <= 296 ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

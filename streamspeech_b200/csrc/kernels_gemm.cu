@@ -299,9 +299,9 @@ void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue&
     ws = g_splitk_ws;
   }
   if (conv)
-    launch_pdl(gemm_kernel<BM, BN, true>, dim3(grid), dim3(NT), 0, st, a, W, M, N, K, ep, tiles, ws);
+    gemm_kernel<BM, BN, true><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);  // tile GEMMs never launch early (see launch_pdl)
   else
-    launch_pdl(gemm_kernel<BM, BN, false>, dim3(grid), dim3(NT), 0, st, a, W, M, N, K, ep, tiles, ws);
+    gemm_kernel<BM, BN, false><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);
   if (splits > 1) {
     ++g_launches;
     int total = M * (ep.glu ? N / 2 : N);
