@@ -167,23 +167,11 @@ __global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* 
   constexpr int A_IT = UM_BM * (UM_BK / 4) / UM_NT;  // 4
   constexpr int B_IT = (BN * (UM_BK / 4) + UM_NT - 1) / UM_NT;
   const int q = tid & 7;
-  for (int kt = 0; kt < nk; ++kt) {
-    const int st = kt & 1;
-    unsigned char* sbase = smem + st * STAGE;
-    if (kt >= 2) {  // the MMAs that read this stage two tiles ago must have completed
-      mbar_wait(smem_u32(&mbar[st]), phase[st]);
-      phase[st] ^= 1;
-    }
-    unsigned char* a_piece[NP];
-    unsigned char* b_piece[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      a_piece[p] = sbase + p * A_TILE;
-      b_piece[p] = sbase + NP * A_TILE + p * B_TILE;
-    }
-    const int k0 = (kt0 + kt) * UM_BK;
-    // ---- issue all global loads of this tile first (A_IT + B_IT independent 128-bit loads per thread in flight)
-    float4 va[A_IT], vb[B_IT];
+  // register double buffering: the global loads of tile kt+1 are issued before tile kt is split / stored, so the
+  // load latency overlaps the bf16 conversion and the (asynchronous) MMAs of the previous tiles
+  float4 va[A_IT], vb[B_IT];
+  auto issue_loads = [&](int kt_abs) {
+    const int k0 = kt_abs * UM_BK;
 #pragma unroll
     for (int i = 0; i < A_IT; ++i) va[i] = load_a4_conv(a, m0 + (tid >> 3) + 32 * i, k0 + q * 4, M, K);
 #pragma unroll
@@ -192,18 +180,41 @@ __global__ void __launch_bounds__(UM_NT) umma_gemm_kernel(ConvA a, const float* 
       int n = n0 + r, kk = k0 + q * 4;
       vb[i] = (r < BN && n < N && kk < K) ? *reinterpret_cast<const float4*>(W + (int64_t)n * K + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  if (nk > 0) issue_loads(kt0);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int st = kt & 1;
+    unsigned char* sbase = smem + st * STAGE;
+    unsigned char* a_piece[NP];
+    unsigned char* b_piece[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      a_piece[p] = sbase + p * A_TILE;
+      b_piece[p] = sbase + NP * A_TILE + p * B_TILE;
+    }
+    // current tile: registers -> local copies, then start fetching the next tile
+    float4 ca[A_IT], cb[B_IT];
+#pragma unroll
+    for (int i = 0; i < A_IT; ++i) ca[i] = va[i];
+#pragma unroll
+    for (int i = 0; i < B_IT; ++i) cb[i] = vb[i];
+    if (kt + 1 < nk) issue_loads(kt0 + kt + 1);
+    if (kt >= 2) {  // the MMAs that read this stage two tiles ago must have completed
+      mbar_wait(smem_u32(&mbar[st]), phase[st]);
+      phase[st] ^= 1;
+    }
 #pragma unroll
     for (int i = 0; i < A_IT; ++i) {
       int r = (tid >> 3) + 32 * i;
       uint32_t off = (uint32_t)(((q >> 1) * (UM_BM / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (q & 1) * 8);
-      split_store<NP>(va[i], a_piece, off);
+      split_store<NP>(ca[i], a_piece, off);
     }
 #pragma unroll
     for (int i = 0; i < B_IT; ++i) {
       int r = (tid >> 3) + 32 * i;
       if (r < BN) {
         uint32_t off = (uint32_t)(((q >> 1) * (BN / 8) + (r >> 3)) * 128 + (r & 7) * 16 + (q & 1) * 8);
-        split_store<NP>(vb[i], b_piece, off);
+        split_store<NP>(cb[i], b_piece, off);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
