@@ -335,8 +335,9 @@ void launch_umma(const ConvA& a, const float* W, int M, int N, int K, const Epil
   const int nk = (K + UM_BK - 1) / UM_BK;
   int splits = 1;
   float* ws = nullptr;
-  if (ctas < 148 && nk >= 8) {
-    splits = (int)std::min<long>((148 + ctas - 1) / ctas, nk / 4);
+  // the register-staged operand path keeps only ~32 KB of loads in flight per CTA: aim for 3 resident CTAs per SM
+  if (ctas < 444 && nk >= 8) {
+    splits = (int)std::min<long>((444 + ctas - 1) / ctas, nk / 4);
     ws = splitk_workspace((size_t)splits * M * N * sizeof(float));
     if (!ws) splits = 1;
   }
