@@ -131,34 +131,67 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def gemm_roofline(engine, peaks):
-    """Dominant kernel = the fp32 conv-as-GEMM kernel (encoder FFN/projections, decoders, every HiFi-GAN conv).
-    Measured live with CUDA events on the launching stream at the vocoder's heaviest shape
-    (stage-1 ResBlock conv k=11: M = 5 * frames, N = K/11 = 256) -> algorithmic FLOPs / duration."""
+def skinny_roofline(engine, peaks):
+    """Dominant kernel of the streaming path = skinny_gemm_kernel (every encoder / MT projection at M <= 16 rows), a
+    weight-streaming kernel -> HBM roofline.  Measured live with CUDA events on the launching stream at the encoder FFN
+    shape (M = 16 active rows, K = 256, N = 2048); 96 distinct weight matrices (201 MB > 126 MB L2) are cycled so every
+    launch streams its 2 MB of weights from HBM like the real step does.  algorithmic bytes = N*K*4 + M*K*4 + M*N*4."""
+    import torch
+
+    M, K, N, NW = 16, 256, 2048, 96
+    x = torch.randn(M, K, device=engine.device)
+    ws = [torch.randn(N, K, device=engine.device) * K ** -0.5 for _ in range(NW)]
+    b = torch.zeros(N, device=engine.device)
+    for i in range(NW):
+        engine.op_linear(x, ws[i], b, 2)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for i in range(NW):
+        engine.op_linear(x, ws[i], b, 2)
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) / NW * 1e3
+    nbytes = N * K * 4 + M * K * 4 + M * N * 4
+    ach = nbytes / (us * 1e-6) / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_dominant_kernel_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "kernel": "skinny_gemm_kernel<16,2,1> (fp32 weight-streaming GEMM, fused SiLU)", "algorithmic_bytes_per_launch": nbytes,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+            "shape": {"M": M, "N": N, "K": K}, "us_per_launch": us,
+            "note": "batch-1 streaming step: per-kernel latency (launch + one DRAM round trip + reduction) dominates, not bandwidth"}
+
+
+def gemm_rooflines(engine, peaks):
+    """Secondary: the two large-M GEMM kernels at the vocoder's heaviest conv shape (M = 5*500, N = 256, K = 11*256)."""
     import torch
 
     M, C, k = 5 * 500, 256, 11
     x = torch.randn(M, C * k, device=engine.device)
     w = torch.randn(C, C * k, device=engine.device) / (C * k) ** 0.5
     b = torch.zeros(C, device=engine.device)
-    for _ in range(3):
-        engine.op_linear(x, w, b)
-    reps = 20
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    s.record()
-    for _ in range(reps):
-        engine.op_linear(x, w, b)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / reps
-    flops = 2.0 * M * C * C * k
-    ach = flops / (ms * 1e-3) / 1e12
-    peak = peaks.get("bf16_tflops", 1590.0)
-    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-            "kernel": "gemm_kernel<128,64> fp32 CUDA-core conv-as-GEMM (tcgen05 path not enabled yet)",
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1.59 PF",
-            "shape": {"M": M, "N": C, "K": C * k}, "us_per_launch": ms * 1e3}
+    out = {}
+    for name, fn in (("gemm_kernel<128,64> fp32 CUDA cores", lambda: engine.op_linear(x, w, b)),
+                     ("umma_gemm_kernel<128,2> tcgen05 bf16x3 (opt-in)", lambda: engine.op_linear_umma(x, w, b, 0, 2))):
+        for _ in range(3):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(20):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 20
+        ach = 2.0 * M * C * C * k / (ms * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops", 1590.0)
+        out[name] = {"bound": "tensor", "achieved_fp32_equivalent": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                     "us_per_launch": ms * 1e3, "shape": {"M": M, "N": C, "K": C * k}}
+    return out
 
 
 def main():
@@ -277,7 +310,8 @@ def main():
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(UTT_SECONDS * SAMPLE_RATE * 4),
                     "d2h_bytes_per_step": int(out_e2e / args.steps * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks}
-    line["roofline"] = gemm_roofline(eng, peaks)
+    line["roofline"] = skinny_roofline(eng, peaks)
+    line["roofline_large_gemm"] = gemm_rooflines(eng, peaks)
     if world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample: the first 4 s of the same utterance through the oracle agent (reference semantics)
         from oracle.agent_oracle import OracleS2STAgent

@@ -56,10 +56,18 @@ __global__ void depthwise_bn_silu_kernel(const float* __restrict__ x, int ldx, c
   // NB: the reference convolves over padded frames too (padding is only masked in attention)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
-    for (int j = 0; j < k; ++j) {
-      int p = t - half + j;
-      if (p < 0 || p >= lim) continue;
-      acc = fmaf(w[j * C + c], x[((int64_t)b * T + p) * ldx + c], acc);
+    // taps in groups of 8: the loads of a group are independent and all in flight before the FMA chain consumes them
+    for (int j0 = 0; j0 < k; j0 += 8) {
+      float xv[8], wv[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        int j = j0 + jj, p = t - half + j;
+        bool ok = j < k && p >= 0 && p < lim;
+        xv[jj] = ok ? x[((int64_t)b * T + p) * ldx + c] : 0.f;
+        wv[jj] = ok ? w[j * C + c] : 0.f;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) acc = fmaf(wv[jj], xv[jj], acc);
     }
     float v = acc * scale[c] + shift[c];
     y[(int64_t)row * ldy + c] = v / (1.0f + expf(-v));

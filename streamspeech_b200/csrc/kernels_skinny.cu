@@ -206,7 +206,9 @@ void launch_skinny(const float* A, int lda, const float* W, int M, int N, int K,
   const int ntasks = N / cpt;
   const int per_cta = SK_WARPS / KS;
   int grid = (ntasks + per_cta - 1) / per_cta;
-  if (grid > 148 * 8) grid = 148 * 8;
+  // with a fused LayerNorm every CTA recomputes the row statistics: keep the grid at two CTAs per SM and loop over tasks
+  const int cap = ep.ln_gamma ? 148 * 2 : 148 * 8;
+  if (grid > cap) grid = cap;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(SK_WARPS * 32);
