@@ -2,10 +2,14 @@
 //   out[m][n] = epilogue( sum_k A[m][k] * W[n][k] ),  A row-major [M][K], W row-major [N][K].
 // These GEMMs are weight-streaming problems (2 MB of W for 16 rows), so the kernel is organised around memory-level
 // parallelism instead of tiles:
-//   * one warp per (output column, K-slice); lanes stride K with 128-bit loads, so a whole slice of the W row is in
-//     flight at once; W is read exactly once (streaming, L1 no-allocate), A (<= 128 KB) is re-read through L1/L2;
-//   * the KS K-slices of a column live in one CTA and are combined through shared memory in a fixed order
-//     (deterministic results), then the epilogue (bias / ReLU / SiLU / GLU / residual) runs one row per lane.
+//   * one warp per (group of CPT output columns, K-slice); lanes stride K with 128-bit loads, so CPT whole slices of
+//     W rows are in flight per warp at once; W is read exactly once (streaming, L1 no-allocate), the A rows
+//     (<= 128 KB) are re-read through L1/L2 once per column group;
+//   * the KS K-slices of a column group live in one CTA and are combined through shared memory in a fixed order
+//     (deterministic results); the epilogue (bias / ReLU / SiLU / GLU / residual / Q|K|V routing) runs one row per lane;
+//   * optional fused LayerNorm of A (row statistics per CTA, normalisation applied while loading A);
+//   * programmatic dependent launch: the first W slices are fetched BEFORE griddepcontrol.wait, i.e. while the previous
+//     kernel of the stream is still running (weights never depend on it).
 // HBM/L2-bound by construction: algorithmic bytes = N*K*4 (weights) + M*K*4 + M*N*4.
 #include "common.cuh"
 #include "kernels.h"
@@ -14,7 +18,7 @@ namespace ss {
 namespace {
 
 constexpr int SK_WARPS = 8;
-constexpr int SK_MR = 16;  // rows per pass (accumulators per lane)
+constexpr int SK_PF = 2;  // prefetched 128-bit W loads per column and lane
 
 __device__ __forceinline__ float sk_act(float x, int act) {
   switch (act) {
@@ -31,8 +35,9 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
   return r;
 }
 
-// KS = K-slices per column (warps cooperating on one column), CPT = columns per task (2 for GLU pairs)
-template <int MR, int KS, int CPT>
+// MR = rows per pass (accumulators per lane and column), KS = K-slices per column group, CPT = columns per task
+// (GLU: CPT = 2 = one (value, gate) pair)
+template <int MR, int KS, int CPT, bool GLU>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                                     int M, int N, int K, Epilogue ep) {
   constexpr int TASKS_PER_CTA = SK_WARPS / KS;
@@ -40,26 +45,24 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
   __shared__ float ln_mean[64], ln_rstd[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool fuse_ln = ep.ln_gamma != nullptr;
-  // Programmatic dependent launch: let the next kernel of the stream start its own prologue now, and fetch this
-  // warp's first slice of W (weights do not depend on the previous kernel) BEFORE waiting for the previous kernel's
-  // results -- the weight-fetch latency of GEMM i+1 hides behind the execution of GEMM i.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  constexpr int PF = 2;  // prefetched 128-bit W loads per column and lane
-  float4 wpre[CPT][PF];
-  {
-    const int slice_ = warp % KS, tslot_ = warp / KS;
-    const int kslice_ = K / KS;
-    const int task_ = blockIdx.x * (SK_WARPS / KS) + tslot_;
+  const int slice = warp % KS, tslot = warp / KS;
+  const int ntasks = N / CPT;
+  const int kslice = K / KS;  // multiple of 128 (checked by the host)
+  const int k_lo = slice * kslice, k_hi = k_lo + kslice;
+  const int first_task = blockIdx.x * TASKS_PER_CTA + tslot;
+
+  pdl_trigger();
+  float4 wpre[CPT][SK_PF];
 #pragma unroll
-    for (int c = 0; c < CPT; ++c)
+  for (int c = 0; c < CPT; ++c)
 #pragma unroll
-      for (int i = 0; i < PF; ++i) {
-        int k = slice_ * kslice_ + lane * 4 + i * 128;
-        wpre[c][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (task_ < N / CPT && k < (slice_ + 1) * kslice_) wpre[c][i] = ld_stream(W + ((int64_t)task_ * CPT + c) * K + k);
-      }
-  }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = 0; i < SK_PF; ++i) {
+      int k = k_lo + lane * 4 + i * 128;
+      wpre[c][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (first_task < ntasks && k < k_hi) wpre[c][i] = ld_stream(W + ((int64_t)first_task * CPT + c) * K + k);
+    }
+  pdl_wait();
+
   if (fuse_ln) {
     // row statistics with the same operation order as layer_norm_kernel (two-pass, lane-strided, shuffle tree)
     for (int m = warp; m < M; m += SK_WARPS) {
@@ -80,10 +83,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
     }
     __syncthreads();
   }
-  const int slice = warp % KS, tslot = warp / KS;
-  const int ntasks = N / CPT;
-  const int kslice = K / KS;  // multiple of 128 (checked by the host)
-  const int k_lo = slice * kslice, k_hi = k_lo + kslice;
+
   for (int tbase = blockIdx.x * TASKS_PER_CTA; tbase < ntasks; tbase += gridDim.x * TASKS_PER_CTA) {
     const int task = tbase + tslot;
     const bool active = task < ntasks;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
         for (int r = 0; r < MR; ++r) acc[c][r] = 0.f;
       if (active) {
         const float* w0 = W + (int64_t)n0 * K;
-        const bool first = (tbase == blockIdx.x * TASKS_PER_CTA) && mb == 0;
+        const bool first = (task == first_task) && mb == 0;
         auto step = [&](int k, const float4* wv) {
           float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (fuse_ln) {
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
         };
         int k = k_lo + lane * 4;
 #pragma unroll
-        for (int i = 0; i < PF; ++i, k += 128) {
+        for (int i = 0; i < SK_PF; ++i, k += 128) {
           if (k < k_hi) {
             float4 wv[CPT];
 #pragma unroll
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
           step(k, wv);
         }
       }
-      // lane r ends up holding the warp total of row r
+      // lane r ends up holding the warp totals of row r
       float mine[CPT];
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
@@ -171,58 +171,57 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const float*
       }
       const int m = mb + lane;
       if (active && slice == 0 && lane < MR && m < M) {
-        float y;
-        int oc;
-        if (CPT == 2) {
-          float av = mine[0] + (ep.bias ? ep.bias[n0] : 0.f);
-          float gv = mine[CPT - 1] + (ep.bias ? ep.bias[n0 + 1] : 0.f);
-          y = ep.alpha * (av * (1.0f / (1.0f + expf(-gv))));
-          oc = n0 >> 1;
-        } else {
-          y = ep.alpha * sk_act(mine[0] + (ep.bias ? ep.bias[n0] : 0.f), ep.act);
-          oc = n0;
+#pragma unroll
+        for (int c = 0; c < (GLU ? 1 : CPT); ++c) {
+          float y;
+          int oc;
+          if (GLU) {
+            float av = mine[0] + (ep.bias ? ep.bias[n0] : 0.f);
+            float gv = mine[CPT - 1] + (ep.bias ? ep.bias[n0 + 1] : 0.f);
+            y = ep.alpha * (av * (1.0f / (1.0f + expf(-gv))));
+            oc = n0 >> 1;
+          } else {
+            y = ep.alpha * sk_act(mine[c] + (ep.bias ? ep.bias[n0 + c] : 0.f), ep.act);
+            oc = n0 + c;
+          }
+          float* obase = ep.out;
+          int ld = ep.ldo;
+          if (ep.split_n > 0) {  // fused Q|K|V: route the column block to its own buffer
+            int p = oc / ep.split_n;
+            oc -= p * ep.split_n;
+            if (p == 1) { obase = ep.out2; ld = ep.ldo2; }
+            else if (p == 2) { obase = ep.out3; ld = ep.ldo3; }
+          }
+          int64_t o = (int64_t)m * ld + oc;
+          if (ep.residual) y += ep.res_scale * ep.residual[o];
+          if (ep.accumulate) y += obase[o];
+          obase[o] = y;
         }
-        float* obase = ep.out;
-        int ld = ep.ldo;
-        if (ep.split_n > 0) {  // fused Q|K|V: route the column block to its own buffer
-          int p = oc / ep.split_n;
-          oc -= p * ep.split_n;
-          if (p == 1) { obase = ep.out2; ld = ep.ldo2; }
-          else if (p == 2) { obase = ep.out3; ld = ep.ldo3; }
-        }
-        int64_t o = (int64_t)m * ld + oc;
-        if (ep.residual) y += ep.res_scale * ep.residual[o];
-        if (ep.accumulate) y += obase[o];
-        obase[o] = y;
       }
       if (KS > 1) __syncthreads();  // `part` is reused by the next pass / task
     }
   }
 }
 
-template <int MR, int KS>
+template <int MR, int KS, int CPT, bool GLU>
 void launch_skinny(const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
-  const int cpt = ep.glu ? 2 : 1;
-  const int ntasks = N / cpt;
+  const int ntasks = N / CPT;
   const int per_cta = SK_WARPS / KS;
   int grid = (ntasks + per_cta - 1) / per_cta;
   // with a fused LayerNorm every CTA recomputes the row statistics: keep the grid at two CTAs per SM and loop over tasks
   const int cap = ep.ln_gamma ? 148 * 2 : 148 * 8;
   if (grid > cap) grid = cap;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(SK_WARPS * 32);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (ep.glu)
-    cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<MR, KS, 2>, A, lda, W, M, N, K, ep);
-  else
-    cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<MR, KS, 1>, A, lda, W, M, N, K, ep);
+  launch_pdl_always(skinny_gemm_kernel<MR, KS, CPT, GLU>, dim3(grid), dim3(SK_WARPS * 32), 0, st, A, lda, W, M, N, K, ep);
+}
+
+template <int MR, int CPT, bool GLU>
+void dispatch_ks(int ks, const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+  switch (ks) {
+    case 1: launch_skinny<MR, 1, CPT, GLU>(A, lda, W, M, N, K, ep, st); break;
+    case 2: launch_skinny<MR, 2, CPT, GLU>(A, lda, W, M, N, K, ep, st); break;
+    case 4: launch_skinny<MR, 4, CPT, GLU>(A, lda, W, M, N, K, ep, st); break;
+    default: launch_skinny<MR, 8, CPT, GLU>(A, lda, W, M, N, K, ep, st); break;
+  }
 }
 
 }  // namespace
@@ -236,31 +235,24 @@ bool skinny_gemm_supported(int M, int N, int K, const Epilogue& ep) {
 
 void skinny_gemm(const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
   ++g_launches;
-  // K-slices per column: enough warp-tasks to cover 148 SMs x 16 warps, every slice a multiple of 128 columns
-  const int ntasks = ep.glu ? N / 2 : N;
+  // columns per warp-task: 4 independent W rows in flight per lane and one A load shared by 4 columns
+  const int cpt = ep.glu ? 2 : ((N & 3) == 0 && (ep.split_n == 0 || (ep.split_n & 3) == 0) ? 4 : 1);
+  const int ntasks = N / cpt;
+  // K-slices per column group: enough warp-tasks to cover the SMs, every slice a multiple of 128 columns
   int ks = 1;
-  while (ks < 8 && (long)ntasks * ks < 2400 && K % (ks * 2 * 128) == 0) ks *= 2;
+  while (ks < 8 && (long)ntasks * ks < 1184 && K % (ks * 2 * 128) == 0) ks *= 2;
   if (M == 1) {
-    switch (ks) {
-      case 1: launch_skinny<1, 1>(A, lda, W, M, N, K, ep, st); break;
-      case 2: launch_skinny<1, 2>(A, lda, W, M, N, K, ep, st); break;
-      case 4: launch_skinny<1, 4>(A, lda, W, M, N, K, ep, st); break;
-      default: launch_skinny<1, 8>(A, lda, W, M, N, K, ep, st); break;
-    }
+    if (ep.glu) dispatch_ks<1, 2, true>(ks, A, lda, W, M, N, K, ep, st);
+    else if (cpt == 4) dispatch_ks<1, 4, false>(ks, A, lda, W, M, N, K, ep, st);
+    else dispatch_ks<1, 1, false>(ks, A, lda, W, M, N, K, ep, st);
   } else if (M <= 8) {
-    switch (ks) {
-      case 1: launch_skinny<8, 1>(A, lda, W, M, N, K, ep, st); break;
-      case 2: launch_skinny<8, 2>(A, lda, W, M, N, K, ep, st); break;
-      case 4: launch_skinny<8, 4>(A, lda, W, M, N, K, ep, st); break;
-      default: launch_skinny<8, 8>(A, lda, W, M, N, K, ep, st); break;
-    }
+    if (ep.glu) dispatch_ks<8, 2, true>(ks, A, lda, W, M, N, K, ep, st);
+    else if (cpt == 4) dispatch_ks<8, 4, false>(ks, A, lda, W, M, N, K, ep, st);
+    else dispatch_ks<8, 1, false>(ks, A, lda, W, M, N, K, ep, st);
   } else {
-    switch (ks) {
-      case 1: launch_skinny<SK_MR, 1>(A, lda, W, M, N, K, ep, st); break;
-      case 2: launch_skinny<SK_MR, 2>(A, lda, W, M, N, K, ep, st); break;
-      case 4: launch_skinny<SK_MR, 4>(A, lda, W, M, N, K, ep, st); break;
-      default: launch_skinny<SK_MR, 8>(A, lda, W, M, N, K, ep, st); break;
-    }
+    if (ep.glu) dispatch_ks<16, 2, true>(ks, A, lda, W, M, N, K, ep, st);
+    else if (cpt == 4) dispatch_ks<16, 4, false>(ks, A, lda, W, M, N, K, ep, st);
+    else dispatch_ks<16, 1, false>(ks, A, lda, W, M, N, K, ep, st);
   }
 }
 
