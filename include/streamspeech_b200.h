@@ -147,8 +147,12 @@ int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, c
 /* same GEMM on the tcgen05 tensor-core kernel (bf16 operand splitting, pieces = 2 or 3); parity-test hook */
 int ss_op_linear_umma(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N,
                       int act, int pieces, float* out_dev);
-/* engine options: "umma_vocoder" / "umma_linear" = 0 (fp32 CUDA cores), 2 or 3 (tcgen05, bf16 pieces per operand) */
+/* engine options: "umma_vocoder" / "umma_linear" = 0 (fp32 CUDA cores), 2 or 3 (tcgen05, bf16 pieces per operand);
+ * "persistent_encoder" = 1 (default): ss_encoder_stream_step runs the layer stack as one cooperative kernel when the
+ * shape fits, 0: one kernel per op; "persistent_profile" = 1: that kernel records a %globaltimer stamp per phase */
 int ss_set_option(ss_engine* h, const char* name, int value);
+/* synchronous copy of a diagnostic buffer to the host: "persist_ts" = uint64 ns stamps of the last persistent step */
+int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes);
 int ss_op_layer_norm(ss_engine* h, void* stream, const float* x_dev, int rows, int C, const float* g_dev, const float* b_dev,
                      float* out_dev);
 

@@ -9,6 +9,7 @@
 
 #include "../../include/streamspeech_b200.h"
 #include "kernels.h"
+#include "kernels_persist.h"
 
 namespace ss {
 
@@ -86,6 +87,7 @@ struct ss_engine {
   int attn_chunk = 8, conv_chunk = 8;
   int umma_vocoder = 0;   // 0 = fp32 CUDA-core convs, 2 / 3 = tcgen05 with that many bf16 pieces per operand
   int umma_linear = 0;    // same for large-M linears (unit decoder, T2U, MT prefill, full-prefix encoder)
+  int persistent_encoder = 1;  // streaming encoder step as ONE cooperative kernel (kernels_persist.cu) when the shape fits
   std::map<std::string, ss::HostTensor> host;  // loaded tensors by key
   std::vector<void*> dev_allocs;
 
@@ -145,6 +147,9 @@ struct ss_engine {
   float* st_k = nullptr;    // [enc_layers][Tpos][enc_dim]
   float* st_v = nullptr;
   float* st_glu = nullptr;  // conv-module GLU outputs (depthwise-conv inputs)
+  unsigned long long* persist_ts = nullptr;    // [512] phase timestamps when option persistent_profile is set
+  int persistent_profile = 0;
+  ss::PersistLayer* persist_layers = nullptr;  // [enc_layers] device copy of the per-layer pointer table
   int* lengths_dev = nullptr;     // [Bcap]
   int lengths_cap = 0;
 

@@ -258,6 +258,20 @@ void finalize_impl(ss_engine* h) {
     h->st_k = dev_alloc<float>(h, n);
     h->st_v = dev_alloc<float>(h, n);
     h->st_glu = dev_alloc<float>(h, n);
+    std::vector<PersistLayer> pl(c.enc_layers);
+    for (int i = 0; i < c.enc_layers; ++i) {
+      const ConformerLayerW& L = h->enc[i];
+      PersistLayer& q = pl[i];
+      q.ffn1_g = L.ffn1_ln.g; q.ffn1_b = L.ffn1_ln.b; q.ffn1_w1 = L.ffn1_w1.w; q.ffn1_b1 = L.ffn1_w1.b; q.ffn1_w2 = L.ffn1_w2.w; q.ffn1_b2 = L.ffn1_w2.b;
+      q.attn_g = L.attn_ln.g; q.attn_b = L.attn_ln.b; q.wqkv = L.qkv.w; q.bqkv = L.qkv.b; q.wo = L.attn_out.w; q.bo = L.attn_out.b;
+      q.pos_u = L.pos_u; q.pos_v = L.pos_v; q.pos_proj = L.pos_proj;
+      q.conv_g = L.conv_ln.g; q.conv_b = L.conv_ln.b; q.pw1 = L.pw1.w; q.pw1_b = L.pw1.b; q.dw_w = L.dw_w; q.bn_scale = L.bn_scale;
+      q.bn_shift = L.bn_shift; q.pw2 = L.pw2.w; q.pw2_b = L.pw2.b;
+      q.ffn2_g = L.ffn2_ln.g; q.ffn2_b = L.ffn2_ln.b; q.ffn2_w1 = L.ffn2_w1.w; q.ffn2_b1 = L.ffn2_w1.b; q.ffn2_w2 = L.ffn2_w2.w; q.ffn2_b2 = L.ffn2_w2.b;
+      q.fin_g = L.final_ln.g; q.fin_b = L.final_ln.b;
+    }
+    h->persist_layers = dev_alloc<PersistLayer>(h, pl.size());
+    cudaMemcpy(h->persist_layers, pl.data(), pl.size() * sizeof(PersistLayer), cudaMemcpyHostToDevice);
   }
   // ---- CTC heads
   h->ctc_head[0] = make_linear(h, "source_unigram_decoder.proj", c.src_vocab, D);

@@ -1,0 +1,21 @@
+// Persistent cooperative encoder-stack kernel (kernels_persist.cu): one launch per streaming step for all layers.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ss {
+
+struct PersistLayer {  // device pointers of one Conformer layer (fp32, layouts as in engine.h ConformerLayerW)
+  const float *ffn1_g, *ffn1_b, *ffn1_w1, *ffn1_b1, *ffn1_w2, *ffn1_b2;
+  const float *attn_g, *attn_b, *wqkv, *bqkv, *wo, *bo, *pos_u, *pos_v, *pos_proj;
+  const float *conv_g, *conv_b, *pw1, *pw1_b, *dw_w, *bn_scale, *bn_shift, *pw2, *pw2_b;
+  const float *ffn2_g, *ffn2_b, *ffn2_w1, *ffn2_b1, *ffn2_w2, *ffn2_b2;
+  const float *fin_g, *fin_b;
+};
+
+bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, int dw_k);
+// returns 0 on success (kernel enqueued on `st`), < 0 if the cooperative launch was refused
+int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
+                              float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
+                              unsigned long long* timestamps_or_null, cudaStream_t st);
+
+}  // namespace ss

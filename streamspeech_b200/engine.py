@@ -80,6 +80,7 @@ def load_library() -> ctypes.CDLL:
     lib.ss_op_linear_umma.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, vp]
     lib.ss_set_option.argtypes = [vp, ctypes.c_char_p, i32]
     lib.ss_op_layer_norm.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    lib.ss_debug_copy.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t]
     lib.ss_launch_count.argtypes = [vp]
     lib.ss_launch_count.restype = i64
     _lib = lib
@@ -90,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_mt_greedy",
     "ss_mt_features", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
-    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_set_option", "ss_op_layer_norm", "ss_launch_count",
+    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count",
 ]
 
 
@@ -172,6 +173,7 @@ class Engine:
         # linears that feed an arg-max stay on the exact fp32 kernels unless explicitly switched on
         self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "0")))
         self.set_option("umma_linear", int(os.environ.get("SS_UMMA_LINEAR", "0")))
+        self.set_option("persistent_encoder", int(os.environ.get("SS_PERSISTENT_ENCODER", "1")))
         self.hop = self.lib.ss_vocoder_hop(self._h)
         self.vocoder_receptive_field = self.lib.ss_vocoder_receptive_field(self._h)
 
@@ -205,6 +207,12 @@ class Engine:
     @staticmethod
     def _ptr(t: Optional[torch.Tensor]):
         return None if t is None else t.data_ptr()
+
+    def persistent_phase_stamps(self, n: int):
+        """ns timestamps the persistent encoder kernel recorded on its last step (option persistent_profile)"""
+        buf = (ctypes.c_uint64 * n)()
+        self._check(self.lib.ss_debug_copy(self._h, b"persist_ts", ctypes.cast(buf, ctypes.c_void_p), n * 8))
+        return list(buf)
 
     def launch_count(self) -> int:
         return int(self.lib.ss_launch_count(self._h))
