@@ -147,8 +147,10 @@ struct ss_engine {
   float* st_k = nullptr;    // [enc_layers][Tpos][enc_dim]
   float* st_v = nullptr;
   float* st_glu = nullptr;  // conv-module GLU outputs (depthwise-conv inputs)
-  unsigned long long* persist_ts = nullptr;    // [512] phase timestamps when option persistent_profile is set
+  unsigned long long* persist_ts = nullptr;    // [4096] phase timestamps when option persistent_profile is set
   int persistent_profile = 0;
+  ss::PersistLayer* persist_alias = nullptr;   // debug: every layer entry = layer 0 (timing experiments only)
+  int persistent_alias = 0;
   ss::PersistLayer* persist_layers = nullptr;  // [enc_layers] device copy of the per-layer pointer table
   int* lengths_dev = nullptr;     // [Bcap]
   int lengths_cap = 0;

@@ -350,7 +350,7 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
     linear(x0, D, nA, h->enc_linear, ep_out(x, D), st);
     bool persistent = h->persistent_encoder && encoder_layers_persistent_supported(nA, D, c.enc_ffn, c.enc_heads, T, c.dw_kernel);
     if (persistent)
-      persistent = encoder_layers_persistent(h->persist_layers, c.enc_layers, x, hid, qb, att, dw, h->st_k, h->st_v, h->st_glu, nA, a0, T, D,
+      persistent = encoder_layers_persistent(h->persistent_alias ? h->persist_alias : h->persist_layers, c.enc_layers, x, hid, qb, att, dw, h->st_k, h->st_v, h->st_glu, nA, a0, T, D,
                                              c.enc_ffn, c.enc_heads, h->Tpos, h->attn_chunk, cc, c.dw_kernel,
                                              h->persistent_profile ? h->persist_ts : nullptr, st) == 0;
     if (!persistent) cudaGetLastError();  // a refused cooperative launch falls back to the per-kernel path
@@ -720,9 +720,18 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   if (n == "umma_vocoder") h->umma_vocoder = value;
   else if (n == "umma_linear") h->umma_linear = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
+  else if (n == "persistent_alias") {  // timing experiment: all layers read layer 0's weights (results are wrong)
+    if (value && !h->persist_alias) {
+      const int L = h->cfg.enc_layers;
+      if (cudaMalloc(&h->persist_alias, L * sizeof(PersistLayer)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
+      h->dev_allocs.push_back(h->persist_alias);
+      for (int i = 0; i < L; ++i) cudaMemcpy(h->persist_alias + i, h->persist_layers, sizeof(PersistLayer), cudaMemcpyDeviceToDevice);
+    }
+    h->persistent_alias = value;
+  }
   else if (n == "persistent_profile") {
     if (value && !h->persist_ts) {
-      if (cudaMalloc(&h->persist_ts, 512 * sizeof(unsigned long long)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
+      if (cudaMalloc(&h->persist_ts, 4096 * sizeof(unsigned long long)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
       h->dev_allocs.push_back(h->persist_ts);
     }
     h->persistent_profile = value;
@@ -735,7 +744,7 @@ int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes) 
   if (!h || !what || !host_dst) return SS_ERR_INVALID;
   std::string n(what);
   if (n == "persist_ts") {
-    if (!h->persist_ts || bytes > 512 * sizeof(unsigned long long)) return h->fail(SS_ERR_STATE, "no phase timestamps (set option persistent_profile)");
+    if (!h->persist_ts || bytes > 4096 * sizeof(unsigned long long)) return h->fail(SS_ERR_STATE, "no phase timestamps (set option persistent_profile)");
     if (cudaMemcpy(host_dst, h->persist_ts, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMemcpy failed");
     return SS_OK;
   }

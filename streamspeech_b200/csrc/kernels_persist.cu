@@ -1,13 +1,18 @@
 // Persistent cooperative kernel for one streaming step of the chunk-Conformer encoder stack.
 //
-// At batch 1 a 320 ms step touches 16 active rows and ~11 MB of fp32 weights per layer; run as separate kernels it is
+// At batch 1 a 320 ms step touches <= 16 active rows and ~11 MB of fp32 weights per layer; run as separate kernels it is
 // bounded by kernel boundaries (137 dependent launches x ~8 us, profiles/r1_*), not by HBM or FLOPs.  This kernel keeps
-// one CTA per SM resident for ALL layers and replaces the kernel boundaries by grid-wide barriers:
-//   per layer:  [LN+W1+SiLU] | [W2 + 0.5 res] | [LN + QKV -> q, K-cache, V-cache] | [rel-pos attention] | [out + res] |
-//               [LN + PW1 + GLU -> conv cache] | [depthwise k31 + BN + SiLU] | [PW2 + res] | [LN+W1+SiLU] | [W2 + 0.5 res] | [LN]
-// The GEMM phases use the skinny-GEMM scheme (warp per 4 columns x K-slice, 128-bit streaming loads of W, fixed-order
-// reduction); attention is one CTA per (query row, head).  Same arithmetic as the multi-kernel path
-// (ss_encoder_stream_step), which remains the fallback for shapes this kernel does not cover (nA > 16, D != 256, ...).
+// one CTA per SM resident for ALL layers and replaces the kernel boundaries by grid-wide barriers, 9 per layer:
+//   [LN + W1 + SiLU] | [W2 + 0.5 res] | [LN + QKV -> q, K-cache, V-cache] | [rel-pos attention] | [out + res] |
+//   [LN + PW1 + GLU -> conv cache, depthwise k31 + BN + SiLU] | [PW2 + res] | [LN + W1 + SiLU] | [W2 + 0.5 res]
+// The layer's final LayerNorm is not a phase of its own: the next layer's first phase applies it while staging its input,
+// and the first residual add after it applies it to the residual it reads (one explicit LN phase closes the last layer).
+//
+// GEMM phases (M <= 16 rows): the CTA stages the (layer-normed) activations once in shared memory, each warp owns CPT
+// output columns x one K-slice, streams its weight rows with 128-bit non-coherent loads issued BEFORE the staging (so the
+// HBM latency overlaps the LayerNorm), reduces the 16 row sums with a halving shuffle tree and a fixed-order K-slice sum.
+// Same arithmetic as the per-kernel path of ss_encoder_stream_step, which remains the fallback for shapes this kernel
+// does not cover (nA > 16, D != 256, ...).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -23,6 +28,7 @@ constexpr int PW = 8;          // warps per CTA
 constexpr int PT = PW * 32;    // threads per CTA
 constexpr int PMR = 16;        // max active rows
 constexpr int PHD = 64;        // head dim
+constexpr int PD = 256;        // model dim
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -43,117 +49,208 @@ struct GemmEpi {
   float* out = nullptr;     // column block 0
   int ldo = 0;
   bool residual = false;    // out += (in place)
+  const float* res_ln_g = nullptr;  // residual read is LN(out) with the stats in Smem::fin_* (deferred final LayerNorm)
+  const float* res_ln_b = nullptr;
   int split_n = 0;          // > 0: route column blocks of this width to out / out2 / out3
   float* out2 = nullptr;
   float* out3 = nullptr;
   int ldo2 = 0, ldo3 = 0;
 };
 
+struct DwFuse {  // depthwise conv + BN + SiLU on the GLU outputs (conv module), fused into the PW1 phase
+  const float* gc;   // conv cache of this layer [Tpos][D] (GLU outputs of all rows so far)
+  const float* w;    // [k][D]
+  const float* scale;
+  const float* shift;
+  float* dw;         // [nA][D]
+  int a0, T, k, chunk;
+};
+
 struct Smem {
+  float As[PMR * PD];        // staged (layer-normed) activations, row stride PD
   float part[PW][4][PMR];
-  float ln_mean[PMR], ln_rstd[PMR];
+  float fin_mean[PMR], fin_rstd[PMR];
   float S[1024];
   float qa[PHD], qb[PHD];
   float pv[PW][PHD];
+  float strip[PW][48];
+  float wstrip[PW][32];
   float red[PW];
-  unsigned long long* fine;  // profile mode, CTA 0, layer 1: clock64 stamps inside the phases
+  unsigned long long* fine;  // profile mode, CTA 0, layer 1: (tag, clock64) stamps inside the phases
   int nfine;
 };
 
-__device__ __forceinline__ void fine_stamp(Smem& sm) {
-  if (threadIdx.x == 0 && sm.fine != nullptr && sm.nfine < 200) sm.fine[sm.nfine++] = (unsigned long long)clock64();
+__device__ __forceinline__ void fine_stamp(Smem& sm, int tag) {
+  if (threadIdx.x == 0 && sm.fine != nullptr && sm.nfine < 120) {
+    sm.fine[2 * sm.nfine] = (unsigned long long)tag;
+    sm.fine[2 * sm.nfine + 1] = (unsigned long long)clock64();
+    ++sm.nfine;
+  }
 }
 
-// Activations are written by other CTAs between barriers: they are read with plain (coherent) loads, never through
-// __restrict__ / ld.global.nc; only weights take the non-coherent streaming path.
-// out[M][N'] = epi( LN?(A)[M][K] @ W[N][K]^T ), M <= 16.  All CTAs of the grid take part.
-template <int CPT, bool GLU>
-__device__ void phase_gemm(Smem& sm, const float* A, int lda, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                           const float* __restrict__ W, int M, int N, int K, int KS, const GemmEpi& ep) {
+// As[m][:] = LN_b(LN_a(x[m][:])) for m < M (zeros above); LN_a (the previous layer's deferred final LayerNorm) is optional
+// and leaves its row statistics in sm.fin_*.  Warp w owns rows w and w + 8; 8 values per lane per row.  No barrier inside.
+__device__ __forceinline__ void stage_ln(Smem& sm, const float* x, int M, const float* __restrict__ ga, const float* __restrict__ ba,
+                                         const float* __restrict__ gb, const float* __restrict__ bb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool fuse_ln = ln_g != nullptr;
-  fine_stamp(sm);
-  if (fuse_ln) {
-    // K == 256 here (checked by encoder_layers_persistent_supported): warp w owns rows w and w + 8, 8 values per lane each
-    float v[2][8];
-    float s[2] = {0.f, 0.f};
+  float v[2][8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = warp + h * PW;
+  for (int h = 0; h < 2; ++h) {
+    const int m = warp + h * PW;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[h][i] = m < M ? A[(int64_t)m * lda + lane + (i << 5)] : 0.f;
-        s[h] += v[h][i];
-      }
+    for (int i = 0; i < 8; ++i) v[h][i] = m < M ? x[(int64_t)m * PD + lane + (i << 5)] : 0.f;
+  }
+  float g[8], b[8];
+  if (ga != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g[i] = ga[lane + (i << 5)];
+      b[i] = ba[lane + (i << 5)];
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int m = warp + h * PW;
-      const float mean = warp_sum(s[h]) / (float)K;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[h][i];
+      const float mean = warp_sum(s) / (float)PD;
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float d = v[h][i] - mean;
         q = fmaf(d, d, q);
       }
-      const float var = warp_sum(q) / (float)K;
-      if (lane == 0 && m < M) {
-        sm.ln_mean[m] = mean;
-        sm.ln_rstd[m] = 1.0f / sqrtf(var + 1e-5f);
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)PD + 1e-5f);
+      if (lane == 0) {
+        sm.fin_mean[m] = mean;
+        sm.fin_rstd[m] = rstd;
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[h][i] = (v[h][i] - mean) * rstd * g[i] + b[i];
     }
-    __syncthreads();
   }
-  fine_stamp(sm);
-  const int tpc = PW / KS;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    g[i] = gb[lane + (i << 5)];
+    b[i] = bb[lane + (i << 5)];
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int m = warp + h * PW;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[h][i];
+    const float mean = warp_sum(s) / (float)PD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float d = v[h][i] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)PD + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm.As[m * PD + lane + (i << 5)] = m < M ? (v[h][i] - mean) * rstd * g[i] + b[i] : 0.f;
+  }
+}
+
+// As[m][:] = a[m][:] (K == PD), zeros for m >= M
+__device__ __forceinline__ void stage_copy(Smem& sm, const float* a, int M) {
+#pragma unroll
+  for (int i = 0; i < (PMR * PD / 4) / PT; ++i) {
+    const int idx = threadIdx.x + i * PT;  // float4 index
+    const int m = idx / (PD / 4);
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M) val = *reinterpret_cast<const float4*>(a + (int64_t)idx * 4);
+    *reinterpret_cast<float4*>(sm.As + idx * 4) = val;
+  }
+}
+
+enum { STAGE_LN = 0, STAGE_COPY = 1, STAGE_NONE = 2 };
+
+// out[M][N'] = epi( A[M][K] @ W[N][K]^T ), M <= 16.  All CTAs of the grid take part.  STAGE_LN / STAGE_COPY: K == PD and A
+// goes through shared memory (LN: As = LN(LN_pre?(A))); STAGE_NONE: every warp reads its K-slice of A from global memory.
+// Activations are written by other CTAs between barriers: they are read with plain (coherent) loads, never through
+// __restrict__ / ld.global.nc; only weights take the non-coherent streaming path.
+template <int CPT, bool GLU, int KS, int K, int STAGE>
+__device__ void phase_gemm(Smem& sm, const float* A, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
+                           const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ W, int M, int N,
+                           const GemmEpi& ep, const DwFuse* dwf, int tag) {
+  constexpr int KSLICE = K / KS;
+  constexpr int NIT = KSLICE / 128;
+  static_assert(KSLICE % 128 == 0, "K slice must be a multiple of 128");
+  static_assert(STAGE == STAGE_NONE || K == PD, "staged GEMMs have K == PD");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int TPC = PW / KS;
   const int slice = warp % KS, tslot = warp / KS;
   const int ntasks = N / CPT;
-  const int kslice = K / KS;
-  const int k_lo = slice * kslice, k_hi = k_lo + kslice;
-  for (int tbase = blockIdx.x * tpc; tbase < ntasks; tbase += gridDim.x * tpc) {
+  const int k_lo = slice * KSLICE;
+  const int m = lane >> 1;  // row owned in the epilogue (even lanes)
+  const bool owner = (lane & 1) == 0;
+  fine_stamp(sm, tag);
+  bool first = true;
+  for (int tbase = blockIdx.x * TPC; tbase < ntasks; tbase += gridDim.x * TPC) {
     const int task = tbase + tslot;
     const bool active = task < ntasks;
     const int n0 = task * CPT;
+    // ---- issue the weight loads of the whole task first: their HBM latency overlaps the staging below
+    float4 wv[NIT][CPT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+        wv[it][c] = active ? ldw(W + (int64_t)(n0 + c) * K + k_lo + it * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // epilogue operands that do not depend on the GEMM: bias, residual, depthwise taps / cached rows
+    float bias_v[CPT], res_v[CPT];
+    float dw_old = 0.f, dw_tap = 0.f;
+    const bool epi_lane = active && slice == 0 && owner && m < M;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      bias_v[c] = (ep.bias != nullptr && active) ? ep.bias[n0 + c] : 0.f;
+      res_v[c] = 0.f;
+    }
+    if (!GLU && ep.residual && epi_lane) {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) res_v[c] = ep.out[(int64_t)m * ep.ldo + n0 + c];
+    }
+    if (GLU && dwf != nullptr && active && slice == 0) {
+      const int half = (dwf->k - 1) >> 1, oc = n0 >> 1;
+      const int p = dwf->a0 - half + lane;
+      if (lane < half && p >= 0) dw_old = dwf->gc[(int64_t)p * PD + oc];
+      if (lane < dwf->k) dw_tap = dwf->w[lane * PD + oc];
+    }
+    if (first) {
+      if (STAGE == STAGE_LN) stage_ln(sm, A, M, pre_g, pre_b, ln_g, ln_b);
+      if (STAGE == STAGE_COPY) stage_copy(sm, A, M);
+      if (STAGE != STAGE_NONE) __syncthreads();
+      first = false;
+      fine_stamp(sm, tag + 1);
+    }
     float acc[CPT][PMR];
 #pragma unroll
     for (int c = 0; c < CPT; ++c)
 #pragma unroll
       for (int r = 0; r < PMR; ++r) acc[c][r] = 0.f;
-    if (active) {
-      const float* w0 = W + (int64_t)n0 * K;
-#pragma unroll 2
-      for (int k = k_lo + lane * 4; k < k_hi; k += 128) {
-        float4 wv[CPT];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) wv[c] = ldw(w0 + (int64_t)c * K + k);
-        float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fuse_ln) {
-          g4 = *reinterpret_cast<const float4*>(ln_g + k);
-          b4 = *reinterpret_cast<const float4*>(ln_b + k);
+    for (int it = 0; it < NIT; ++it) {
+      const int k = k_lo + it * 128 + lane * 4;
+#pragma unroll
+      for (int r = 0; r < PMR; ++r) {
+        float4 x;
+        if (STAGE == STAGE_NONE) {
+          x = (r < M) ? *reinterpret_cast<const float4*>(A + (int64_t)r * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          x = *reinterpret_cast<const float4*>(sm.As + r * PD + k);
         }
 #pragma unroll
-        for (int r = 0; r < PMR; ++r) {
-          if (r < M) {
-            float4 x = *reinterpret_cast<const float4*>(A + (int64_t)r * lda + k);
-            if (fuse_ln) {
-              const float mu = sm.ln_mean[r], rs = sm.ln_rstd[r];
-              x.x = (x.x - mu) * rs * g4.x + b4.x;
-              x.y = (x.y - mu) * rs * g4.y + b4.y;
-              x.z = (x.z - mu) * rs * g4.z + b4.z;
-              x.w = (x.w - mu) * rs * g4.w + b4.w;
-            }
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-              acc[c][r] = fmaf(x.x, wv[c].x, acc[c][r]);
-              acc[c][r] = fmaf(x.y, wv[c].y, acc[c][r]);
-              acc[c][r] = fmaf(x.z, wv[c].z, acc[c][r]);
-              acc[c][r] = fmaf(x.w, wv[c].w, acc[c][r]);
-            }
-          }
+        for (int c = 0; c < CPT; ++c) {
+          acc[c][r] = fmaf(x.x, wv[it][c].x, acc[c][r]);
+          acc[c][r] = fmaf(x.y, wv[it][c].y, acc[c][r]);
+          acc[c][r] = fmaf(x.z, wv[it][c].z, acc[c][r]);
+          acc[c][r] = fmaf(x.w, wv[it][c].w, acc[c][r]);
         }
       }
     }
-    fine_stamp(sm);
+    fine_stamp(sm, tag + 2);
     // 16 row sums per column across the warp: recursive halving (16 shuffles per column instead of 16 x 5); even lane
     // 2m ends up with the sum of row m.  Fixed order -> deterministic.
     float mine[CPT];
@@ -184,9 +281,6 @@ __device__ void phase_gemm(Smem& sm, const float* A, int lda, const float* __res
       float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
       mine[c] = w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
     }
-    const int m = lane >> 1;
-    const bool owner = (lane & 1) == 0;
-    fine_stamp(sm);
     if (KS > 1) {
       if (owner) {
 #pragma unroll
@@ -197,27 +291,53 @@ __device__ void phase_gemm(Smem& sm, const float* A, int lda, const float* __res
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           float t = sm.part[warp][c][m];
+#pragma unroll
           for (int s = 1; s < KS; ++s) t += sm.part[warp + s][c][m];
           mine[c] = t;
         }
       }
     }
-    if (active && slice == 0 && owner && m < M) {
-#pragma unroll
-      for (int c = 0; c < (GLU ? 1 : CPT); ++c) {
-        float y;
-        int oc;
-        if (GLU) {
-          float av = mine[0] + (ep.bias ? ep.bias[n0] : 0.f);
-          float gv = mine[CPT - 1] + (ep.bias ? ep.bias[n0 + 1] : 0.f);
-          y = ep.alpha * (av * (1.0f / (1.0f + expf(-gv))));
-          oc = n0 >> 1;
-        } else {
-          float v = mine[c] + (ep.bias ? ep.bias[n0 + c] : 0.f);
-          if (ep.act == ACT_SILU) v = v / (1.0f + expf(-v));
-          y = ep.alpha * v;
-          oc = n0 + c;
+    fine_stamp(sm, tag + 3);
+    if (GLU) {
+      float y = 0.f;
+      const int oc = n0 >> 1;
+      if (epi_lane) {
+        float av = mine[0] + bias_v[0];
+        float gv = mine[CPT - 1] + bias_v[CPT - 1];
+        y = ep.alpha * (av * (1.0f / (1.0f + expf(-gv))));
+        ep.out[(int64_t)m * ep.ldo + oc] = y;
+      }
+      if (dwf != nullptr && active && slice == 0) {
+        // depthwise conv over time for channel oc: strip = [half cached rows | the M new rows | zeros]
+        const int half = (dwf->k - 1) >> 1;
+        float* strip = sm.strip[warp];
+        float* wst = sm.wstrip[warp];
+        if (lane < half) strip[lane] = dw_old;
+        if (half + M + lane < 48) strip[half + M + lane] = 0.f;  // (rows past the last new one are masked by `lim` anyway)
+        wst[lane] = dw_tap;
+        __syncwarp();
+        if (epi_lane) strip[half + m] = y;
+        __syncwarp();
+        if (lane < M) {
+          const int t = dwf->a0 + lane;
+          const int lim = dwf->chunk > 0 ? min(dwf->T, (t / dwf->chunk + 1) * dwf->chunk) : dwf->T;
+          float a = 0.f;
+          for (int j = 0; j < dwf->k; ++j) {
+            const int p = t - half + j;
+            if (p >= 0 && p < lim) a = fmaf(wst[j], strip[lane + j], a);
+          }
+          float v = a * dwf->scale[oc] + dwf->shift[oc];
+          dwf->dw[(int64_t)lane * PD + oc] = v / (1.0f + expf(-v));
         }
+        __syncwarp();
+      }
+    } else if (epi_lane) {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        float v = mine[c] + bias_v[c];
+        if (ep.act == ACT_SILU) v = v / (1.0f + expf(-v));
+        float y = ep.alpha * v;
+        int oc = n0 + c;
         float* obase = ep.out;
         int ld = ep.ldo;
         if (ep.split_n > 0) {
@@ -226,20 +346,27 @@ __device__ void phase_gemm(Smem& sm, const float* A, int lda, const float* __res
           if (p == 1) { obase = ep.out2; ld = ep.ldo2; }
           else if (p == 2) { obase = ep.out3; ld = ep.ldo3; }
         }
-        int64_t o = (int64_t)m * ld + oc;
-        if (ep.residual) y += obase[o];
-        obase[o] = y;
+        if (ep.residual) {
+          float r = res_v[c];
+          if (ep.res_ln_g != nullptr) r = (r - sm.fin_mean[m]) * sm.fin_rstd[m] * ep.res_ln_g[oc] + ep.res_ln_b[oc];
+          y += r;
+        }
+        obase[(int64_t)m * ld + oc] = y;
       }
     }
     if (KS > 1) __syncthreads();
-    fine_stamp(sm);
+    fine_stamp(sm, tag + 4);
+  }
+  if (STAGE == STAGE_LN && first && pre_g != nullptr) {  // CTA without a task: the next phase still needs sm.fin_*
+    stage_ln(sm, A, M, pre_g, pre_b, ln_g, ln_b);
+    __syncthreads();
   }
 }
 
 // rel-pos attention for the active rows: one CTA per (row, head) task
-__device__ void phase_attention(Smem& sm, const float* q, const float* kc, const float* vc,
-                                const float* __restrict__ pos, int Tpos, const float* __restrict__ bias_u, const float* __restrict__ bias_v,
-                                float* out, int nA, int a0, int T, int D, int H, int chunk) {
+__device__ void phase_attention(Smem& sm, const float* q, const float* kc, const float* vc, const float* __restrict__ pos, int Tpos,
+                                const float* __restrict__ bias_u, const float* __restrict__ bias_v, float* out, int nA, int a0, int T, int D,
+                                int H, int chunk) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (int task = blockIdx.x; task < nA * H; task += gridDim.x) {
     const int r = task / H, h = task - r * H;
@@ -260,13 +387,19 @@ __device__ void phase_attention(Smem& sm, const float* q, const float* kc, const
     for (int j = tid; j < n; j += PT) {
       const float* kr = kb + (int64_t)j * D;
       const float* pr = pb + (int64_t)(i - j + Tpos - 1) * D;
+      float4 kk[PHD / 4], pp[PHD / 4];
+#pragma unroll
+      for (int d = 0; d < PHD / 4; ++d) {
+        kk[d] = *reinterpret_cast<const float4*>(kr + 4 * d);
+        pp[d] = *reinterpret_cast<const float4*>(pr + 4 * d);
+      }
       float ac = 0.f, bd = 0.f;
 #pragma unroll
-      for (int d = 0; d < PHD; d += 4) {
-        float4 kk = *reinterpret_cast<const float4*>(kr + d);
-        float4 pp = *reinterpret_cast<const float4*>(pr + d);
-        ac = fmaf(sm.qa[d], kk.x, ac); ac = fmaf(sm.qa[d + 1], kk.y, ac); ac = fmaf(sm.qa[d + 2], kk.z, ac); ac = fmaf(sm.qa[d + 3], kk.w, ac);
-        bd = fmaf(sm.qb[d], pp.x, bd); bd = fmaf(sm.qb[d + 1], pp.y, bd); bd = fmaf(sm.qb[d + 2], pp.z, bd); bd = fmaf(sm.qb[d + 3], pp.w, bd);
+      for (int d = 0; d < PHD / 4; ++d) {
+        ac = fmaf(sm.qa[4 * d], kk[d].x, ac); ac = fmaf(sm.qa[4 * d + 1], kk[d].y, ac);
+        ac = fmaf(sm.qa[4 * d + 2], kk[d].z, ac); ac = fmaf(sm.qa[4 * d + 3], kk[d].w, ac);
+        bd = fmaf(sm.qb[4 * d], pp[d].x, bd); bd = fmaf(sm.qb[4 * d + 1], pp[d].y, bd);
+        bd = fmaf(sm.qb[4 * d + 2], pp[d].z, bd); bd = fmaf(sm.qb[4 * d + 3], pp[d].w, bd);
       }
       float s = (ac + bd) * 0.125f;
       sm.S[j] = s;
@@ -291,13 +424,23 @@ __device__ void phase_attention(Smem& sm, const float* q, const float* kc, const
     sum = sm.red[0];
 #pragma unroll
     for (int x = 1; x < PW; ++x) sum += sm.red[x];
+    // out[d] = sum_j p_j V[j][d]: warp w takes keys j = w (mod 8), 8 keys in flight; lane owns dims 2*lane, 2*lane+1
     float a0_ = 0.f, a1_ = 0.f;
-#pragma unroll 4
-    for (int j = w; j < n; j += PW) {
-      float p = sm.S[j];
-      float2 vv = *reinterpret_cast<const float2*>(vb + (int64_t)j * D + 2 * lane);
-      a0_ = fmaf(p, vv.x, a0_);
-      a1_ = fmaf(p, vv.y, a1_);
+    for (int j0 = w; j0 < n; j0 += PW * 8) {
+      float2 vv[8];
+      float p[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * PW;
+        const bool ok = j < n;
+        vv[u] = ok ? *reinterpret_cast<const float2*>(vb + (int64_t)j * D + 2 * lane) : make_float2(0.f, 0.f);
+        p[u] = ok ? sm.S[j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a0_ = fmaf(p[u], vv[u].x, a0_);
+        a1_ = fmaf(p[u], vv[u].y, a1_);
+      }
     }
     sm.pv[w][2 * lane] = a0_;
     sm.pv[w][2 * lane + 1] = a1_;
@@ -307,32 +450,6 @@ __device__ void phase_attention(Smem& sm, const float* q, const float* kc, const
 #pragma unroll
       for (int x = 0; x < PW; ++x) t += sm.pv[x][tid];
       out[(int64_t)r * D + h * PHD + tid] = t / sum;
-    }
-  }
-}
-
-__device__ void phase_depthwise(const float* gc, const float* __restrict__ w, const float* __restrict__ scale,
-                                const float* __restrict__ shift, float* dw, int nA, int a0, int T, int D, int k, int chunk) {
-  const int half = (k - 1) >> 1;
-  for (int r = blockIdx.x; r < nA; r += gridDim.x) {
-    const int t = a0 + r;
-    const int lim = chunk > 0 ? min(T, (t / chunk + 1) * chunk) : T;
-    for (int c = threadIdx.x; c < D; c += PT) {
-      float acc = 0.f;
-      for (int j0 = 0; j0 < k; j0 += 8) {
-        float xv[8], wv[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          int j = j0 + jj, p = t - half + j;
-          bool ok = j < k && p >= 0 && p < lim;
-          xv[jj] = ok ? gc[(int64_t)p * D + c] : 0.f;
-          wv[jj] = ok ? w[j * D + c] : 0.f;
-        }
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) acc = fmaf(wv[jj], xv[jj], acc);
-      }
-      float v = acc * scale[c] + shift[c];
-      dw[(int64_t)r * D + c] = v / (1.0f + expf(-v));
     }
   }
 }
@@ -364,14 +481,20 @@ __device__ void phase_layer_norm(float* x, const float* __restrict__ g, const fl
   }
 }
 
+template <int FFN>
 __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const PersistLayer* __restrict__ layers, int n_layers, float* x,
                                                                           float* hid, float* qb, float* att, float* dw, float* kc_all,
-                                                                          float* vc_all, float* gc_all, int nA, int a0, int T, int D, int FFN,
-                                                                          int H, int Tpos, int chunk, int conv_chunk, int dw_k, unsigned long long* ts) {
+                                                                          float* vc_all, float* gc_all, int nA, int a0, int T, int H, int Tpos,
+                                                                          int chunk, int conv_chunk, int dw_k, unsigned long long* ts) {
+  constexpr int D = PD;
   cg::grid_group grid = cg::this_grid();
-  __shared__ Smem sm;
+  __shared__ __align__(16) Smem sm;
   int nts = 0;
   const bool stamp = ts != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (threadIdx.x == 0) {
+    sm.fine = nullptr;
+    sm.nfine = 0;
+  }
   if (ts != nullptr) {  // profile mode: two back-to-back barriers first (pure barrier cost)
     if (stamp) ts[nts++] = globaltimer_ns();
     grid.sync();
@@ -379,92 +502,84 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
     grid.sync();
     if (stamp) ts[nts++] = globaltimer_ns();
   }
-  if (threadIdx.x == 0) { sm.fine = nullptr; sm.nfine = 0; }
+  // profile mode: every CTA also records when it ARRIVES at each barrier of layer 1 (ts[512 + cta * 16 + phase])
+#define PHASE_END(tag)                                                                                          \
+  fine_stamp(sm, tag);                                                                                          \
+  if (ts != nullptr && li == 1 && threadIdx.x == 0) ts[512 + blockIdx.x * 16 + (tag) / 10 - 1] = globaltimer_ns(); \
+  grid.sync();                                                                                                  \
+  if (stamp) ts[nts++] = globaltimer_ns();
   for (int li = 0; li < n_layers; ++li) {
     if (threadIdx.x == 0) sm.fine = (ts != nullptr && blockIdx.x == 0 && li == 1) ? ts + 256 : nullptr;
     const PersistLayer L = layers[li];
+    // the previous layer's final LayerNorm is still pending on x (applied on the fly in the first two phases)
+    const float* pre_g = li > 0 ? layers[li - 1].fin_g : nullptr;
+    const float* pre_b = li > 0 ? layers[li - 1].fin_b : nullptr;
     float* kc = kc_all + (size_t)li * Tpos * D;
     float* vc = vc_all + (size_t)li * Tpos * D;
     float* gc = gc_all + (size_t)li * Tpos * D;
     GemmEpi e;
     // x = x + 0.5 * W2(SiLU(W1 LN(x)))
     e = GemmEpi(); e.bias = L.ffn1_b1; e.act = ACT_SILU; e.out = hid; e.ldo = FFN;
-    phase_gemm<4, false>(sm, x, D, L.ffn1_g, L.ffn1_b, L.ffn1_w1, nA, FFN, D, 2, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
-    e = GemmEpi(); e.bias = L.ffn1_b2; e.alpha = 0.5f; e.out = x; e.ldo = D; e.residual = true;
-    phase_gemm<2, false>(sm, hid, FFN, nullptr, nullptr, L.ffn1_w2, nA, D, FFN, 8, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
+    phase_gemm<4, false, 2, D, STAGE_LN>(sm, x, pre_g, pre_b, L.ffn1_g, L.ffn1_b, L.ffn1_w1, nA, FFN, e, nullptr, 10);
+    PHASE_END(15);
+    e = GemmEpi(); e.bias = L.ffn1_b2; e.alpha = 0.5f; e.out = x; e.ldo = D; e.residual = true; e.res_ln_g = pre_g; e.res_ln_b = pre_b;
+    phase_gemm<2, false, 8, FFN, STAGE_NONE>(sm, hid, nullptr, nullptr, nullptr, nullptr, L.ffn1_w2, nA, D, e, nullptr, 20);
+    PHASE_END(25);
     // q -> qb, k / v -> cache rows a0..
     e = GemmEpi(); e.bias = L.bqkv; e.out = qb; e.ldo = D; e.split_n = D; e.out2 = kc + (size_t)a0 * D; e.ldo2 = D; e.out3 = vc + (size_t)a0 * D; e.ldo3 = D;
-    phase_gemm<2, false>(sm, x, D, L.attn_g, L.attn_b, L.wqkv, nA, 3 * D, D, 2, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
+    phase_gemm<2, false, 2, D, STAGE_LN>(sm, x, nullptr, nullptr, L.attn_g, L.attn_b, L.wqkv, nA, 3 * D, e, nullptr, 30);
+    PHASE_END(35);
+    fine_stamp(sm, 40);
     phase_attention(sm, qb, kc, vc, L.pos_proj, Tpos, L.pos_u, L.pos_v, att, nA, a0, T, D, H, chunk);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
+    PHASE_END(45);
     e = GemmEpi(); e.bias = L.bo; e.out = x; e.ldo = D; e.residual = true;
-    phase_gemm<1, false>(sm, att, D, nullptr, nullptr, L.wo, nA, D, D, 2, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    // conv module
+    phase_gemm<1, false, 2, D, STAGE_COPY>(sm, att, nullptr, nullptr, nullptr, nullptr, L.wo, nA, D, e, nullptr, 50);
+    PHASE_END(55);
+    // conv module: LN + PW1 + GLU (-> conv cache) + depthwise + BN + SiLU
     e = GemmEpi(); e.bias = L.pw1_b; e.out = gc + (size_t)a0 * D; e.ldo = D;
-    phase_gemm<2, true>(sm, x, D, L.conv_g, L.conv_b, L.pw1, nA, 2 * D, D, 2, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
-    phase_depthwise(gc, L.dw_w, L.bn_scale, L.bn_shift, dw, nA, a0, T, D, dw_k, conv_chunk);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
+    DwFuse dwf{gc, L.dw_w, L.bn_scale, L.bn_shift, dw, a0, T, dw_k, conv_chunk};
+    phase_gemm<2, true, 2, D, STAGE_LN>(sm, x, nullptr, nullptr, L.conv_g, L.conv_b, L.pw1, nA, 2 * D, e, &dwf, 60);
+    PHASE_END(65);
     e = GemmEpi(); e.bias = L.pw2_b; e.out = x; e.ldo = D; e.residual = true;
-    phase_gemm<1, false>(sm, dw, D, nullptr, nullptr, L.pw2, nA, D, D, 2, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
+    phase_gemm<1, false, 2, D, STAGE_COPY>(sm, dw, nullptr, nullptr, nullptr, nullptr, L.pw2, nA, D, e, nullptr, 70);
+    PHASE_END(75);
     e = GemmEpi(); e.bias = L.ffn2_b1; e.act = ACT_SILU; e.out = hid; e.ldo = FFN;
-    phase_gemm<4, false>(sm, x, D, L.ffn2_g, L.ffn2_b, L.ffn2_w1, nA, FFN, D, 2, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
+    phase_gemm<4, false, 2, D, STAGE_LN>(sm, x, nullptr, nullptr, L.ffn2_g, L.ffn2_b, L.ffn2_w1, nA, FFN, e, nullptr, 80);
+    PHASE_END(85);
     e = GemmEpi(); e.bias = L.ffn2_b2; e.alpha = 0.5f; e.out = x; e.ldo = D; e.residual = true;
-    phase_gemm<2, false>(sm, hid, FFN, nullptr, nullptr, L.ffn2_w2, nA, D, FFN, 8, e);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
-    fine_stamp(sm);
-    phase_layer_norm(x, L.fin_g, L.fin_b, nA, D);
-    grid.sync();
-    if (stamp) ts[nts++] = globaltimer_ns();
+    phase_gemm<2, false, 8, FFN, STAGE_NONE>(sm, hid, nullptr, nullptr, nullptr, nullptr, L.ffn2_w2, nA, D, e, nullptr, 90);
+    PHASE_END(95);
   }
+#undef PHASE_END
+  phase_layer_norm(x, layers[n_layers - 1].fin_g, layers[n_layers - 1].fin_b, nA, D);
 }
 
 }  // namespace
 
 bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, int dw_k) {
-  return nA >= 1 && nA <= PMR && D == 256 && (FFN % 1024) == 0 && H * PHD == D && T <= 1024 && dw_k <= 64;
+  return nA >= 1 && nA <= PMR && D == PD && FFN == 2048 && H * PHD == D && T <= 1024 && (dw_k & 1) == 1 && dw_k <= 31;
 }
 
 int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
                               unsigned long long* ts, cudaStream_t st) {
   ++g_launches;
+  (void)D;
+  (void)FFN;
+  auto kernel = encoder_layers_persistent_kernel<2048>;
   static int grid = 0;
   if (grid == 0) {
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encoder_layers_persistent_kernel, PT, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PT, 0);
     if (occ < 1) return -1;
     grid = sms;
   }
   void* args[] = {(void*)&layers_dev, (void*)&n_layers, (void*)&x, (void*)&hid, (void*)&qb, (void*)&att, (void*)&dw, (void*)&kc, (void*)&vc,
-                  (void*)&gc, (void*)&nA, (void*)&a0, (void*)&T, (void*)&D, (void*)&FFN, (void*)&H, (void*)&Tpos, (void*)&chunk,
-                  (void*)&conv_chunk, (void*)&dw_k, (void*)&ts};
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)encoder_layers_persistent_kernel, dim3(grid), dim3(PT), args, 0, st);
+                  (void*)&gc, (void*)&nA, (void*)&a0, (void*)&T, (void*)&H, (void*)&Tpos, (void*)&chunk, (void*)&conv_chunk, (void*)&dw_k,
+                  (void*)&ts};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(PT), args, 0, st);
   return e == cudaSuccess ? 0 : -2;
 }
 

@@ -10,7 +10,7 @@ import bench
 from streamspeech_b200 import synth
 from streamspeech_b200.agent import StreamSpeechS2STAgent
 
-PHASES = ["ffn1_w1", "ffn1_w2", "qkv", "attention", "attn_out", "pw1_glu", "depthwise", "pw2", "ffn2_w1", "ffn2_w2", "final_ln"]
+PHASES = ["ffn1_w1", "ffn1_w2", "qkv", "attention", "attn_out", "pw1_glu_dw", "pw2", "ffn2_w1", "ffn2_w2"]
 
 torch.set_grad_enabled(False)
 agent = StreamSpeechS2STAgent(bench.agent_args(0, "cached"))
@@ -61,6 +61,16 @@ eng.encoder_stream_reset()
 for k in range(1, 20):
     eng.encoder_stream_step(feats[:32 * k - 2], buf)
 torch.cuda.synchronize()
-ts = eng.persistent_phase_stamps(256 + 60)[256:]
-d = [ts[i] - ts[i - 1] for i in range(1, 50)]
-print("fine cycle deltas (CTA 0, layer 1):", d)
+ts = eng.persistent_phase_stamps(256 + 240)[256:]
+pairs = [(int(ts[2 * i]), int(ts[2 * i + 1])) for i in range(60) if ts[2 * i + 1]]
+print("fine (tag: cycles since previous stamp), CTA 0, layer 1; tags: x0 gemm entry, x1 staged, x2 main loop done, x3 reduced, x4 epilogue done, x5 barrier arrive")
+print(" ".join(f"{t}:{c - pairs[i - 1][1] if i else 0}" for i, (t, c) in enumerate(pairs)))
+# arrival of every CTA at each barrier of layer 1, relative to the start of that phase (= end of the previous barrier)
+all_ts = eng.persistent_phase_stamps(4096)
+L1 = 3 + len(PHASES)  # index of the stamp taken after the last barrier of layer 0
+import statistics
+for p, name in enumerate(PHASES):
+    start = all_ts[L1 + p - 1]
+    arr = [all_ts[512 + c * 16 + p] - start for c in range(148)]
+    order = sorted(range(148), key=lambda c: arr[c])
+    print(f"{name:12s} arrive ns: min {min(arr)} med {int(statistics.median(arr))} max {max(arr)}  slowest CTAs {order[-4:]}  fastest {order[:3]}  barrier done {all_ts[L1 + p] - start}")
