@@ -151,6 +151,9 @@ struct ss_engine {
   int persistent_profile = 0;
   ss::PersistLayer* persist_alias = nullptr;   // debug: every layer entry = layer 0 (timing experiments only)
   int persistent_alias = 0;
+  unsigned* persist_bar = nullptr;   // arrival counter of the kernel's own grid barrier (option persistent_barrier)
+  unsigned persist_bar_target = 0;
+  int persistent_barrier = 1;        // 0: cooperative-groups grid.sync(), 1: own counter barrier (1.6 us cheaper per barrier)
   ss::PersistLayer* persist_layers = nullptr;  // [enc_layers] device copy of the per-layer pointer table
   int* lengths_dev = nullptr;     // [Bcap]
   int lengths_cap = 0;

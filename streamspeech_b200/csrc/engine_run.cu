@@ -352,7 +352,8 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
     if (persistent)
       persistent = encoder_layers_persistent(h->persistent_alias ? h->persist_alias : h->persist_layers, c.enc_layers, x, hid, qb, att, dw, h->st_k, h->st_v, h->st_glu, nA, a0, T, D,
                                              c.enc_ffn, c.enc_heads, h->Tpos, h->attn_chunk, cc, c.dw_kernel,
-                                             h->persistent_profile ? h->persist_ts : nullptr, st) == 0;
+                                             h->persistent_profile ? h->persist_ts : nullptr,
+                                             h->persistent_barrier ? h->persist_bar : nullptr, &h->persist_bar_target, st) == 0;
     if (!persistent) cudaGetLastError();  // a refused cooperative launch falls back to the per-kernel path
     for (int i = 0; i < c.enc_layers && !persistent; ++i) {
       const ConformerLayerW& L = h->enc[i];
@@ -720,6 +721,15 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   if (n == "umma_vocoder") h->umma_vocoder = value;
   else if (n == "umma_linear") h->umma_linear = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
+  else if (n == "persistent_barrier") {
+    if (value && !h->persist_bar) {
+      if (cudaMalloc(&h->persist_bar, 256) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
+      h->dev_allocs.push_back(h->persist_bar);
+      cudaMemset(h->persist_bar, 0, 256);
+      h->persist_bar_target = 0;
+    }
+    h->persistent_barrier = value;
+  }
   else if (n == "persistent_alias") {  // timing experiment: all layers read layer 0's weights (results are wrong)
     if (value && !h->persist_alias) {
       const int L = h->cfg.enc_layers;

@@ -42,6 +42,22 @@ __device__ __forceinline__ float4 ldw(const float* p) {
   return r;
 }
 
+// Grid barrier on a monotonic arrival counter (one red.release per CTA, relaxed polling, one acquire fence at the end).
+// `target` is the counter value that marks "every CTA has arrived at this barrier"; the host carries it across launches.
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned v, spins = 0;
+    do {  // (bounded: a counter out of step with the host's target must not hang the device)
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0 && ++spins < (1u << 22));
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+  __syncthreads();
+}
+
 struct GemmEpi {
   const float* bias = nullptr;
   int act = ACT_NONE;       // ignored when GLU
@@ -485,7 +501,8 @@ template <int FFN>
 __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const PersistLayer* __restrict__ layers, int n_layers, float* x,
                                                                           float* hid, float* qb, float* att, float* dw, float* kc_all,
                                                                           float* vc_all, float* gc_all, int nA, int a0, int T, int H, int Tpos,
-                                                                          int chunk, int conv_chunk, int dw_k, unsigned long long* ts) {
+                                                                          int chunk, int conv_chunk, int dw_k, unsigned long long* ts,
+                                                                          unsigned* bar_ctr, unsigned bar_target) {
   constexpr int D = PD;
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) Smem sm;
@@ -495,18 +512,21 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
     sm.fine = nullptr;
     sm.nfine = 0;
   }
+#define GRID_SYNC()                                       \
+  if (bar_ctr != nullptr) grid_barrier(bar_ctr, bar_target); \
+  else grid.sync();
   if (ts != nullptr) {  // profile mode: two back-to-back barriers first (pure barrier cost)
     if (stamp) ts[nts++] = globaltimer_ns();
-    grid.sync();
+    GRID_SYNC();
     if (stamp) ts[nts++] = globaltimer_ns();
-    grid.sync();
+    GRID_SYNC();
     if (stamp) ts[nts++] = globaltimer_ns();
   }
   // profile mode: every CTA also records when it ARRIVES at each barrier of layer 1 (ts[512 + cta * 16 + phase])
 #define PHASE_END(tag)                                                                                          \
   fine_stamp(sm, tag);                                                                                          \
   if (ts != nullptr && li == 1 && threadIdx.x == 0) ts[512 + blockIdx.x * 16 + (tag) / 10 - 1] = globaltimer_ns(); \
-  grid.sync();                                                                                                  \
+  GRID_SYNC();                                                                                                  \
   if (stamp) ts[nts++] = globaltimer_ns();
   for (int li = 0; li < n_layers; ++li) {
     if (threadIdx.x == 0) sm.fine = (ts != nullptr && blockIdx.x == 0 && li == 1) ? ts + 256 : nullptr;
@@ -551,6 +571,7 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
     PHASE_END(95);
   }
 #undef PHASE_END
+#undef GRID_SYNC
   phase_layer_norm(x, layers[n_layers - 1].fin_g, layers[n_layers - 1].fin_b, nA, D);
 }
 
@@ -562,7 +583,7 @@ bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, i
 
 int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
-                              unsigned long long* ts, cudaStream_t st) {
+                              unsigned long long* ts, unsigned* bar_ctr, unsigned* bar_target_host, cudaStream_t st) {
   ++g_launches;
   (void)D;
   (void)FFN;
@@ -576,11 +597,14 @@ int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, floa
     if (occ < 1) return -1;
     grid = sms;
   }
+  unsigned bar_target = bar_target_host ? *bar_target_host : 0u;
   void* args[] = {(void*)&layers_dev, (void*)&n_layers, (void*)&x, (void*)&hid, (void*)&qb, (void*)&att, (void*)&dw, (void*)&kc, (void*)&vc,
                   (void*)&gc, (void*)&nA, (void*)&a0, (void*)&T, (void*)&H, (void*)&Tpos, (void*)&chunk, (void*)&conv_chunk, (void*)&dw_k,
-                  (void*)&ts};
+                  (void*)&ts, (void*)&bar_ctr, (void*)&bar_target};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(PT), args, 0, st);
-  return e == cudaSuccess ? 0 : -2;
+  if (e != cudaSuccess) return -2;
+  if (bar_ctr != nullptr && bar_target_host != nullptr) *bar_target_host += (unsigned)grid * (unsigned)(9 * n_layers + (ts != nullptr ? 2 : 0));
+  return 0;
 }
 
 }  // namespace ss

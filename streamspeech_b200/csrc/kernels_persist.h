@@ -16,6 +16,7 @@ bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, i
 // returns 0 on success (kernel enqueued on `st`), < 0 if the cooperative launch was refused
 int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
-                              unsigned long long* timestamps_or_null, cudaStream_t st);
+                              unsigned long long* timestamps_or_null, unsigned* barrier_counter_dev_or_null,
+                              unsigned* barrier_target_host, cudaStream_t st);
 
 }  // namespace ss

@@ -17,8 +17,9 @@ u = synth.make_audio(10.0, seed=1234).cuda()
 feats = eng.fbank(u)
 buf = torch.zeros(1024, 256, device="cuda")
 res = {}
-for alias in (0, 1, 0, 1):
+for alias, bar in ((0, 0), (0, 1), (1, 0), (1, 1), (0, 0), (0, 1)):
     eng.set_option("persistent_alias", alias)
+    eng.set_option("persistent_barrier", bar)
     gpu = []
     for rep in range(2):
         eng.encoder_stream_reset()
@@ -31,4 +32,4 @@ for alias in (0, 1, 0, 1):
             torch.cuda.synchronize()
             if rep == 1 and k > 4:
                 gpu.append(s.elapsed_time(e))
-    print("alias", alias, "gpu ms/step", sum(gpu) / len(gpu))
+    print("alias", alias, "own_barrier", bar, "gpu ms/step", sum(gpu) / len(gpu))
