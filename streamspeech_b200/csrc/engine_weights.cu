@@ -272,6 +272,9 @@ void finalize_impl(ss_engine* h) {
     }
     h->persist_layers = dev_alloc<PersistLayer>(h, pl.size());
     cudaMemcpy(h->persist_layers, pl.data(), pl.size() * sizeof(PersistLayer), cudaMemcpyHostToDevice);
+    h->persist_bar = dev_alloc<unsigned>(h, 64);
+    cudaMemset(h->persist_bar, 0, 64 * sizeof(unsigned));
+    h->persist_bar_target = 0;
   }
   // ---- CTC heads
   h->ctc_head[0] = make_linear(h, "source_unigram_decoder.proj", c.src_vocab, D);

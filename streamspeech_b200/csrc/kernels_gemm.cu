@@ -83,32 +83,37 @@ __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restri
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  float4 ra[A_PER], rb[B_PER];
-  auto gload = [&](int k0) {
+  // Global -> register -> shared staging with a register prefetch distance of PF k-tiles: the loads of tile kt + PF are in
+  // flight while tile kt is computed, so one DRAM / L2 round trip (~1 us) is covered by PF iterations of FMAs even at one
+  // CTA per SM (the streaming vocoder / decoder GEMMs launch 100-300 CTAs).  The im2col predicates and the pre-activation
+  // stay on the register path (cp.async could not apply them).
+  constexpr int PF = 3;
+  float4 ra[PF][A_PER], rb[PF][B_PER];
+  auto gload = [&](int k0, float4* qa, float4* qb) {
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
       int idx = tid + i * NT;
-      if (idx < A_F4) ra[i] = load_a4<CONV>(a, m0 + (idx >> 2), k0 + ((idx & 3) << 2), M, K);
+      if (idx < A_F4) qa[i] = load_a4<CONV>(a, m0 + (idx >> 2), k0 + ((idx & 3) << 2), M, K);
     }
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
       int idx = tid + i * NT;
       if (idx < B_F4) {
         int n = n0 + (idx >> 2), kk = k0 + ((idx & 3) << 2);
-        rb[i] = (n < N && kk < K) ? *reinterpret_cast<const float4*>(W + (int64_t)n * K + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        qb[i] = (n < N && kk < K) ? *reinterpret_cast<const float4*>(W + (int64_t)n * K + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   };
-  auto sstore = [&](int buf) {
+  auto sstore = [&](int buf, const float4* qa, const float4* qb) {
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
       int idx = tid + i * NT;
       if (idx < A_F4) {
         int r = idx >> 2, kq = (idx & 3) << 2;
-        As[buf][kq + 0][r] = ra[i].x;
-        As[buf][kq + 1][r] = ra[i].y;
-        As[buf][kq + 2][r] = ra[i].z;
-        As[buf][kq + 3][r] = ra[i].w;
+        As[buf][kq + 0][r] = qa[i].x;
+        As[buf][kq + 1][r] = qa[i].y;
+        As[buf][kq + 2][r] = qa[i].z;
+        As[buf][kq + 3][r] = qa[i].w;
       }
     }
 #pragma unroll
@@ -116,10 +121,10 @@ __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restri
       int idx = tid + i * NT;
       if (idx < B_F4) {
         int r = idx >> 2, kq = (idx & 3) << 2;
-        Bs[buf][kq + 0][r] = rb[i].x;
-        Bs[buf][kq + 1][r] = rb[i].y;
-        Bs[buf][kq + 2][r] = rb[i].z;
-        Bs[buf][kq + 3][r] = rb[i].w;
+        Bs[buf][kq + 0][r] = qb[i].x;
+        Bs[buf][kq + 1][r] = qb[i].y;
+        Bs[buf][kq + 2][r] = qb[i].z;
+        Bs[buf][kq + 3][r] = qb[i].w;
       }
     }
   };
@@ -127,27 +132,34 @@ __global__ void __launch_bounds__(NT) gemm_kernel(ConvA a, const float* __restri
   const int nk_all = (K + BK - 1) / BK;
   const int kt0 = blockIdx.z * tiles_per_split;
   const int nk = min(nk_all, kt0 + tiles_per_split) - kt0;
-  gload(kt0 * BK);
-  sstore(0);
-  __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) gload((kt0 + kt + 1) * BK);
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float av[TM], bv[TN];
+  for (int d = 0; d < PF; ++d)
+    if (d < nk) gload((kt0 + d) * BK, ra[d], rb[d]);
+  // iteration kt: registers of tile kt -> smem[kt & 1]; barrier; refill that register set with tile kt + PF; compute.
+  // (a warp that runs ahead stores tile kt + 1 into the other buffer, and reaches tile kt + 2's store only after the
+  // barrier of iteration kt + 1, i.e. after every warp has finished computing on smem[kt & 1])
+  for (int ktb = 0; ktb < nk; ktb += PF) {
 #pragma unroll
-      for (int i = 0; i < TM; ++i) av[i] = As[buf][k][ty * TM + i];
+    for (int d = 0; d < PF; ++d) {
+      const int kt = ktb + d;
+      if (kt < nk) {
+        const int buf = kt & 1;
+        sstore(buf, ra[d], rb[d]);
+        __syncthreads();
+        if (kt + PF < nk) gload((kt0 + kt + PF) * BK, ra[d], rb[d]);
 #pragma unroll
-      for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][k][tx * TN + j];
+        for (int k = 0; k < BK; ++k) {
+          float av[TM], bv[TN];
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+          for (int i = 0; i < TM; ++i) av[i] = As[buf][k][ty * TM + i];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    if (kt + 1 < nk) {
-      sstore(buf ^ 1);
-      __syncthreads();
+          for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][k][tx * TN + j];
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+      }
     }
   }
 
