@@ -149,7 +149,10 @@ int ss_op_linear_umma(ss_engine* h, void* stream, const float* x_dev, int M, int
                       int act, int pieces, float* out_dev);
 /* engine options: "umma_vocoder" / "umma_linear" = 0 (fp32 CUDA cores), 2 or 3 (tcgen05, bf16 pieces per operand);
  * "persistent_encoder" = 1 (default): ss_encoder_stream_step runs the layer stack as one cooperative kernel when the
- * shape fits, 0: one kernel per op; "persistent_profile" = 1: that kernel records a %globaltimer stamp per phase */
+ * shape fits, 0: one kernel per op; "persistent_barrier" = 1 (default): that kernel's own counter barrier instead of
+ * cooperative-groups grid.sync(); "vocoder_streams" = 1 (default): the three parallel resblocks of a vocoder stage run
+ * on the caller's stream plus two engine-owned streams (joined before the call returns control of the stream);
+ * "persistent_profile" = 1: that kernel records a %globaltimer stamp per phase */
 int ss_set_option(ss_engine* h, const char* name, int value);
 /* synchronous copy of a diagnostic buffer to the host: "persist_ts" = uint64 ns stamps of the last persistent step */
 int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes);

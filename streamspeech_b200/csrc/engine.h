@@ -87,6 +87,9 @@ struct ss_engine {
   int attn_chunk = 8, conv_chunk = 8;
   int umma_vocoder = 0;   // 0 = fp32 CUDA-core convs, 2 / 3 = tcgen05 with that many bf16 pieces per operand
   int umma_linear = 0;    // same for large-M linears (unit decoder, T2U, MT prefill, full-prefix encoder)
+  int vocoder_streams = 1;     // 1: the parallel resblocks of a vocoder stage run on three streams, 0: one stream
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t fork_event = nullptr, join_event[2] = {nullptr, nullptr};
   int persistent_encoder = 1;  // streaming encoder step as ONE cooperative kernel (kernels_persist.cu) when the shape fits
   std::map<std::string, ss::HostTensor> host;  // loaded tensors by key
   std::vector<void*> dev_allocs;

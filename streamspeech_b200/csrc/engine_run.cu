@@ -631,16 +631,31 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
       maxbuf = std::max(maxbuf, L * ch);
     }
   }
-  size_t total = ((size_t)N * c.voc_in_dim + 5 * maxbuf + (size_t)N * h->hop + 8192) * sizeof(float);
+  const int nrb = c.voc_n_rb;
+  size_t total = ((size_t)N * c.voc_in_dim + (size_t)(2 + 4 * nrb) * maxbuf + (size_t)N * h->hop + 8192) * sizeof(float) + 64 * 256;
   if (!ws_begin(h, total)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
   float* frames = h->ws.f32((size_t)N * c.voc_in_dim);
   float* bufX = h->ws.f32(maxbuf);   // stage input / output
   float* bufY = h->ws.f32(maxbuf);   // upsampled stage activation
-  float* bufA = h->ws.f32(maxbuf);
-  float* bufB = h->ws.f32(maxbuf);
-  float* bufT = h->ws.f32(maxbuf);
+  // per resblock (they run concurrently): ping-pong pair, conv1 output, block output
+  std::vector<float*> rbA(nrb), rbB(nrb), rbT(nrb), rbO(nrb);
+  bool ok = frames && bufX && bufY;
+  for (int j = 0; j < nrb; ++j) {
+    rbA[j] = h->ws.f32(maxbuf); rbB[j] = h->ws.f32(maxbuf); rbT[j] = h->ws.f32(maxbuf); rbO[j] = h->ws.f32(maxbuf);
+    ok = ok && rbA[j] && rbB[j] && rbT[j] && rbO[j];
+  }
   float* wav = h->ws.f32((size_t)N * h->hop);
-  if (!frames || !bufX || !bufY || !bufA || !bufB || !bufT || !wav) return h->fail(SS_ERR_CUDA, "workspace too small");
+  if (!ok || !wav) return h->fail(SS_ERR_CUDA, "workspace too small");
+  // The resblocks of a stage are independent until their outputs are averaged (hifigan.py:158-165).  Each one is a chain of
+  // small latency-bound convs, so they run on separate streams (block 0 on the caller's) and overlap on the GPU.
+  const bool fan_out = h->vocoder_streams && nrb == 3 && g_umma_conv == 0;
+  if (fan_out && !h->fork_event) {
+    bool made = cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && made; ++i)
+      made = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->join_event[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!made) return h->fail(SS_ERR_CUDA, "cannot create the vocoder's auxiliary streams");
+  }
   // V1 tail: repeat_interleave(x, dur) for the frame window (agent/tts/codehifigan.py:66)
   expand_frames(h->voc_unit_emb, h->voc_cumsum, h->voc_U, f_lo, N, c.voc_embedding_dim, frames, st);
   // conv_pre
@@ -672,9 +687,15 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
     L = Lout;
     ch = U.cout;
     // xs = sum_j resblock_j(x) / num_kernels  (hifigan.py:158-165); ResBlock.forward :95-102
-    for (int j = 0; j < c.voc_n_rb; ++j) {
+    if (fan_out) {
+      cudaEventRecord(h->fork_event, st);
+      for (int q = 0; q < 2; ++q) cudaStreamWaitEvent(h->aux_stream[q], h->fork_event, 0);
+    }
+    for (int j = 0; j < nrb; ++j) {
+      cudaStream_t sj = (fan_out && j > 0) ? h->aux_stream[j - 1] : st;
+      set_splitk_slot(fan_out ? j : 0);
       const float* cur = bufY;
-      float* pingpong[2] = {bufA, bufB};
+      float* pingpong[2] = {rbA[j], rbB[j]};
       int nd = c.voc_rb_ndil;
       for (int m = 0; m < nd; ++m) {
         const ConvW& w1 = h->rb1[i][j][m];
@@ -682,32 +703,36 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
         ConvA a1;
         a1.x = cur; a1.B = 1; a1.L_in = L; a1.L_rows = L; a1.C_in = ch; a1.ldx = ch; a1.ksize = w1.ksize; a1.dil = w1.dil;
         a1.pad_left = (w1.ksize * w1.dil - w1.dil) / 2; a1.pre_lrelu = 0.1f;
-        Epilogue e1 = ep_out(bufT, ch);
+        Epilogue e1 = ep_out(rbT[j], ch);
         e1.bias = w1.lin.b;
-        conv_gemm(a1, w1.lin.w, ch, e1, st);
+        conv_gemm(a1, w1.lin.w, ch, e1, sj);
         ConvA a2;
-        a2.x = bufT; a2.B = 1; a2.L_in = L; a2.L_rows = L; a2.C_in = ch; a2.ldx = ch; a2.ksize = w2.ksize; a2.dil = 1;
+        a2.x = rbT[j]; a2.B = 1; a2.L_in = L; a2.L_rows = L; a2.C_in = ch; a2.ldx = ch; a2.ksize = w2.ksize; a2.dil = 1;
         a2.pad_left = (w2.ksize - 1) / 2; a2.pre_lrelu = 0.1f;
         Epilogue e2;
         e2.bias = w2.lin.b;
         e2.ldo = ch;
+        e2.residual = cur;  // x = xt + x
         if (m + 1 < nd) {
           e2.out = pingpong[m & 1];
-          e2.residual = cur;  // x = xt + x
           e2.res_scale = 1.0f;
         } else {
-          // last pair of the block: accumulate (xt + x) / num_kernels into the stage output
-          e2.out = bufX;
-          e2.alpha = 1.0f / c.voc_n_rb;
-          e2.residual = cur;
-          e2.res_scale = 1.0f / c.voc_n_rb;
-          e2.accumulate = (j > 0);
+          // last pair of the block: (xt + x) / num_kernels, summed over the blocks below
+          e2.out = nrb == 3 ? rbO[j] : bufX;
+          e2.alpha = 1.0f / nrb;
+          e2.res_scale = 1.0f / nrb;
+          e2.accumulate = nrb != 3 && j > 0;  // (other block counts: accumulate in place, single stream)
         }
-        // NB: residual and out must not alias for the accumulate form; cur is bufY/bufA/bufB, out is bufX or the other ping-pong
-        conv_gemm(a2, w2.lin.w, ch, e2, st);
+        conv_gemm(a2, w2.lin.w, ch, e2, sj);
         cur = e2.out;
       }
+      if (fan_out && j > 0) cudaEventRecord(h->join_event[j - 1], sj);
     }
+    set_splitk_slot(0);
+    if (fan_out)
+      for (int q = 0; q < 2; ++q) cudaStreamWaitEvent(st, h->join_event[q], 0);
+    // stage output in the reference's summation order: block 0, then + block 1, then + block 2
+    if (nrb == 3) add3_f32(rbO[0], rbO[1], rbO[2], bufX, (int64_t)L * ch, st);
   }
   // x = leaky_relu(x) [slope 0.01, hifigan.py:166]; conv_post; tanh
   conv_post_tanh(bufX, L, ch, h->conv_post_w, h->conv_post_b, h->conv_post_k, 0.01f, wav, st);
@@ -721,6 +746,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   if (n == "umma_vocoder") h->umma_vocoder = value;
   else if (n == "umma_linear") h->umma_linear = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
+  else if (n == "vocoder_streams") h->vocoder_streams = value;
   else if (n == "persistent_barrier") {
     if (value && !h->persist_bar) {
       if (cudaMalloc(&h->persist_bar, 256) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");

@@ -442,6 +442,11 @@ int ss_destroy(ss_engine* h) {
   if (h->voc_unit_emb) cudaFree(h->voc_unit_emb);
   if (h->voc_cumsum) cudaFree(h->voc_cumsum);
   if (h->lengths_dev) cudaFree(h->lengths_dev);
+  for (int i = 0; i < 2; ++i) {
+    if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
+    if (h->join_event[i]) cudaEventDestroy(h->join_event[i]);
+  }
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
   delete h;
   return SS_OK;
 }

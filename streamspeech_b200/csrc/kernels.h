@@ -66,6 +66,8 @@ void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaSt
 
 // split-K scratch (one per process; launches of a handle are stream-ordered) and its fixed-order reduce + epilogue
 float* splitk_workspace(size_t bytes);
+// split-K scratch region (0..2) used by the GEMM launches of the calling thread from now on; 0 is the default
+void set_splitk_slot(int slot);
 void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, const Epilogue& ep, cudaStream_t st);
 
 // tcgen05 tensor-core GEMM with bf16 operand splitting (pieces = 2: 3 MMAs, ~2^-16 relative; pieces = 3: 6 MMAs,
@@ -125,5 +127,7 @@ void expand_frames(const float* emb /*[U][C]*/, const int* cumsum /*[U+1]*/, int
 void conv_post_tanh(const float* x, int L, int C, const float* w /*[k][C]*/, float bias, int k, float pre_slope, float* out,
                     cudaStream_t st);
 void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
+// out = c + (b + a), elementwise (n % 4 == 0): joins the vocoder's three resblock streams in the reference's summation order
+void add3_f32(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t st);
 
 }  // namespace ss

@@ -259,24 +259,33 @@ __global__ void splitk_epilogue_kernel(const float* __restrict__ ws, int splits,
   *op = y;
 }
 
-// scratch for split-K partial sums (one per process; all launches of a handle are stream-ordered)
-float* g_splitk_ws = nullptr;
-size_t g_splitk_cap = 0;
+// scratch for split-K partial sums: one process-wide buffer of SPLITK_SLOTS independent regions.  Launches of a handle
+// are stream-ordered; an entry point that fans work out over several streams (the vocoder's three parallel resblocks)
+// gives each stream its own region with set_splitk_slot().
+float* g_splitk_base = nullptr;
 constexpr size_t SPLITK_WS_BYTES = 32u << 20;
+constexpr int SPLITK_SLOTS = 3;
+thread_local int g_splitk_slot = 0;
+
+float* splitk_region() {
+  if (!g_splitk_base) {
+    if (cudaMalloc((void**)&g_splitk_base, SPLITK_WS_BYTES * SPLITK_SLOTS) != cudaSuccess) {
+      g_splitk_base = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return g_splitk_base + (size_t)g_splitk_slot * (SPLITK_WS_BYTES / sizeof(float));
+}
 
 }  // namespace
 
 float* splitk_workspace(size_t bytes) {
   if (bytes > SPLITK_WS_BYTES) return nullptr;
-  if (!g_splitk_ws) {
-    if (cudaMalloc((void**)&g_splitk_ws, SPLITK_WS_BYTES) != cudaSuccess) {
-      g_splitk_ws = nullptr;
-      return nullptr;
-    }
-    g_splitk_cap = SPLITK_WS_BYTES;
-  }
-  return g_splitk_ws;
+  return splitk_region();
 }
+
+void set_splitk_slot(int slot) { g_splitk_slot = (slot >= 0 && slot < SPLITK_SLOTS) ? slot : 0; }
 
 void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, const Epilogue& ep, cudaStream_t st) {
   ++g_launches;
@@ -299,16 +308,13 @@ void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue&
   float* ws = nullptr;
   int tiles = nk;
   if (splits > 1) {
-    if (!g_splitk_ws) {
-      if (cudaMalloc((void**)&g_splitk_ws, SPLITK_WS_BYTES) != cudaSuccess) { g_splitk_ws = nullptr; splits = 1; }
-      else g_splitk_cap = SPLITK_WS_BYTES;
-    }
+    ws = splitk_region();
+    if (!ws) splits = 1;
   }
   if (splits > 1) {
     tiles = (nk + splits - 1) / splits;
     splits = (nk + tiles - 1) / tiles;
     grid.z = splits;
-    ws = g_splitk_ws;
   }
   if (conv)
     gemm_kernel<BM, BN, true><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);  // tile GEMMs never launch early (see launch_pdl)

@@ -81,6 +81,20 @@ __global__ void scale_kernel(float* x, int64_t n, float s) {
   if (i < n) x[i] *= s;
 }
 
+__global__ void add3_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c, float4* __restrict__ out,
+                            int64_t n4) {
+  pdl_trigger();
+  pdl_wait();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 x = a[i], y = b[i], z = c[i], r;
+  r.x = z.x + (y.x + x.x);
+  r.y = z.y + (y.y + x.y);
+  r.z = z.z + (y.z + x.z);
+  r.w = z.w + (y.w + x.w);
+  out[i] = r;
+}
+
 __global__ void copy_kernel(const float* __restrict__ s, float* __restrict__ d, int64_t n) {
   pdl_trigger();
   pdl_wait();
@@ -308,6 +322,13 @@ void scale_rows(float* x, int64_t n, float s, cudaStream_t st) {
   ++g_launches;
   if (n <= 0) return;
   launch_pdl(scale_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, n, s);
+}
+
+void add3_f32(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t st) {
+  ++g_launches;
+  if (n <= 0) return;
+  const int64_t n4 = n / 4;
+  launch_pdl(add3_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, (const float4*)a, (const float4*)b, (const float4*)c, (float4*)out, n4);
 }
 
 void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st) {
