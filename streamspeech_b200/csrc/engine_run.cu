@@ -468,6 +468,7 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
   // round trip.  Steps are enqueued in bursts; the host reads the burst's tokens back once and stops at the first eos
   // (steps enqueued past an eos only produce rows that are never read).
   const int burst = (max_new_tokens >= 0) ? std::max(1, max_new_tokens) : 16;
+  const bool persistent_mt = h->persistent_mt && mt_decode_persistent_supported(dim, c.mt_ffn, c.mt_heads, c.tgt_vocab, c.max_mt_positions, T);
   int step = start;
   bool done = false;
   while (!done) {
@@ -476,6 +477,24 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
     for (; step <= max_len && enq < burst; ++step, ++enq) {
       // feed tokens[fed .. step]  (first iteration: the whole prefix; afterwards one token)
       int n = step + 1 - fed;
+      if (n == 1 && persistent_mt && h->persist_bar) {
+        // the rest of the burst as ONE cooperative launch (it stops by itself at eos / max_len)
+        const int cnt = std::min(max_len - step + 1, burst - enq);
+        MtDecodeParams P;
+        P.n_layers = c.mt_layers; P.heads = c.mt_heads; P.vocab = c.tgt_vocab; P.pad = c.pad; P.eos = c.eos;
+        P.max_pos = c.max_mt_positions; P.cross_cap = h->mt_cross_cap;
+        P.emb = h->mt_emb; P.pos = h->mt_pos; P.out_g = h->mt_ln.g; P.out_b = h->mt_ln.b;
+        P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
+        P.tok = h->mt_tok_dev; P.feats = feats_out_dev; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
+        if (mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, T, h->persist_bar, &h->persist_bar_target, st) == 0) {
+          fed = step + cnt;
+          if (step + cnt - 1 >= max_len) done = true;
+          step += cnt;
+          enq += cnt;
+          break;
+        }
+        cudaGetLastError();  // refused launch: per-kernel path below
+      }
       mt_forward(h, fed, n, T, nullptr, feats_out_dev + (size_t)fed * dim, s, x, st);
       fed = step + 1;
       if (step >= max_len) {  // eos is forced here (sequence_generator.py:362-364): no need for the logits
@@ -747,6 +766,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "umma_linear") h->umma_linear = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
   else if (n == "vocoder_streams") h->vocoder_streams = value;
+  else if (n == "persistent_mt") h->persistent_mt = value;
   else if (n == "persistent_barrier") {
     if (value && !h->persist_bar) {
       if (cudaMalloc(&h->persist_bar, 256) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");

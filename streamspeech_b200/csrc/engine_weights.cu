@@ -297,6 +297,16 @@ void finalize_impl(ss_engine* h) {
     h->mt_tok_dev = dev_alloc<int64_t>(h, c.max_mt_positions + 8);
     h->mt_next_dev = dev_alloc<int64_t>(h, 8);
     cudaMallocHost((void**)&h->mt_next_pinned, (size_t)(c.max_mt_positions + 8) * sizeof(int64_t));
+    std::vector<MtLayerP> ml(c.mt_layers);
+    for (int i = 0; i < c.mt_layers; ++i) {
+      const DecLayerW& L = h->mt[i];
+      MtLayerP& q = ml[i];
+      q.self_g = L.self_ln.g; q.self_b = L.self_ln.b; q.wqkv = L.qkv.w; q.bqkv = L.qkv.b; q.wo = L.out.w; q.bo = L.out.b;
+      q.cross_g = L.cross_ln.g; q.cross_b = L.cross_ln.b; q.wcq = L.cq.w; q.bcq = L.cq.b; q.wco = L.cout.w; q.bco = L.cout.b;
+      q.fin_g = L.final_ln.g; q.fin_b = L.final_ln.b; q.w1 = L.fc1.w; q.b1 = L.fc1.b; q.w2 = L.fc2.w; q.b2 = L.fc2.b;
+    }
+    h->mt_persist_layers = dev_alloc<MtLayerP>(h, ml.size());
+    cudaMemcpy(h->mt_persist_layers, ml.data(), ml.size() * sizeof(MtLayerP), cudaMemcpyHostToDevice);
   }
   // ---- T2U encoder + unit decoder
   for (int i = 0; i < c.t2u_layers; ++i)

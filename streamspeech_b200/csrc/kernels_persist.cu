@@ -52,7 +52,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     unsigned v, spins = 0;
     do {  // (bounded: a counter out of step with the host's target must not hang the device)
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while ((int)(v - target) < 0 && ++spins < (1u << 22));
+    } while ((int)(v - target) < 0 && ++spins < (1u << 18));
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();

@@ -1,6 +1,7 @@
 // Persistent cooperative encoder-stack kernel (kernels_persist.cu): one launch per streaming step for all layers.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace ss {
 
@@ -18,5 +19,25 @@ int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, floa
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
                               unsigned long long* timestamps_or_null, unsigned* barrier_counter_dev_or_null,
                               unsigned* barrier_target_host, cudaStream_t st);
+
+// ---- MT decoder, single-token greedy steps (kernels_persist_mt.cu)
+struct MtLayerP {  // device pointers of one pre-LN decoder layer (fp32, [N][K] weights)
+  const float *self_g, *self_b, *wqkv, *bqkv, *wo, *bo;
+  const float *cross_g, *cross_b, *wcq, *bcq, *wco, *bco;
+  const float *fin_g, *fin_b, *w1, *b1, *w2, *b2;
+};
+struct MtDecodeParams {
+  int n_layers, heads, vocab, pad, eos, max_pos, cross_cap;
+  const float *emb, *pos, *out_g, *out_b;   // tied embedding / output projection [vocab][dim], sinusoidal table, final LN
+  float *self_k, *self_v;                   // [layers][max_pos][dim]
+  const float* cross_kv;                    // [layers][cross_cap][2 * dim] (K | V per row)
+  int64_t* tok;                             // device token buffer: tok[s] is fed at step s, the arg-max goes to tok[s + 1]
+  float* feats;                             // [.][dim] final-LN features, row s
+  float *x, *q, *attn, *hid, *logits;       // scratch: dim, dim, dim, ffn, vocab floats
+};
+bool mt_decode_persistent_supported(int dim, int ffn, int heads, int vocab, int max_pos, int T);
+// enqueue `nsteps` greedy steps starting with the token at position step0; returns 0, or < 0 if the launch was refused
+int mt_decode_persistent(const MtDecodeParams& P, const MtLayerP* layers_dev, int step0, int nsteps, int max_len, int T,
+                         unsigned* barrier_counter_dev, unsigned* barrier_target_host, cudaStream_t st);
 
 }  // namespace ss

@@ -1,0 +1,364 @@
+// Persistent cooperative kernel for the single-token steps of the MT decoder's greedy search (beam 1).
+//
+// One decode step is a chain of ~37 dependent M = 1 operations (4 pre-LN layers of self-attention, cross-attention and
+// FFN, the tied output projection over 6000 entries and the arg-max); as separate kernels it costs ~175 us per token,
+// nearly all of it kernel boundaries (profiles/r1_stage_*).  This kernel keeps one CTA per SM resident for a whole burst
+// of steps and separates the phases with the counter barrier of kernels_persist.cu (33 barriers per token):
+//   per layer: [LN + QKV -> q, K/V cache row] | [self-attention, CTA per head] | [out + res] | [LN + Q] |
+//              [cross-attention over the encoder states, CTA per head] | [out + res] | [LN + FC1 + ReLU] | [FC2 + res]
+//   then:      [final LN -> features row, logits = E @ feat] | arg-max of log_softmax (every CTA redundantly) + embedding
+// The 512-float residual stream lives in global memory and is re-read into shared memory by every CTA after each phase
+// that updates it; GEMV phases give each warp up to MAXC output columns and issue all weight loads before the reduction.
+// Semantics follow ss_mt_greedy's per-kernel path (sequence_generator.py:generate_decoder with beam 1): pad is always
+// masked, eos only while step < min_len (= 1), eos is forced at max_len (no logits are computed for that step).
+#include "common.cuh"
+#include "kernels.h"
+#include "kernels_persist.h"
+
+namespace ss {
+namespace {
+
+constexpr int MW = 8;
+constexpr int MTT = MW * 32;
+constexpr int MHD = 64;
+
+__device__ __forceinline__ float4 ldw(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned v, spins = 0;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0 && ++spins < (1u << 18));
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+struct MtSmem {
+  float x[512];     // residual stream of the token (model dim <= 512)
+  float v[2048];    // GEMV input vector (LN(x), attention output or FFN hidden)
+  float S[1024];    // attention scores
+  float qh[MHD];
+  float pv[4][MHD];
+  float red[MW];
+  float rbest[MW];
+  int ridx[MW];
+  int tok;
+};
+
+__device__ __forceinline__ float block_reduce_sum(MtSmem& sm, float v) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm.red[w] = v;
+  __syncthreads();
+  float t = sm.red[0];
+#pragma unroll
+  for (int i = 1; i < MW; ++i) t += sm.red[i];
+  return t;
+}
+__device__ __forceinline__ float block_reduce_max(MtSmem& sm, float v) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sm.red[w] = v;
+  __syncthreads();
+  float t = sm.red[0];
+#pragma unroll
+  for (int i = 1; i < MW; ++i) t = fmaxf(t, sm.red[i]);
+  return t;
+}
+
+// sm.v[0..dim) = LayerNorm(sm.x[0..dim)) (two-pass, as layer_norm_kernel); dim == 512: two values per thread
+__device__ __forceinline__ void ln_to_v(MtSmem& sm, const float* __restrict__ g, const float* __restrict__ b, int dim) {
+  const int t = threadIdx.x;
+  float a0 = sm.x[t], a1 = sm.x[t + MTT];
+  float mean = block_reduce_sum(sm, a0 + a1) / (float)dim;
+  float d0 = a0 - mean, d1 = a1 - mean;
+  float var = block_reduce_sum(sm, fmaf(d0, d0, d1 * d1)) / (float)dim;
+  float rstd = 1.0f / sqrtf(var + 1e-5f);
+  sm.v[t] = d0 * rstd * g[t] + b[t];
+  sm.v[t + MTT] = d1 * rstd * g[t + MTT] + b[t + MTT];
+  __syncthreads();
+}
+
+// coherent copy global -> shared (activations written by other CTAs before the last barrier)
+__device__ __forceinline__ void load_vec(float* dst, const float* src, int n) {
+  for (int i = threadIdx.x * 4; i < n; i += MTT * 4) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
+  __syncthreads();
+}
+
+// y[col] = epi(col, W[col][:] . xs) for col in [0, N): warp gw owns columns gw, gw + nw, ... (at most MAXC: every phase is
+// sized so that one round covers N).  Split in two so that the weight loads are in flight while the CTA stages the input
+// vector (global -> shared, LayerNorm): gemv_issue() before the staging, gemv_finish() after it.
+template <int K, int MAXC>
+struct GemvW {
+  float4 w[MAXC][K / 128];
+};
+template <int K, int MAXC>
+__device__ __forceinline__ void gemv_issue(GemvW<K, MAXC>& r, const float* __restrict__ W, int N) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * MW + (threadIdx.x >> 5), nw = gridDim.x * MW;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = gw + c * nw;
+#pragma unroll
+    for (int it = 0; it < K / 128; ++it)
+      r.w[c][it] = col < N ? ldw(W + (int64_t)col * K + it * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int K, int MAXC, typename F>
+__device__ __forceinline__ void gemv_finish(const GemvW<K, MAXC>& r, const float* xs, int N, F&& epi) {
+  constexpr int NIT = K / 128;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * MW + (threadIdx.x >> 5), nw = gridDim.x * MW;
+  float4 xv[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) xv[it] = *reinterpret_cast<const float4*>(xs + it * 128 + lane * 4);
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      acc = fmaf(xv[it].x, r.w[c][it].x, acc);
+      acc = fmaf(xv[it].y, r.w[c][it].y, acc);
+      acc = fmaf(xv[it].z, r.w[c][it].z, acc);
+      acc = fmaf(xv[it].w, r.w[c][it].w, acc);
+    }
+    acc = warp_sum(acc);
+    const int col = gw + c * nw;
+    if (lane == 0 && col < N) epi(col, acc);
+  }
+}
+
+// softmax(q . K^T * scale) V for one head by one CTA: q[64], K/V rows at kbase/vbase + j * ld, n keys; out[64]
+__device__ void attend_head(MtSmem& sm, const float* q, const float* kbase, const float* vbase, int ld, int n, float* out) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid < MHD) sm.qh[tid] = q[tid] * 0.125f;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < n; j += MTT) {
+    const float* kr = kbase + (int64_t)j * ld;
+    float4 kk[MHD / 4];
+#pragma unroll
+    for (int d = 0; d < MHD / 4; ++d) kk[d] = *reinterpret_cast<const float4*>(kr + 4 * d);
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < MHD / 4; ++d) {
+      s = fmaf(sm.qh[4 * d], kk[d].x, s);
+      s = fmaf(sm.qh[4 * d + 1], kk[d].y, s);
+      s = fmaf(sm.qh[4 * d + 2], kk[d].z, s);
+      s = fmaf(sm.qh[4 * d + 3], kk[d].w, s);
+    }
+    sm.S[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce_max(sm, mx);
+  float sum = 0.f;
+  for (int j = tid; j < n; j += MTT) {
+    float e = expf(sm.S[j] - mx);
+    sm.S[j] = e;
+    sum += e;
+  }
+  sum = block_reduce_sum(sm, sum);
+  // thread (part, d): keys j = part (mod 4)
+  const int d = tid & (MHD - 1), part = tid >> 6;
+  float a = 0.f;
+#pragma unroll 4
+  for (int j = part; j < n; j += 4) a = fmaf(sm.S[j], vbase[(int64_t)j * ld + d], a);
+  sm.pv[part][d] = a;
+  __syncthreads();
+  if (tid < MHD) out[tid] = ((sm.pv[0][tid] + sm.pv[1][tid]) + (sm.pv[2][tid] + sm.pv[3][tid])) / sum;
+}
+
+__global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel(MtDecodeParams P, const MtLayerP* __restrict__ layers, int step0,
+                                                                      int nsteps, int max_len, int T, unsigned* bar_ctr,
+                                                                      unsigned bar_target) {
+  __shared__ __align__(16) MtSmem sm;
+  constexpr int DIM = 512, FFN = 2048;
+  const int tid = threadIdx.x;
+  const int barriers_per_step = P.n_layers * 8 + 1;
+  int done_barriers = 0;
+  const float emb_scale = sqrtf((float)DIM);
+#define BAR()                          \
+  grid_barrier(bar_ctr, bar_target);   \
+  ++done_barriers;
+  for (int si = 0; si < nsteps; ++si) {
+    const int s = step0 + si;  // position of the token fed in this step = its row in the self-attention cache
+    // ---- embedding (every CTA; the token was written by the previous step's arg-max or by the host)
+    {
+      const int64_t tok = (si == 0) ? P.tok[s] : (int64_t)sm.tok;  // later tokens: this CTA's own arg-max (no barrier needed)
+      const int p = (tok == P.pad) ? P.pad : P.pad + 1 + s;
+      for (int c = tid; c < DIM; c += MTT) sm.x[c] = emb_scale * P.emb[tok * DIM + c] + P.pos[(int64_t)p * DIM + c];
+      __syncthreads();
+    }
+    for (int l = 0; l < P.n_layers; ++l) {
+      const MtLayerP L = layers[l];
+      float* kc = P.self_k + ((size_t)l * P.max_pos + s) * DIM;
+      float* vc = P.self_v + ((size_t)l * P.max_pos + s) * DIM;
+      // (1) q | k | v = LN(x) Wqkv^T
+      GemvW<DIM, 2> w_qkv;
+      gemv_issue(w_qkv, L.wqkv, 3 * DIM);
+      if (l > 0) load_vec(sm.x, P.x, DIM);
+      ln_to_v(sm, L.self_g, L.self_b, DIM);
+      gemv_finish(w_qkv, sm.v, 3 * DIM, [&](int col, float acc) {
+        float y = acc + (L.bqkv ? L.bqkv[col] : 0.f);
+        if (col < DIM) P.q[col] = y;
+        else if (col < 2 * DIM) kc[col - DIM] = y;
+        else vc[col - 2 * DIM] = y;
+      });
+      BAR();
+      // (2) causal self-attention over rows 0..s of the cache
+      if (blockIdx.x < P.heads) {
+        const int h = blockIdx.x;
+        attend_head(sm, P.q + h * MHD, P.self_k + (size_t)l * P.max_pos * DIM + h * MHD, P.self_v + (size_t)l * P.max_pos * DIM + h * MHD, DIM,
+                    s + 1, P.attn + h * MHD);
+      }
+      BAR();
+      // (3) x += attn Wo^T
+      GemvW<DIM, 1> w_o;
+      gemv_issue(w_o, L.wo, DIM);
+      load_vec(sm.v, P.attn, DIM);
+      gemv_finish(w_o, sm.v, DIM, [&](int col, float acc) { P.x[col] = (acc + (L.bo ? L.bo[col] : 0.f)) + sm.x[col]; });
+      BAR();
+      // (4) q = LN(x) Wcq^T
+      GemvW<DIM, 1> w_cq;
+      gemv_issue(w_cq, L.wcq, DIM);
+      load_vec(sm.x, P.x, DIM);
+      ln_to_v(sm, L.cross_g, L.cross_b, DIM);
+      gemv_finish(w_cq, sm.v, DIM, [&](int col, float acc) { P.q[col] = acc + (L.bcq ? L.bcq[col] : 0.f); });
+      BAR();
+      // (5) cross-attention over the T encoder states (K | V rows precomputed by mt_begin)
+      if (blockIdx.x < P.heads) {
+        const int h = blockIdx.x;
+        const float* cross = P.cross_kv + (size_t)l * P.cross_cap * 2 * DIM;
+        attend_head(sm, P.q + h * MHD, cross + h * MHD, cross + DIM + h * MHD, 2 * DIM, T, P.attn + h * MHD);
+      }
+      BAR();
+      // (6) x += attn Wco^T
+      GemvW<DIM, 1> w_co;
+      gemv_issue(w_co, L.wco, DIM);
+      load_vec(sm.v, P.attn, DIM);
+      gemv_finish(w_co, sm.v, DIM, [&](int col, float acc) { P.x[col] = (acc + (L.bco ? L.bco[col] : 0.f)) + sm.x[col]; });
+      BAR();
+      // (7) hid = relu(LN(x) W1^T)
+      GemvW<DIM, 2> w_1;
+      gemv_issue(w_1, L.w1, FFN);
+      load_vec(sm.x, P.x, DIM);
+      ln_to_v(sm, L.fin_g, L.fin_b, DIM);
+      gemv_finish(w_1, sm.v, FFN, [&](int col, float acc) {
+        float y = acc + (L.b1 ? L.b1[col] : 0.f);
+        P.hid[col] = y > 0.f ? y : 0.f;
+      });
+      BAR();
+      // (8) x += hid W2^T
+      GemvW<FFN, 1> w_2;
+      gemv_issue(w_2, L.w2, DIM);
+      load_vec(sm.v, P.hid, FFN);
+      gemv_finish(w_2, sm.v, DIM, [&](int col, float acc) { P.x[col] = (acc + (L.b2 ? L.b2[col] : 0.f)) + sm.x[col]; });
+      BAR();
+    }
+    // ---- final LN -> feature row; logits over the tied embedding unless eos is forced at this step
+    const bool forced_eos = s >= max_len;
+    GemvW<DIM, 6> w_out;
+    if (!forced_eos) gemv_issue(w_out, P.emb, P.vocab);
+    load_vec(sm.x, P.x, DIM);
+    ln_to_v(sm, P.out_g, P.out_b, DIM);
+    if (blockIdx.x == 0)
+      for (int c = tid; c < DIM; c += MTT) P.feats[(size_t)s * DIM + c] = sm.v[c];
+    if (!forced_eos) gemv_finish(w_out, sm.v, P.vocab, [&](int col, float acc) { P.logits[col] = acc; });
+    BAR();
+    if (forced_eos) break;
+    // ---- arg-max of log_softmax(logits) with masks, first index wins on ties (argmax_rows_kernel); every CTA
+    {
+      const float* x = P.logits;
+      float mx = -INFINITY;
+      for (int c = tid; c < P.vocab; c += MTT) mx = fmaxf(mx, x[c]);
+      mx = block_reduce_max(sm, mx);
+      float su = 0.f;
+      for (int c = tid; c < P.vocab; c += MTT) su += expf(x[c] - mx);
+      su = block_reduce_sum(sm, su);
+      const float lse = logf(su);
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = tid; c < P.vocab; c += MTT) {
+        const bool masked = (c == P.pad) || (s < 1 && c == P.eos);
+        float lp = masked ? -INFINITY : (x[c] - mx) - lse;
+        if (lp > best || (lp == best && c < bi)) {
+          best = lp;
+          bi = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
+      }
+      __syncthreads();
+      if ((tid & 31) == 0) {
+        sm.rbest[tid >> 5] = best;
+        sm.ridx[tid >> 5] = bi;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int i = 1; i < MW; ++i)
+          if (sm.rbest[i] > best || (sm.rbest[i] == best && sm.ridx[i] < bi)) {
+            best = sm.rbest[i];
+            bi = sm.ridx[i];
+          }
+        sm.tok = bi;
+        if (blockIdx.x == 0) P.tok[s + 1] = bi;
+      }
+      __syncthreads();
+      if (sm.tok == P.eos) break;  // the host stops at the first eos; later steps would never be read
+    }
+  }
+#undef BAR
+  // leave the barrier counter where the host expects it after a full burst
+  const int planned = nsteps * barriers_per_step;
+  if (threadIdx.x == 0 && done_barriers < planned) atomicAdd(bar_ctr, (unsigned)(planned - done_barriers));
+}
+
+}  // namespace
+
+bool mt_decode_persistent_supported(int dim, int ffn, int heads, int vocab, int max_pos, int T) {
+  // (one round of columns per phase: vocab <= 6 columns x 8 warps x #SMs, checked against the smallest supported grid)
+  return vocab <= 6 * MW * 132 && dim == 512 && ffn == 2048 && heads * MHD == dim && vocab >= 1 && max_pos <= 1024 && T >= 1 && T <= 1024;
+}
+
+int mt_decode_persistent(const MtDecodeParams& P, const MtLayerP* layers_dev, int step0, int nsteps, int max_len, int T, unsigned* bar_ctr,
+                         unsigned* bar_target_host, cudaStream_t st) {
+  ++g_launches;
+  static int grid = 0;
+  if (grid == 0) {
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mt_decode_persistent_kernel, MTT, 0);
+    if (occ < 1) return -1;
+    grid = sms;
+  }
+  if (grid < 128 || P.vocab > 6 * MW * grid) return -1;  // one round of columns per GEMV phase (see gemv_issue)
+  MtDecodeParams p = P;
+  unsigned bar_target = *bar_target_host;
+  void* args[] = {(void*)&p, (void*)&layers_dev, (void*)&step0, (void*)&nsteps, (void*)&max_len, (void*)&T, (void*)&bar_ctr, (void*)&bar_target};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)mt_decode_persistent_kernel, dim3(grid), dim3(MTT), args, 0, st);
+  if (e != cudaSuccess) return -2;
+  *bar_target_host += (unsigned)grid * (unsigned)(nsteps * (P.n_layers * 8 + 1));
+  return 0;
+}
+
+}  // namespace ss

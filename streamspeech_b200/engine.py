@@ -174,6 +174,7 @@ class Engine:
         self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "0")))
         self.set_option("umma_linear", int(os.environ.get("SS_UMMA_LINEAR", "0")))
         self.set_option("persistent_encoder", int(os.environ.get("SS_PERSISTENT_ENCODER", "1")))
+        self.set_option("persistent_mt", int(os.environ.get("SS_PERSISTENT_MT", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))
         self.set_option("persistent_barrier", int(os.environ.get("SS_PERSISTENT_BARRIER", "1")))
         self.hop = self.lib.ss_vocoder_hop(self._h)
