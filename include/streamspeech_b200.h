@@ -103,6 +103,11 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
  * argmax_dev[rows] int64; tokens_dev[rows] int64 / index_dev[rows] int32 hold *count_dev collapsed entries. enqueue only */
 int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev,
                   int64_t* tokens_dev, int32_t* index_dev, int32_t* count_dev);
+/* Same, for a caller that keeps `argmax_dev` across calls on a growing sequence: only rows [row0, rows) are projected and
+ * arg-maxed (rows below row0 keep their cached arg-max, valid when those encoder rows have not changed, i.e. they are
+ * below the T_final of the previous ss_encoder_stream_step); the collapse runs over all `rows`. */
+int ss_ctc_greedy_rows(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int row0, int64_t* argmax_dev,
+                       int64_t* tokens_dev, int32_t* index_dev, int32_t* count_dev);
 
 /* ---- M1/M2: SequenceGenerator.generate_decoder, beam 1 (agent/sequence_generator.py:165-582) + the extra
  * mt_decoder(prev_output_tokens, features_only=True) forward (agent:638-642).

@@ -119,13 +119,16 @@ class _EngineAgentMixin:
         self._resident = None
         self.encoder_mode = getattr(args, "encoder_mode", "cached")
         self.enc_buf = torch.zeros(getattr(args, "max_enc_frames", 1024), cfg.enc_dim, dtype=torch.float32, device=self.torch_device)
+        self._enc_final = 0
+        self._ctc_valid = [0, 0]
 
     def _encode(self, feature: torch.Tensor) -> torch.Tensor:
         """forward_encoder (agent:433).  "cached": only the rows of the not yet final chunk group are recomputed
         (ss_encoder_stream_step); "recompute": the whole prefix every call, like the reference."""
         if self.encoder_mode == "recompute":
             return self.engine.encoder(feature.unsqueeze(0))[0]
-        T, _ = self.engine.encoder_stream_step(feature, self.enc_buf)
+        T, t_final = self.engine.encoder_stream_step(feature, self.enc_buf)
+        self._enc_final = t_final  # rows below it never change again (their CTC arg-max can be cached, see _ctc)
         return self.enc_buf[:T]
 
     def step_resident(self, audio_dev: torch.Tensor, n_valid: int, finished: bool):
@@ -146,6 +149,8 @@ class _EngineAgentMixin:
             self.audio.n = 0
             self.n_feat = 0
             self.engine.encoder_stream_reset()
+        self._enc_final = 0
+        self._ctc_valid = [0, 0]
 
     def _features(self):
         """OnlineFeatureExtractor.__call__ (agent:66-87) with a per-frame cache."""
@@ -164,9 +169,14 @@ class _EngineAgentMixin:
         return self.feat_cache[:F]
 
     def _ctc(self, head: int, enc: torch.Tensor):
-        r = self.engine.ctc_greedy(head, enc)
-        n = int(r["count"].item())
-        return r["tokens"][:n].tolist(), r["index"][:n].tolist()
+        """CTC greedy over the encoder rows so far.  Encoder rows below the previous step's T_final are final, so their
+        arg-max is cached on the device and only the newer rows are projected (ss_ctc_greedy_rows)."""
+        if not hasattr(self, "_ctc_am") or self._ctc_am.shape[1] < self.enc_buf.shape[0]:
+            self._ctc_am = torch.zeros(2, self.enc_buf.shape[0], dtype=torch.int64, device=self.enc_buf.device)
+        row0 = min(self._ctc_valid[head], enc.shape[0]) if self.encoder_mode == "cached" else 0
+        out = self.engine.ctc_greedy_rows(head, enc, row0, self._ctc_am[head])
+        self._ctc_valid[head] = min(self._enc_final, enc.shape[0])  # arg-max of rows that are final now is reusable
+        return out
 
 
 @entrypoint

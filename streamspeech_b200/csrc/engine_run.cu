@@ -383,19 +383,27 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
   return check_launch(h, "ss_encoder_stream_step");
 }
 
-int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev, int64_t* tokens_dev,
-                  int32_t* index_dev, int32_t* count_dev) {
+int ss_ctc_greedy_rows(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int row0, int64_t* argmax_dev,
+                       int64_t* tokens_dev, int32_t* index_dev, int32_t* count_dev) {
   if (h) g_umma_linear = h->umma_linear;
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
-  if (head < 0 || head > 1 || rows <= 0) return h->fail(SS_ERR_INVALID, "bad ctc head / rows");
+  if (head < 0 || head > 1 || rows <= 0 || row0 < 0 || row0 > rows) return h->fail(SS_ERR_INVALID, "bad ctc head / rows");
   const Linear& l = h->ctc_head[head];
   cudaStream_t st = S(stream);
-  if (!ws_begin(h, (size_t)rows * l.N * sizeof(float) + 4096)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
-  float* logits = h->ws.f32((size_t)rows * l.N);
-  linear(enc_dev, h->cfg.enc_dim, rows, l, ep_out(logits, l.N), st);
-  argmax_rows(logits, l.N, rows, l.N, h->mask_pad_unk, 2, argmax_dev, nullptr, st);  // never select pad, unk
+  const int nr = rows - row0;  // rows below row0 keep the arg-max the caller cached from an earlier call
+  if (nr > 0) {
+    if (!ws_begin(h, (size_t)nr * l.N * sizeof(float) + 4096)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+    float* logits = h->ws.f32((size_t)nr * l.N);
+    linear(enc_dev + (size_t)row0 * h->cfg.enc_dim, h->cfg.enc_dim, nr, l, ep_out(logits, l.N), st);
+    argmax_rows(logits, l.N, nr, l.N, h->mask_pad_unk, 2, argmax_dev + row0, nullptr, st);  // never select pad, unk
+  }
   ctc_collapse(argmax_dev, rows, 0 /* <s> is the CTC blank (agent/ctc_decoder.py:72-76) */, h->cfg.pad, tokens_dev, index_dev, count_dev, st);
   return check_launch(h, "ss_ctc_greedy");
+}
+
+int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev, int64_t* tokens_dev,
+                  int32_t* index_dev, int32_t* count_dev) {
+  return ss_ctc_greedy_rows(h, stream, head, enc_dev, rows, 0, argmax_dev, tokens_dev, index_dev, count_dev);
 }
 
 int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* tokens_host, int n, float* feats_out_dev,
@@ -689,20 +697,35 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
   for (int i = 0; i < c.voc_n_ups; ++i) {
     const UpsampleW& U = h->ups[i];
     const int Lout = L * U.u;
-    // x = ups[i](leaky_relu(x, 0.1)): one GEMM per output phase, rows scattered with stride u
+    // x = ups[i](leaky_relu(x, 0.1)): one GEMM per output phase, rows scattered with stride u.  The phases are independent
+    // (disjoint output rows): they are spread over the same three streams as the resblocks below.
+    const bool fan_up = fan_out && U.u > 1;
+    if (fan_up) {
+      cudaEventRecord(h->fork_event, st);
+      for (int q = 0; q < 2; ++q) cudaStreamWaitEvent(h->aux_stream[q], h->fork_event, 0);
+    }
     for (int phi = 0; phi < U.u; ++phi) {
       int J = U.phase_J[phi], q0 = U.phase_q0[phi];
       int qmax = (Lout - 1 - phi + U.pad) / U.u;
       int nrows = qmax - q0 + 1;
       if (nrows <= 0) continue;
+      const int lane = fan_up ? phi % 3 : 0;
+      cudaStream_t sp = lane > 0 ? h->aux_stream[lane - 1] : st;
+      set_splitk_slot(lane);
       ConvA a;
       a.x = bufX; a.B = 1; a.L_in = L; a.L_rows = nrows; a.C_in = U.cin; a.ldx = U.cin; a.ksize = J; a.pad_left = (J - 1) - q0;
       a.pre_lrelu = 0.1f;
       Epilogue e = ep_out(bufY, U.cout);
       e.bias = U.bias;
       e.out_L = Lout; e.out_row_stride = U.u; e.out_row_offset = q0 * U.u + phi - U.pad;
-      conv_gemm(a, U.phase_w[phi].w, U.cout, e, st);
+      conv_gemm(a, U.phase_w[phi].w, U.cout, e, sp);
     }
+    set_splitk_slot(0);
+    if (fan_up)
+      for (int q = 0; q < 2; ++q) {
+        cudaEventRecord(h->join_event[q], h->aux_stream[q]);
+        cudaStreamWaitEvent(st, h->join_event[q], 0);
+      }
     L = Lout;
     ch = U.cout;
     // xs = sum_j resblock_j(x) / num_kernels  (hifigan.py:158-165); ResBlock.forward :95-102

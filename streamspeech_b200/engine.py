@@ -69,6 +69,7 @@ def load_library() -> ctypes.CDLL:
     lib.ss_encoder_stream_reset.argtypes = [vp]
     lib.ss_encoder_stream_step.argtypes = [vp, vp, vp, i32, vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.ss_ctc_greedy.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    lib.ss_ctc_greedy_rows.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
     lib.ss_mt_greedy.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, i32, ctypes.POINTER(i32), vp]
     lib.ss_mt_features.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp]
     lib.ss_t2u_unit_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
@@ -89,7 +90,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
-    "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_mt_greedy",
+    "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_ctc_greedy_rows", "ss_mt_greedy",
     "ss_mt_features", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
     "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count",
 ]
@@ -279,6 +280,23 @@ class Engine:
         cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._check(self.lib.ss_ctc_greedy(self._h, self._stream(), head, enc.data_ptr(), T, am.data_ptr(), toks.data_ptr(), idx.data_ptr(), cnt.data_ptr()))
         return {"argmax": am, "tokens": toks, "index": idx, "count": cnt}
+
+    def ctc_greedy_rows(self, head: int, enc: torch.Tensor, row0: int, argmax: torch.Tensor):
+        """Incremental form for a growing sequence: `argmax` (int64, >= T entries, owned by the caller) already holds the
+        arg-max of rows < row0 from earlier calls; rows [row0, T) are computed, then all T rows are collapsed.
+        Returns (tokens, index) as python lists with ONE device->host copy."""
+        assert enc.is_cuda and enc.is_contiguous() and enc.dim() == 2 and argmax.dtype == torch.int64
+        T = enc.shape[0]
+        out = torch.empty(2 * T + 2, dtype=torch.int64, device=self.device)  # [count | tokens[T] | index (int32 pairs)]
+        toks = out[1:1 + T]
+        idx = out[1 + T:].view(torch.int32)[:T]
+        cnt = out[:1].view(torch.int32)
+        cnt.zero_()
+        self._check(self.lib.ss_ctc_greedy_rows(self._h, self._stream(), head, enc.data_ptr(), T, int(row0), argmax.data_ptr(), toks.data_ptr(),
+                                                idx.data_ptr(), cnt.data_ptr()))
+        host = out.cpu()
+        n = int(host[:1].view(torch.int32)[0])
+        return host[1:1 + n].tolist(), host[1 + T:].view(torch.int32)[:n].tolist()
 
     def mt_greedy(self, enc: torch.Tensor, prefix: Optional[Sequence[int]], max_new_tokens: int, max_len_b: int = 100) -> Tuple[List[int], torch.Tensor]:
         """Returns (tokens without the trailing eos, decoder features of [eos]+tokens as [n+1, mt_dim])."""
