@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--encoder-mode", type=str, default="cached", choices=["cached", "recompute"])
+    ap.add_argument("--ncu-window", action="store_true",
+                    help="after the timed runs, stream one more resident utterance between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -300,6 +302,12 @@ def main():
     utts_host = [u.tolist() for u in utts]
     ms_e2e, out_e2e, _ = timed(stream_e2e, utts_host, args.steps, max(1, args.warmup // 2))
     clocks = sampler.stop() if rank == 0 else None
+    if args.ncu_window and rank == 0:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        stream_resident(utts_dev[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
     if rank != 0:
         if dist is not None:

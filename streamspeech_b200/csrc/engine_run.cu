@@ -21,10 +21,25 @@ int check_launch(ss_engine* h, const char* where) {
 // tensor-core routing of the current entry point (set from the handle at the top of each entry point)
 thread_local int g_umma_linear = 0;
 thread_local int g_umma_conv = 0;
+thread_local int g_umma_min_rows = 128;
+thread_local int g_umma_min_channels = 16;
+thread_local Umma2Cache* g_umma2_cache = nullptr;
 
-// conv-as-GEMM dispatch: tcgen05 split-bf16 kernel for large tiles when enabled, fp32 CUDA-core kernel otherwise
+void route_from(ss_engine* h) {
+  g_umma_linear = h->umma_linear;
+  g_umma_min_rows = h->umma_min_rows;
+  g_umma_min_channels = h->umma_min_channels;
+  if (!h->umma2_cache) h->umma2_cache = umma2_cache_create();
+  g_umma2_cache = h->umma2_cache;
+}
+
+// conv-as-GEMM dispatch: a tcgen05 split-bf16 kernel when enabled and the shape fits, fp32 CUDA-core kernel otherwise
+// (mode 2 / 3: kernels_umma.cu with that many pieces, 12 / 13: kernels_umma2.cu)
 void conv_gemm(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaStream_t st) {
-  if (g_umma_conv >= 2 && a.B * a.L_rows >= 128 && umma_gemm_supported(a, N, ep))
+  const int rows = a.B * a.L_rows;
+  if (g_umma_conv >= 12 && g_umma2_cache && rows >= g_umma_min_rows && a.C_in >= g_umma_min_channels && umma2_supported(a, N, ep))
+    umma2_conv(g_umma2_cache, a, W, N, ep, g_umma_conv - 10, st);
+  else if (g_umma_conv >= 2 && g_umma_conv < 10 && rows >= 128 && umma_gemm_supported(a, N, ep))
     umma_gemm_conv(a, W, N, ep, g_umma_conv, st);
   else
     gemm_conv(a, W, N, ep, st);
@@ -37,7 +52,9 @@ void linear(const float* x, int ldx, int M, const Linear& l, Epilogue ep, cudaSt
   ep.bias = l.b;
   if (skinny_gemm_supported(M, l.N, l.K, ep) && (ldx & 3) == 0)
     skinny_gemm(x, ldx, l.w, M, l.N, l.K, ep, st);
-  else if (g_umma_linear >= 2 && M >= 128 && (ldx & 3) == 0 && umma_gemm_supported(a, l.N, ep))
+  else if (g_umma_linear >= 12 && g_umma2_cache && M >= g_umma_min_rows && umma2_supported(a, l.N, ep))
+    umma2_conv(g_umma2_cache, a, l.w, l.N, ep, g_umma_linear - 10, st);
+  else if (g_umma_linear >= 2 && g_umma_linear < 10 && M >= 128 && (ldx & 3) == 0 && umma_gemm_supported(a, l.N, ep))
     umma_gemm_conv(a, l.w, l.N, ep, g_umma_linear, st);
   else
     gemm_conv(a, l.w, l.N, ep, st);
@@ -201,7 +218,7 @@ int ss_fbank(ss_engine* h, void* stream, const float* samples_dev, int64_t n_sam
 }
 
 int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const int32_t* lengths_host, int B, int F, float* out_dev) {
-  if (h) g_umma_linear = h->umma_linear;
+  if (h) route_from(h);
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   if (B <= 0 || F <= 0) return h->fail(SS_ERR_INVALID, "empty encoder input");
   const ss_config& c = h->cfg;
@@ -300,7 +317,7 @@ int ss_encoder_stream_reset(ss_engine* h) {
 }
 
 int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, int F, float* enc_out_dev, int32_t* T_out, int32_t* T_final_out) {
-  if (h) g_umma_linear = h->umma_linear;
+  if (h) route_from(h);
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   if (h->attn_chunk <= 0 || h->conv_chunk <= 0) return h->fail(SS_ERR_STATE, "streaming encoder needs a chunked model (ss_set_chunk)");
   const ss_config& c = h->cfg;
@@ -385,7 +402,7 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
 
 int ss_ctc_greedy_rows(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int row0, int64_t* argmax_dev,
                        int64_t* tokens_dev, int32_t* index_dev, int32_t* count_dev) {
-  if (h) g_umma_linear = h->umma_linear;
+  if (h) route_from(h);
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   if (head < 0 || head > 1 || rows <= 0 || row0 < 0 || row0 > rows) return h->fail(SS_ERR_INVALID, "bad ctc head / rows");
   const Linear& l = h->ctc_head[head];
@@ -408,7 +425,7 @@ int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, in
 
 int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* tokens_host, int n, float* feats_out_dev,
                    float* logits_last_dev) {
-  if (h) g_umma_linear = h->umma_linear;
+  if (h) route_from(h);
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   const ss_config& c = h->cfg;
   if (n <= 0 || n > c.max_mt_positions || T <= 0) return h->fail(SS_ERR_INVALID, "bad MT sequence length");
@@ -442,7 +459,7 @@ int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, cons
 
 int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* prefix_host, int n_prefix, int max_new_tokens,
                  int max_len_b, int64_t* tokens_out_host, int max_out, int* n_out, float* feats_out_dev) {
-  if (h) g_umma_linear = h->umma_linear;
+  if (h) route_from(h);
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   const ss_config& c = h->cfg;
   cudaStream_t st = S(stream);
@@ -540,7 +557,7 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
 
 int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, int Slen, int n_pad_tail, int mask_eos, int64_t* argmax_dev,
                        int64_t* units_dev, int32_t* count_dev, float* t2u_out_dev, float* logits_dev) {
-  if (h) g_umma_linear = h->umma_linear;
+  if (h) route_from(h);
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   const ss_config& c = h->cfg;
   cudaStream_t st = S(stream);
@@ -641,6 +658,7 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
   if (n_frames <= 0 || frame0 < 0 || frame0 + n_frames != total_frames) return h->fail(SS_ERR_INVALID, "vocoder frame range must be the tail of the sequence");
   const ss_config& c = h->cfg;
   cudaStream_t st = S(stream);
+  route_from(h);
   g_umma_conv = h->umma_vocoder;
   int ctx = left_context < 0 ? h->receptive_field : left_context;
   ctx = std::min(ctx, frame0);
@@ -675,7 +693,7 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
   if (!ok || !wav) return h->fail(SS_ERR_CUDA, "workspace too small");
   // The resblocks of a stage are independent until their outputs are averaged (hifigan.py:158-165).  Each one is a chain of
   // small latency-bound convs, so they run on separate streams (block 0 on the caller's) and overlap on the GPU.
-  const bool fan_out = h->vocoder_streams && nrb == 3 && g_umma_conv == 0;
+  const bool fan_out = h->vocoder_streams && nrb == 3 && (g_umma_conv == 0 || g_umma_conv >= 12);
   if (fan_out && !h->fork_event) {
     bool made = cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && made; ++i)
@@ -787,6 +805,9 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   std::string n(name);
   if (n == "umma_vocoder") h->umma_vocoder = value;
   else if (n == "umma_linear") h->umma_linear = value;
+  else if (n == "umma_min_rows") h->umma_min_rows = value;
+  else if (n == "umma_min_channels") h->umma_min_channels = value;
+  else if (n == "umma2_cache_clear") umma2_cache_clear(h->umma2_cache);  // debug tools that reuse a weight address
   else if (n == "persistent_encoder") h->persistent_encoder = value;
   else if (n == "vocoder_streams") h->vocoder_streams = value;
   else if (n == "persistent_mt") h->persistent_mt = value;
@@ -840,6 +861,27 @@ int ss_op_linear_umma(ss_engine* h, void* stream, const float* x_dev, int M, int
   if (!umma_gemm_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 GEMM");
   umma_gemm_conv(a, w_dev, N, ep, pieces, S(stream));
   return check_launch(h, "ss_op_linear_umma");
+}
+
+int ss_op_conv1d(ss_engine* h, void* stream, const float* x_dev, int L, int C_in, const float* w_dev, const float* bias_dev, int N, int ksize,
+                 int dil, int pad_left, float pre_lrelu, int mode, float* out_dev) {
+  if (!h) return SS_ERR_INVALID;
+  route_from(h);
+  ConvA a;
+  a.x = x_dev; a.B = 1; a.L_in = L; a.L_rows = L; a.C_in = C_in; a.ldx = C_in; a.ksize = ksize; a.dil = dil; a.pad_left = pad_left;
+  a.pre_lrelu = pre_lrelu;
+  Epilogue ep = ep_out(out_dev, N);
+  ep.bias = bias_dev;
+  if (mode >= 12) {
+    if (!umma2_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 conv kernel");
+    umma2_conv(h->umma2_cache, a, w_dev, N, ep, mode - 10, S(stream));
+  } else if (mode >= 2) {
+    if (!umma_gemm_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 GEMM");
+    umma_gemm_conv(a, w_dev, N, ep, mode, S(stream));
+  } else {
+    gemm_conv(a, w_dev, N, ep, S(stream));
+  }
+  return check_launch(h, "ss_op_conv1d");
 }
 
 int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N, int act,

@@ -446,6 +446,7 @@ int ss_destroy(ss_engine* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->dev_allocs) cudaFree(p);
+  ss::umma2_cache_destroy(h->umma2_cache);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->mt_cross_kv) cudaFree(h->mt_cross_kv);
   if (h->mt_next_pinned) cudaFreeHost(h->mt_next_pinned);

@@ -75,6 +75,16 @@ void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, cons
 bool umma_gemm_supported(const ConvA& a, int N, const Epilogue& ep);
 void umma_gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, int pieces, cudaStream_t st);
 
+// Second-generation tcgen05 path (kernels_umma2.cu): stride-1 convolutions / linears over one sequence (B = 1) with
+// pre-packed bf16-split weights streamed by cp.async.bulk and activations converted once per channel chunk (taps are
+// descriptor row shifts).  The cache owns the packed weight copies (keyed by weight pointer and tiling).
+struct Umma2Cache;
+Umma2Cache* umma2_cache_create();
+void umma2_cache_clear(Umma2Cache* c);
+void umma2_cache_destroy(Umma2Cache* c);
+bool umma2_supported(const ConvA& a, int N, const Epilogue& ep);
+void umma2_conv(Umma2Cache* cache, const ConvA& a, const float* W, int N, const Epilogue& ep, int pieces, cudaStream_t st);
+
 // Weight-streaming GEMM for M <= 64 rows (plain row-major A): one warp per output column, see kernels_skinny.cu.
 bool skinny_gemm_supported(int M, int N, int K, const Epilogue& ep);
 void skinny_gemm(const float* A, int lda, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st);

@@ -79,6 +79,7 @@ def load_library() -> ctypes.CDLL:
     lib.ss_vocoder_receptive_field.argtypes = [vp]
     lib.ss_op_linear.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, vp]
     lib.ss_op_linear_umma.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, vp]
+    lib.ss_op_conv1d.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, ctypes.c_float, i32, vp]
     lib.ss_set_option.argtypes = [vp, ctypes.c_char_p, i32]
     lib.ss_op_layer_norm.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     lib.ss_debug_copy.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t]
@@ -92,7 +93,7 @@ EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_ctc_greedy_rows", "ss_mt_greedy",
     "ss_mt_features", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
-    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count",
+    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count",
 ]
 
 
@@ -174,6 +175,8 @@ class Engine:
         # linears that feed an arg-max stay on the exact fp32 kernels unless explicitly switched on
         self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "0")))
         self.set_option("umma_linear", int(os.environ.get("SS_UMMA_LINEAR", "0")))
+        self.set_option("umma_min_rows", int(os.environ.get("SS_UMMA_MIN_ROWS", "128")))
+        self.set_option("umma_min_channels", int(os.environ.get("SS_UMMA_MIN_CHANNELS", "16")))
         self.set_option("persistent_encoder", int(os.environ.get("SS_PERSISTENT_ENCODER", "1")))
         self.set_option("persistent_mt", int(os.environ.get("SS_PERSISTENT_MT", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))
@@ -358,6 +361,16 @@ class Engine:
         N = w.shape[0]
         out = self._f32(M, N)
         self._check(self.lib.ss_op_linear_umma(self._h, self._stream(), x.data_ptr(), M, K, w.data_ptr(), self._ptr(b), N, act, pieces, out.data_ptr()))
+        return out
+
+    def op_conv1d(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], ksize: int, dil: int = 1, pad_left: int = 0,
+                  pre_lrelu: float = 1.0, mode: int = 0) -> torch.Tensor:
+        """x [L][C_in] channels-last, w [N][ksize*C_in] tap-major; mode 0 = fp32 CUDA cores, 2/3 = tcgen05 im2col, 12/13 = tcgen05 tap-shift"""
+        L, C = x.shape
+        N = w.shape[0]
+        out = self._f32(L, N)
+        self._check(self.lib.ss_op_conv1d(self._h, self._stream(), x.data_ptr(), L, C, w.data_ptr(), self._ptr(b), N, ksize, dil, pad_left,
+                                          float(pre_lrelu), mode, out.data_ptr()))
         return out
 
     def set_option(self, name: str, value: int):
