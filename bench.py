@@ -131,63 +131,49 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def skinny_roofline(engine, peaks):
-    """Dominant kernel of the streaming path = skinny_gemm_kernel (every encoder / MT projection at M <= 16 rows), a
-    weight-streaming kernel -> HBM roofline.  Measured live with CUDA events on the launching stream at the encoder FFN
-    shape (M = 16 active rows, K = 256, N = 2048); 96 distinct weight matrices (201 MB > 126 MB L2) are cycled so every
-    launch streams its 2 MB of weights from HBM like the real step does.  algorithmic bytes = N*K*4 + M*K*4 + M*N*4."""
-    import torch
-
-    M, K, N, NW = 16, 256, 2048, 96
-    x = torch.randn(M, K, device=engine.device)
-    ws = [torch.randn(N, K, device=engine.device) * K ** -0.5 for _ in range(NW)]
-    b = torch.zeros(N, device=engine.device)
-    out = torch.empty(M, N, device=engine.device)
-
-    def launch_all():
-        for i in range(NW):
-            engine.lib.ss_op_linear(engine._h, engine._stream(), x.data_ptr(), M, K, ws[i].data_ptr(), b.data_ptr(), N, 2, out.data_ptr())
-
-    launch_all()
-    torch.cuda.synchronize()
-    # the 96 launches are replayed from a CUDA graph so that the host enqueue rate (python/ctypes, ~8 us per call) does not
-    # hide the kernel duration; events bracket the replay on the launching stream
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        launch_all()
-    graph.replay()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    graph.replay()
-    e.record()
-    torch.cuda.synchronize()
-    us = s.elapsed_time(e) / NW * 1e3
-    nbytes = N * K * 4 + M * K * 4 + M * N * 4
-    ach = nbytes / (us * 1e-6) / 1e9
+def encoder_roofline(engine, peaks, run_utterance):
+    """Dominant kernel of the step = encoder_layers_persistent_kernel (one launch per 320 ms chunk runs all 12 Conformer
+    layers over the <= 16 not-yet-final rows; 19 % of the step's GPU time in profiles/r1_launches_v4_bench_window.md).
+    It streams every GEMM weight of the stack once per launch -> HBM roofline.  Measured live: the engine brackets each
+    launch with CUDA events on the launching stream while one more resident utterance is streamed (32 launches).
+    algorithmic bytes per launch = 12 x (4*D*FFN + 7*D*D) x 4 B of weights (122.7 MB) + the K / V cache and
+    relative-position rows the attention reads (12 x (3T + nA) x D x 4 B)."""
+    engine.set_option("persistent_time", 1)
+    engine.persistent_time()  # drop stale records
+    run_utterance()
+    ms, n, nbytes = engine.persistent_time()
+    engine.set_option("persistent_time", 0)
     peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r1_dominant_kernel_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    if n == 0:
+        return {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
+                "kernel": "encoder_layers_persistent_kernel", "note": "no persistent launches were recorded"}
+    ach = nbytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-            "kernel": "skinny_gemm_kernel<16,2,1> (fp32 weight-streaming GEMM, fused SiLU)", "algorithmic_bytes_per_launch": nbytes,
+            "kernel": "encoder_layers_persistent_kernel<2048> (fp32, all 12 Conformer layers of one streaming step, 148 CTAs cooperative)",
+            "algorithmic_bytes_per_launch": nbytes / n, "launches_timed": n, "us_per_launch": ms / n * 1e3,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-            "shape": {"M": M, "N": N, "K": K}, "us_per_launch": us,
-            "note": "batch-1 streaming step: per-kernel latency (launch + one DRAM round trip + reduction) dominates, not bandwidth"}
+            "note": "batch-1 streaming: 16 rows per launch, 108 grid barriers; the kernel is bound by dependent-phase latency "
+                    "(barrier + one L2/HBM round trip per phase), not by bandwidth"}
 
 
 def gemm_rooflines(engine, peaks):
-    """Secondary: the two large-M GEMM kernels at the vocoder's heaviest conv shape (M = 5*500, N = 256, K = 11*256)."""
+    """Secondary: the GEMM / conv kernels at the vocoder's heaviest conv shape (L = 5*500 rows, 256 -> 256 channels, k = 11):
+    fp32 CUDA cores, the first tcgen05 kernel (im2col gather) and the tap-shift tcgen05 kernel with pre-packed weights.
+    FLOPs are fp32-equivalent (2*L*C*C*k); the tcgen05 kernels spend 3 bf16 MMAs per product (bf16x3 split)."""
     import torch
 
-    M, C, k = 5 * 500, 256, 11
-    x = torch.randn(M, C * k, device=engine.device)
+    L, C, k = 5 * 500, 256, 11
+    x = torch.randn(L, C, device=engine.device)
     w = torch.randn(C, C * k, device=engine.device) / (C * k) ** 0.5
     b = torch.zeros(C, device=engine.device)
     out = {}
-    for name, fn in (("gemm_kernel<128,64> fp32 CUDA cores", lambda: engine.op_linear(x, w, b)),
-                     ("umma_gemm_kernel<128,2> tcgen05 bf16x3 (opt-in)", lambda: engine.op_linear_umma(x, w, b, 0, 2))):
+    for name, mode in (("gemm_kernel<128,64> fp32 CUDA cores", 0), ("umma_gemm_kernel tcgen05 bf16x3, im2col gather (v1)", 2),
+                       ("umma2_kernel tcgen05 bf16x3, tap-shift + cp.async.bulk weights (default path)", 12)):
+        fn = lambda: engine.op_conv1d(x, w, b, k, 1, k // 2, 0.1, mode)
         for _ in range(3):
             fn()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -198,10 +184,10 @@ def gemm_rooflines(engine, peaks):
         e.record()
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / 20
-        ach = 2.0 * M * C * C * k / (ms * 1e-3) / 1e12
+        ach = 2.0 * L * C * C * k / (ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops", 1590.0)
         out[name] = {"bound": "tensor", "achieved_fp32_equivalent": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     "us_per_launch": ms * 1e3, "shape": {"M": M, "N": C, "K": C * k}}
+                     "us_per_launch": ms * 1e3, "shape": {"L": L, "C_in": C, "C_out": C, "k": k}}
     return out
 
 
@@ -328,8 +314,13 @@ def main():
                        "output_audio_s_per_step": out_res / args.steps / SAMPLE_RATE},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(UTT_SECONDS * SAMPLE_RATE * 4),
                     "d2h_bytes_per_step": int(out_e2e / args.steps * 4), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks}
-    line["roofline"] = skinny_roofline(eng, peaks)
+            "gpu_launches": int(launches), "clocks": clocks,
+            "engine_options": {k: os.environ.get(k) for k in sorted(os.environ) if k.startswith("SS_")}}
+    def one_more():
+        flush.fill_(0.0)
+        stream_resident(utts_dev[0])
+
+    line["roofline"] = encoder_roofline(eng, peaks, one_more)
     line["roofline_large_gemm"] = gemm_rooflines(eng, peaks)
     if world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample: the first 4 s of the same utterance through the oracle agent (reference semantics)

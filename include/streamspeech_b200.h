@@ -118,6 +118,11 @@ int ss_ctc_greedy_rows(ss_engine* h, void* stream, int head, const float* enc_de
 int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* prefix_host, int n_prefix,
                  int max_new_tokens, int max_len_b, int64_t* tokens_out_host, int max_out, int* n_out,
                  float* feats_out_dev);
+/* Streaming hint for the NEXT ss_mt_greedy / ss_mt_features call: rows [0, rows) of the encoder output passed to it are
+ * final, i.e. bit-identical in every later call with the same buffer until ss_encoder_stream_reset (ss_encoder_stream_step
+ * reports that count as T_final).  Their cross-attention keys / values are then projected once instead of on every call.
+ * Without the hint every call projects all rows (the reference recomputes everything, agent:520-538). */
+int ss_mt_stable_rows(ss_engine* h, int rows);
 /* teacher-forced features for tokens_host[n] (pads allowed only as a tail): TransformerDecoderBase.extract_features_scriptable
  * (ctc_unity/modules/transformer_decoder.py:257-403).  feats_out_dev [n][mt_dim]; logits_last_dev (optional) [tgt_vocab]. enqueue only */
 int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* tokens_host, int n,

@@ -301,7 +301,9 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
         tr["new_subword_tokens"] = new_subword_tokens
 
         # 1. MT decoder (agent:520-538); the hypothesis comes back without its trailing eos
-        tokens, feats = eng.mt_greedy(enc, self.tgt_subwords_indices, new_subword_tokens, max_len_b=100)
+        # encoder rows below T_final are final in cached mode: their cross-attention K / V are projected once (ss_mt_stable_rows)
+        stable = self._enc_final if self.encoder_mode == "cached" else 0
+        tokens, feats = eng.mt_greedy(enc, self.tgt_subwords_indices, new_subword_tokens, max_len_b=100, stable_rows=stable)
         tgt_subwords_indices = list(tokens)
         n_pad_tail = 0
         if self.whole_word:  # agent:540-574
@@ -330,7 +332,7 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
         # mt_decoder(prev_output_tokens_mt, features_only=True) (agent:638-642): already produced by the greedy pass
         # unless whole-word trimming changed the sequence
         if self.whole_word:
-            feats = eng.mt_features(enc, prev_output_tokens_mt)
+            feats = eng.mt_features(enc, prev_output_tokens_mt, stable_rows=stable)
         else:
             feats = feats[: len(prev_output_tokens_mt)]
         # 2./3. T2U encoder + CTC unit decoder (agent:662-689)

@@ -4,6 +4,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <unordered_set>
+
 namespace ss {
 
 // Programmatic dependent launch: allow the next kernel in the stream (if it was launched with the PDL attribute, see
@@ -12,11 +14,27 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // ... and the matching wait: everything the previous kernels of the stream wrote is visible after it.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// set while a stream capture is recording the launches (CUDA-graph replay of a stage): programmatic launches are recorded
+// as plain launches unless the engine option graph_pdl asks otherwise
+extern thread_local int g_pdl_off;
+
+// Shared-memory carve-out: the tcgen05 kernels need > 100 KB of shared memory per CTA, the SIMT kernels a few KB.  An SM
+// holds ONE carve-out at a time, so kernels that ask for different ones cannot share an SM and every change drains it
+// -- which is what the vocoder's three concurrent streams of alternating conv / reduce kernels would do.  With the option on
+// (default) every kernel of the library asks for the maximum shared-memory carve-out, once per kernel function.
+extern int g_prefer_shared;
+inline void prefer_shared_once(const void* fn) {
+  if (!g_prefer_shared) return;
+  static thread_local std::unordered_set<const void*> done;
+  if (done.insert(fn).second) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
 // launch with programmatic stream serialization: the grid may be scheduled while its predecessor is still running; every
 // kernel launched this way calls pdl_wait() before it touches memory (so semantics equal a normal launch, minus the
 // launch / scheduling latency that now overlaps the predecessor)
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  prefer_shared_once((const void*)kernel);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -27,7 +45,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   // only small grids launch early: CTAs of a large dependent grid would sit on shared memory / registers that the
   // (multi-wave) predecessor still needs (measured: vocoder convs 35 ms -> 48 ms with unconditional PDL)
   const unsigned long long ctas = (unsigned long long)grid.x * grid.y * grid.z;
-  attr[0].val.programmaticStreamSerializationAllowed = ctas <= 296 ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (ctas <= 296 && !g_pdl_off) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -36,6 +54,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 // same, unconditionally (kernels that do real work before pdl_wait(): the skinny GEMM's weight prefetch)
 template <typename... KArgs, typename... Args>
 inline void launch_pdl_always(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  prefer_shared_once((const void*)kernel);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -43,7 +62,7 @@ inline void launch_pdl_always(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl_off ? 0 : 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <tuple>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -94,6 +96,11 @@ struct ss_engine {
   int vocoder_streams = 1;     // 1: the parallel resblocks of a vocoder stage run on three streams, 0: one stream
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   cudaEvent_t fork_event = nullptr, join_event[2] = {nullptr, nullptr};
+  // CUDA-graph replay of the vocoder generator (conv_pre .. conv_post) per (frames, arena, routing): value = (exec, nodes)
+  int vocoder_graph = 0;  // measured on B200: no gain (the generator is bound by kernel execution, not by host enqueue)
+  int graph_pdl = 0;
+  cudaStream_t capture_stream = nullptr;
+  std::map<std::tuple<int, uintptr_t, int, int, int>, std::pair<cudaGraphExec_t, int>> voc_graphs;
   int persistent_encoder = 1;  // streaming encoder step as ONE cooperative kernel (kernels_persist.cu) when the shape fits
   std::map<std::string, ss::HostTensor> host;  // loaded tensors by key
   std::vector<void*> dev_allocs;
@@ -142,6 +149,9 @@ struct ss_engine {
   float* mt_self_v = nullptr;
   float* mt_cross_kv = nullptr;  // [layers][Tcap][2*mt_dim]
   int mt_cross_cap = 0;
+  int mt_cross_final = 0;            // rows of mt_cross_kv that were projected from final encoder rows (ss_mt_stable_rows)
+  int mt_stable_hint = 0;            // hint for the next MT call, consumed by it
+  const float* mt_cross_enc = nullptr;  // encoder buffer those rows came from
   int64_t* mt_tok_dev = nullptr;  // [max_pos]
   int64_t* mt_next_dev = nullptr;
   int64_t* mt_next_pinned = nullptr;
@@ -156,6 +166,10 @@ struct ss_engine {
   float* st_glu = nullptr;  // conv-module GLU outputs (depthwise-conv inputs)
   unsigned long long* persist_ts = nullptr;    // [4096] phase timestamps when option persistent_profile is set
   int persistent_profile = 0;
+  int persistent_prefetch = 0;       // persistent encoder kernel prefetches the next layer's weights into L2
+  int persistent_time = 0;           // record CUDA events around the persistent encoder kernel (bench roofline)
+  struct TimedLaunch { cudaEvent_t e0, e1; double bytes; };
+  std::vector<TimedLaunch> time_events;
   ss::PersistLayer* persist_alias = nullptr;   // debug: every layer entry = layer 0 (timing experiments only)
   int persistent_alias = 0;
   unsigned* persist_bar = nullptr;   // arrival counter of the kernel's own grid barrier (option persistent_barrier)

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include <tuple>
 
 #include "engine.h"
 
@@ -110,6 +111,12 @@ Epilogue ep_residual(float* inout, int ldo, float alpha = 1.0f) {  // inout = in
   return e;
 }
 
+void clear_graphs(ss_engine* h) {
+  cudaDeviceSynchronize();
+  for (auto& kv : h->voc_graphs) cudaGraphExecDestroy(kv.second.first);
+  h->voc_graphs.clear();
+}
+
 bool ws_begin(ss_engine* h, size_t bytes) {
   h->ws.reset();
   return h->ws.ensure(bytes);
@@ -149,6 +156,7 @@ int ensure_mt_cross(ss_engine* h, int T) {
   if (T <= h->mt_cross_cap) return SS_OK;
   if (h->mt_cross_kv) cudaFree(h->mt_cross_kv);
   h->mt_cross_kv = nullptr;
+  h->mt_cross_final = 0;
   int cap = std::max(T + T / 2, 512);
   size_t bytes = (size_t)h->cfg.mt_layers * cap * 2 * h->cfg.mt_dim * sizeof(float);
   if (cudaMalloc((void**)&h->mt_cross_kv, bytes) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc(mt cross kv) failed");
@@ -171,12 +179,21 @@ void mt_forward(ss_engine* h, int past, int n, int T, const int* self_kv_len_dev
   layer_norm(x, dim, feats, dim, h->mt_ln.g, h->mt_ln.b, n, dim, st);
 }
 
+// cross-attention K | V of the encoder rows.  Rows the caller declared final (ss_mt_stable_rows) at the previous call were
+// projected then and are not touched again; everything above is (re)computed.
 void mt_begin(ss_engine* h, const float* enc_dev, int T, cudaStream_t st) {
   const ss_config& c = h->cfg;
-  for (int l = 0; l < c.mt_layers; ++l) {
-    float* cross = h->mt_cross_kv + (size_t)l * h->mt_cross_cap * 2 * c.mt_dim;
-    linear(enc_dev, c.enc_dim, T, h->mt[l].ckv, ep_out(cross, 2 * c.mt_dim), st);
+  int from = (h->mt_cross_enc == enc_dev) ? std::min(h->mt_cross_final, T) : 0;
+  if (from < 0) from = 0;
+  if (T > from) {
+    for (int l = 0; l < c.mt_layers; ++l) {
+      float* cross = h->mt_cross_kv + (size_t)l * h->mt_cross_cap * 2 * c.mt_dim;
+      linear(enc_dev + (size_t)from * c.enc_dim, c.enc_dim, T - from, h->mt[l].ckv, ep_out(cross + (size_t)from * 2 * c.mt_dim, 2 * c.mt_dim), st);
+    }
   }
+  h->mt_cross_final = std::min(h->mt_stable_hint, T);
+  h->mt_stable_hint = 0;
+  h->mt_cross_enc = enc_dev;
 }
 
 DecScratch dec_scratch(ss_engine* h, int n, int dim, int ffn) {
@@ -313,6 +330,14 @@ int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const
 int ss_encoder_stream_reset(ss_engine* h) {
   if (!h) return SS_ERR_INVALID;
   h->st_T_final = 0;
+  h->mt_cross_final = 0;
+  h->mt_stable_hint = 0;
+  return SS_OK;
+}
+
+int ss_mt_stable_rows(ss_engine* h, int rows) {
+  if (!h) return SS_ERR_INVALID;
+  h->mt_stable_hint = rows > 0 ? rows : 0;
   return SS_OK;
 }
 
@@ -366,11 +391,27 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
     }
     linear(x0, D, nA, h->enc_linear, ep_out(x, D), st);
     bool persistent = h->persistent_encoder && encoder_layers_persistent_supported(nA, D, c.enc_ffn, c.enc_heads, T, c.dw_kernel);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (persistent && h->persistent_time) {  // bench: CUDA events on the launching stream around the dominant kernel
+      if (h->time_events.size() < 4096 && cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess) {
+        cudaEventRecord(ev0, st);
+      } else {
+        ev0 = ev1 = nullptr;
+      }
+    }
     if (persistent)
       persistent = encoder_layers_persistent(h->persistent_alias ? h->persist_alias : h->persist_layers, c.enc_layers, x, hid, qb, att, dw, h->st_k, h->st_v, h->st_glu, nA, a0, T, D,
                                              c.enc_ffn, c.enc_heads, h->Tpos, h->attn_chunk, cc, c.dw_kernel,
                                              h->persistent_profile ? h->persist_ts : nullptr,
-                                             h->persistent_barrier ? h->persist_bar : nullptr, &h->persist_bar_target, st) == 0;
+                                             h->persistent_barrier ? h->persist_bar : nullptr, &h->persist_bar_target,
+                                             h->persistent_prefetch, st) == 0;
+    if (ev0 && ev1) {
+      cudaEventRecord(ev1, st);
+      // algorithmic bytes of this launch: every GEMM weight once + the K / V caches and relative-position rows the attention reads
+      const double wbytes = (double)c.enc_layers * (4.0 * D * c.enc_ffn + 7.0 * D * D) * 4.0;
+      const double kvbytes = (double)c.enc_layers * (2.0 * T + (T + nA)) * D * 4.0;
+      h->time_events.push_back({ev0, ev1, wbytes + kvbytes});
+    }
     if (!persistent) cudaGetLastError();  // a refused cooperative launch falls back to the per-kernel path
     for (int i = 0; i < c.enc_layers && !persistent; ++i) {
       const ConformerLayerW& L = h->enc[i];
@@ -703,6 +744,10 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
   }
   // V1 tail: repeat_interleave(x, dur) for the frame window (agent/tts/codehifigan.py:66)
   expand_frames(h->voc_unit_emb, h->voc_cumsum, h->voc_U, f_lo, N, c.voc_embedding_dim, frames, st);
+  // Everything from conv_pre to conv_post depends on the call only through N (buffer addresses are arena offsets): ~190
+  // launches on three streams whose host enqueue time exceeds their GPU time.  With option vocoder_graph the sequence is
+  // recorded once per (N, arena, routing) by stream capture and replayed as one CUDA graph afterwards.
+  auto generator_body = [&](cudaStream_t st) {
   // conv_pre
   {
     ConvA a;
@@ -796,6 +841,48 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
   }
   // x = leaky_relu(x) [slope 0.01, hifigan.py:166]; conv_post; tanh
   conv_post_tanh(bufX, L, ch, h->conv_post_w, h->conv_post_b, h->conv_post_k, 0.01f, wav, st);
+  };
+  bool replayed = false;
+  if (h->vocoder_graph) {
+    const auto key = std::make_tuple(N, (uintptr_t)h->ws.base, g_umma_conv, g_umma_min_rows * 4096 + g_umma_min_channels, h->vocoder_streams);
+    auto it = h->voc_graphs.find(key);
+    if (it != h->voc_graphs.end()) {
+      if (cudaGraphLaunch(it->second.first, st) == cudaSuccess) {
+        g_launches += it->second.second;
+        replayed = true;
+      } else {
+        cudaGetLastError();
+      }
+    } else {
+      // first sight of this key: run eagerly now (that also performs every lazy initialisation: packed weights, split
+      // scratch, function attributes), then record the same sequence for the next call.  The capture runs on an
+      // engine-owned stream because the caller's stream may be the legacy default stream, which cannot be captured.
+      generator_body(st);
+      replayed = true;
+      if (!h->capture_stream) cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking);
+      const unsigned long long before = g_launches;
+      if (h->capture_stream && cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        g_pdl_off = h->graph_pdl ? 0 : 1;
+        generator_body(h->capture_stream);
+        g_pdl_off = 0;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        if (cudaStreamEndCapture(h->capture_stream, &graph) == cudaSuccess && graph != nullptr &&
+            cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          h->voc_graphs[key] = std::make_pair(exec, (int)(g_launches - before));
+        } else {
+          cudaGetLastError();
+          h->vocoder_graph = 0;  // capture is not possible here: stay on the eager path
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        cudaGetLastError();
+        h->vocoder_graph = 0;
+      }
+      g_launches = before;
+    }
+  }
+  if (!replayed) generator_body(st);
   copy_f32(wav + (size_t)ctx * h->hop, wav_out_dev, (int64_t)n_frames * h->hop, st);
   return check_launch(h, "ss_vocoder_generate");
 }
@@ -807,10 +894,31 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "umma_linear") h->umma_linear = value;
   else if (n == "umma_min_rows") h->umma_min_rows = value;
   else if (n == "umma_min_channels") h->umma_min_channels = value;
-  else if (n == "umma2_cache_clear") umma2_cache_clear(h->umma2_cache);  // debug tools that reuse a weight address
+  else if (n == "umma2_cache_clear") {  // debug tools that reuse a weight address
+    umma2_cache_clear(h->umma2_cache);
+    clear_graphs(h);
+  }
+  else if (n == "umma2_split_below") { g_umma2_split_below = value; clear_graphs(h); }
+  else if (n == "umma2_min_units") { g_umma2_min_units = value; clear_graphs(h); }
+  else if (n == "umma2_debug") {
+    if (value && !g_umma2_dbg) {
+      if (cudaMalloc(&g_umma2_dbg, 16 * sizeof(unsigned long long)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
+      cudaMemset(g_umma2_dbg, 0, 16 * sizeof(unsigned long long));
+    }
+    if (!value && g_umma2_dbg) {
+      cudaDeviceSynchronize();
+      cudaFree(g_umma2_dbg);
+      g_umma2_dbg = nullptr;
+    }
+  }
+  else if (n == "prefer_shared") g_prefer_shared = value;  // takes effect for kernels that have not been launched yet
+  else if (n == "vocoder_graph") h->vocoder_graph = value;
+  else if (n == "graph_pdl") h->graph_pdl = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
   else if (n == "vocoder_streams") h->vocoder_streams = value;
   else if (n == "persistent_mt") h->persistent_mt = value;
+  else if (n == "persistent_prefetch") h->persistent_prefetch = value;
+  else if (n == "persistent_time") h->persistent_time = value;
   else if (n == "persistent_barrier") {
     if (value && !h->persist_bar) {
       if (cudaMalloc(&h->persist_bar, 256) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
@@ -846,6 +954,30 @@ int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes) 
   if (n == "persist_ts") {
     if (!h->persist_ts || bytes > 4096 * sizeof(unsigned long long)) return h->fail(SS_ERR_STATE, "no phase timestamps (set option persistent_profile)");
     if (cudaMemcpy(host_dst, h->persist_ts, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMemcpy failed");
+    return SS_OK;
+  }
+  if (n == "umma2_ts") {
+    if (!g_umma2_dbg || bytes > 16 * sizeof(unsigned long long)) return h->fail(SS_ERR_STATE, "no stamps (set option umma2_debug)");
+    if (cudaMemcpy(host_dst, g_umma2_dbg, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMemcpy failed");
+    return SS_OK;
+  }
+  if (n == "persist_time") {  // double[3] = {summed ms, launches, summed algorithmic bytes} since the last query
+    if (bytes < 3 * sizeof(double)) return h->fail(SS_ERR_INVALID, "persist_time needs 3 doubles");
+    cudaDeviceSynchronize();
+    double* out = (double*)host_dst;
+    out[0] = out[1] = out[2] = 0.0;
+    for (auto& e : h->time_events) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e.e0, e.e1) == cudaSuccess) {
+        out[0] += ms;
+        out[1] += 1.0;
+        out[2] += e.bytes;
+      }
+      cudaEventDestroy(e.e0);
+      cudaEventDestroy(e.e1);
+    }
+    cudaGetLastError();
+    h->time_events.clear();
     return SS_OK;
   }
   return h->fail(SS_ERR_INVALID, "unknown debug buffer " + n);

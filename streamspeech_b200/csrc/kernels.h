@@ -7,6 +7,8 @@
 namespace ss {
 
 extern unsigned long long g_launches;  // kernels launched by this library (process-wide)
+extern int g_prefer_shared;            // 1: every kernel asks for the maximum shared-memory carve-out (see common.cuh)
+extern thread_local int g_pdl_off;     // 1 while a stream capture records launches (see common.cuh)
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_TANH = 3 };
 
@@ -79,6 +81,8 @@ void umma_gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, i
 // pre-packed bf16-split weights streamed by cp.async.bulk and activations converted once per channel chunk (taps are
 // descriptor row shifts).  The cache owns the packed weight copies (keyed by weight pointer and tiling).
 struct Umma2Cache;
+extern int g_umma2_split_below, g_umma2_min_units;  // split heuristics (tuning knobs)
+extern unsigned long long* g_umma2_dbg;             // optional %globaltimer stamps of CTA (0,0,0)
 Umma2Cache* umma2_cache_create();
 void umma2_cache_clear(Umma2Cache* c);
 void umma2_cache_destroy(Umma2Cache* c);

@@ -316,6 +316,7 @@ void launch(const ConvA& a, const float* W, int M, int N, int K, const Epilogue&
     splits = (nk + tiles - 1) / tiles;
     grid.z = splits;
   }
+  prefer_shared_once(conv ? (const void*)gemm_kernel<BM, BN, true> : (const void*)gemm_kernel<BM, BN, false>);
   if (conv)
     gemm_kernel<BM, BN, true><<<grid, NT, 0, st>>>(a, W, M, N, K, ep, tiles, ws);  // tile GEMMs never launch early (see launch_pdl)
   else

@@ -6,6 +6,8 @@
 
 namespace ss {
 unsigned long long g_launches = 0;
+thread_local int g_pdl_off = 0;
+int g_prefer_shared = 1;
 namespace {
 
 // one warp per row; two-pass (mean, then centred sum of squares) like ATen's RowwiseMoments result

@@ -58,6 +58,26 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
   __syncthreads();
 }
 
+// L2 prefetch of a weight matrix, spread over the whole grid (one 128-byte line per request)
+__device__ __forceinline__ void prefetch_l2(const float* p, int n_floats) {
+  const int lines = n_floats >> 5;
+  for (int i = blockIdx.x * PT + threadIdx.x; i < lines; i += gridDim.x * PT)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)i * 32));
+}
+
+// All GEMM weights of one layer (~10 MB): issued one layer ahead, so the phases of the next layer stream their weights from
+// L2 instead of paying an HBM round trip right after every grid barrier.
+__device__ __forceinline__ void prefetch_layer(const PersistLayer& L, int D, int FFN) {
+  prefetch_l2(L.ffn1_w1, D * FFN);
+  prefetch_l2(L.ffn1_w2, D * FFN);
+  prefetch_l2(L.wqkv, 3 * D * D);
+  prefetch_l2(L.wo, D * D);
+  prefetch_l2(L.pw1, 2 * D * D);
+  prefetch_l2(L.pw2, D * D);
+  prefetch_l2(L.ffn2_w1, D * FFN);
+  prefetch_l2(L.ffn2_w2, D * FFN);
+}
+
 struct GemmEpi {
   const float* bias = nullptr;
   int act = ACT_NONE;       // ignored when GLU
@@ -502,7 +522,7 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
                                                                           float* hid, float* qb, float* att, float* dw, float* kc_all,
                                                                           float* vc_all, float* gc_all, int nA, int a0, int T, int H, int Tpos,
                                                                           int chunk, int conv_chunk, int dw_k, unsigned long long* ts,
-                                                                          unsigned* bar_ctr, unsigned bar_target) {
+                                                                          unsigned* bar_ctr, unsigned bar_target, int prefetch) {
   constexpr int D = PD;
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) Smem sm;
@@ -531,6 +551,10 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
   for (int li = 0; li < n_layers; ++li) {
     if (threadIdx.x == 0) sm.fine = (ts != nullptr && blockIdx.x == 0 && li == 1) ? ts + 256 : nullptr;
     const PersistLayer L = layers[li];
+    if (prefetch) {
+      if (li == 0 && prefetch > 1) prefetch_layer(L, D, FFN);
+      if (li + 1 < n_layers) prefetch_layer(layers[li + 1], D, FFN);
+    }
     // the previous layer's final LayerNorm is still pending on x (applied on the fly in the first two phases)
     const float* pre_g = li > 0 ? layers[li - 1].fin_g : nullptr;
     const float* pre_b = li > 0 ? layers[li - 1].fin_b : nullptr;
@@ -583,7 +607,7 @@ bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, i
 
 int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
-                              unsigned long long* ts, unsigned* bar_ctr, unsigned* bar_target_host, cudaStream_t st) {
+                              unsigned long long* ts, unsigned* bar_ctr, unsigned* bar_target_host, int prefetch, cudaStream_t st) {
   ++g_launches;
   (void)D;
   (void)FFN;
@@ -600,7 +624,7 @@ int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, floa
   unsigned bar_target = bar_target_host ? *bar_target_host : 0u;
   void* args[] = {(void*)&layers_dev, (void*)&n_layers, (void*)&x, (void*)&hid, (void*)&qb, (void*)&att, (void*)&dw, (void*)&kc, (void*)&vc,
                   (void*)&gc, (void*)&nA, (void*)&a0, (void*)&T, (void*)&H, (void*)&Tpos, (void*)&chunk, (void*)&conv_chunk, (void*)&dw_k,
-                  (void*)&ts, (void*)&bar_ctr, (void*)&bar_target};
+                  (void*)&ts, (void*)&bar_ctr, (void*)&bar_target, (void*)&prefetch};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(PT), args, 0, st);
   if (e != cudaSuccess) return -2;
   if (bar_ctr != nullptr && bar_target_host != nullptr) *bar_target_host += (unsigned)grid * (unsigned)(9 * n_layers + (ts != nullptr ? 2 : 0));

@@ -18,7 +18,7 @@ bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, i
 int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
                               unsigned long long* timestamps_or_null, unsigned* barrier_counter_dev_or_null,
-                              unsigned* barrier_target_host, cudaStream_t st);
+                              unsigned* barrier_target_host, int prefetch /*0 off, 1 next layer, 2 also layer 0*/, cudaStream_t st);
 
 // ---- MT decoder, single-token greedy steps (kernels_persist_mt.cu)
 struct MtLayerP {  // device pointers of one pre-LN decoder layer (fp32, [N][K] weights)

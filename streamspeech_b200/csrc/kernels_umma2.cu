@@ -117,7 +117,16 @@ struct U2Params {
   int units_per_split;
   int SB;                   // weight ring stages
   float* ws;                // split partial sums [gridDim.z][M][N] or null
+  unsigned long long* dbg;  // optional: %globaltimer stamps of CTA (0,0,0) at the hand-off points (tools/umma2_check.py)
 };
+
+__device__ __forceinline__ void u2_stamp(const U2Params& p, int slot) {
+  if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[slot] = t;
+  }
+}
 
 template <int NP>
 __device__ __forceinline__ void u2_split_store(float4 v, unsigned char* stage, uint32_t piece_bytes, uint32_t off) {
@@ -138,7 +147,7 @@ __device__ __forceinline__ void u2_split_store(float4 v, unsigned char* stage, u
   }
 }
 
-template <int BN, int NP>
+template <int BN, int NP, int UPT, int SETS>
 __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant__ U2Params p) {
   constexpr int TM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -163,13 +172,14 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
   const int c_first = u0 / k, c_last = (u1 - 1) / k;
   const int n_local = c_last - c_first + 1;
 
+  if (tid == 0) u2_stamp(p, 0);
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full + 8 * i), "r"(U2_CONVERTERS) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full + 8 * i), "r"(U2_CONVERTERS / 32) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_empty + 8 * i), "r"(1) : "memory");
     }
     for (int i = 0; i < U2_MAX_SB; ++i) {
@@ -183,16 +193,17 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
+  if (tid == 0) u2_stamp(p, 1);
 
   if (warp < 8) {
     // ---------------- converters: activation rows -> bf16 pieces, one channel chunk per stage
     const int upr_shift = (CK == 32) ? 3 : 2;  // float4 units per row = CK / 4
     const int upr = 1 << upr_shift;
     const int n_a = p.rs * upr;
-    int64_t goff[U2_MAX_UNITS];
-    uint32_t soff[U2_MAX_UNITS];
+    int64_t goff[UPT];
+    uint32_t soff[UPT];
 #pragma unroll
-    for (int i = 0; i < U2_MAX_UNITS; ++i) {
+    for (int i = 0; i < UPT; ++i) {
       const int idx = tid + i * U2_CONVERTERS;
       const int r = idx >> upr_shift, q = idx & (upr - 1);
       const int pos = m0 + r - p.a.pad_left;
@@ -201,37 +212,48 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
       soff[i] = (uint32_t)(q >> 1) * a_plane + (uint32_t)r * 16u + (uint32_t)(q & 1) * 8u;
     }
     const float slope = p.a.pre_lrelu;
-    float4 nxt[U2_MAX_UNITS];
-    auto issue = [&](int c) {
+    // register ring of SETS chunk loads: while chunk cl is converted, the loads of chunks cl+1 .. cl+SETS-1 are in flight
+    // (UPT = 6, SETS = 2 for convolutions with a halo; UPT = 4, SETS = 3 for linears, whose chunks carry few MMAs)
+    float4 pf[SETS][UPT];
+    auto issue = [&](int c, float4* dst) {
       const float* xc = p.a.x + (int64_t)c * CK;
 #pragma unroll
-      for (int i = 0; i < U2_MAX_UNITS; ++i)
-        nxt[i] = goff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(xc + goff[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < UPT; ++i)
+        dst[i] = goff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(xc + goff[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    issue(c_first);
-    for (int cl = 0; cl < n_local; ++cl) {
-      const int sa = cl & 1, ua = cl >> 1;
-      float4 cur[U2_MAX_UNITS];
 #pragma unroll
-      for (int i = 0; i < U2_MAX_UNITS; ++i) cur[i] = nxt[i];
-      if (cl + 1 < n_local) issue(c_first + cl + 1);
-      if (ua >= 1) u2_wait(a_empty + 8 * sa, (uint32_t)((ua - 1) & 1));  // the MMAs of chunk cl-2 have read this stage
-      unsigned char* stage = a_smem + (size_t)sa * a_stage;
+    for (int d = 0; d < SETS - 1; ++d)
+      if (d < n_local) issue(c_first + d, pf[d]);
+    for (int clb = 0; clb < n_local; clb += SETS) {
 #pragma unroll
-      for (int i = 0; i < U2_MAX_UNITS; ++i) {
-        if (tid + i * U2_CONVERTERS < n_a) {
-          float4 v = cur[i];
-          if (slope != 1.0f) {
-            v.x = v.x > 0.f ? v.x : v.x * slope;
-            v.y = v.y > 0.f ? v.y : v.y * slope;
-            v.z = v.z > 0.f ? v.z : v.z * slope;
-            v.w = v.w > 0.f ? v.w : v.w * slope;
+      for (int d = 0; d < SETS; ++d) {
+        const int cl = clb + d;
+        if (cl < n_local) {
+          const int sa = cl & 1, ua = cl >> 1;
+          if (cl + SETS - 1 < n_local) issue(c_first + cl + SETS - 1, pf[(d + SETS - 1) % SETS]);
+          if (ua >= 1) u2_wait(a_empty + 8 * sa, (uint32_t)((ua - 1) & 1));  // the MMAs of chunk cl-2 have read this stage
+          unsigned char* stage = a_smem + (size_t)sa * a_stage;
+#pragma unroll
+          for (int i = 0; i < UPT; ++i) {
+            if (tid + i * U2_CONVERTERS < n_a) {
+              float4 v = pf[d][i];
+              if (slope != 1.0f) {
+                v.x = v.x > 0.f ? v.x : v.x * slope;
+                v.y = v.y > 0.f ? v.y : v.y * slope;
+                v.z = v.z > 0.f ? v.z : v.z * slope;
+                v.w = v.w > 0.f ? v.w : v.w * slope;
+              }
+              u2_split_store<NP>(v, stage, a_piece, soff[i]);
+            }
           }
-          u2_split_store<NP>(v, stage, a_piece, soff[i]);
+          // every lane publishes its own generic-proxy writes to the async proxy, then one lane per warp arrives (256
+          // arrivals on one mbarrier serialise; 8 do not)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) u2_arrive(a_full + 8 * sa);
+          if (tid == 0) u2_stamp(p, cl == 0 ? 2 : 6);
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-      u2_arrive(a_full + 8 * sa);
     }
   } else if (warp == 8) {
     // ---------------- MMA issuer
@@ -243,6 +265,7 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
         const int sa = cl & 1, ua = cl >> 1;
         u2_wait(a_full + 8 * sa, (uint32_t)(ua & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (cl == 0) u2_stamp(p, 3);
         const int c = c_first + cl;
         const int j_lo = (cl == 0) ? u0 - c * k : 0;
         const int j_hi = (cl == n_local - 1) ? (u1 - 1) - c * k : k - 1;
@@ -251,6 +274,7 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
           const uint32_t sb = uc % (uint32_t)SB, ub = uc / (uint32_t)SB;
           u2_wait(b_full + 8 * sb, ub & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (uc == 0) u2_stamp(p, 4);
           const uint32_t a_tap = a_base + (uint32_t)(j * p.dil) * 16u;
           const uint32_t b_base = smem_u32(b_smem + (size_t)sb * b_unit);
           for (int ks = 0; ks < (CK >> 4); ++ks) {
@@ -275,6 +299,7 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
         u2_commit(a_empty + 8 * sa);
       }
       u2_commit(acc_full);
+      u2_stamp(p, 5);
     }
   } else {
     // ---------------- weight ring: one bulk copy per (chunk, tap) unit, all pieces
@@ -295,6 +320,7 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
   if (warp < 8) {
     u2_wait(acc_full, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) u2_stamp(p, 7);
     const Epilogue& ep = p.ep;
     const int M = p.M, N = p.N;
     const int quad = warp & 3;
@@ -353,6 +379,7 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
       }
     }
   }
+  if (tid == 0) u2_stamp(p, 8);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 8) {
@@ -396,16 +423,30 @@ __global__ void umma2_pack_kernel(const float* __restrict__ W, int N, int C_in, 
   }
 }
 
+}  // namespace
+int g_umma2_split_below = 148;  // tile grids smaller than this are split over (chunk, tap) units (ss_set_option umma2_split_below)
+int g_umma2_min_units = 4;      // ... into slices of at least this many units
+unsigned long long* g_umma2_dbg = nullptr;  // device buffer of 16 stamps when the debug option is on
+namespace {
+
 int u2_bn(int N) { return N >= 128 ? 128 : N > 32 ? 64 : N > 16 ? 32 : 16; }
+
+template <int BN, int NP, int UPT, int SETS>
+void u2_launch_v(const U2Params& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(umma2_kernel<BN, NP, UPT, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    prefer_shared_once((const void*)umma2_kernel<BN, NP, UPT, SETS>);
+    configured = true;
+  }
+  umma2_kernel<BN, NP, UPT, SETS><<<grid, U2_THREADS, smem, st>>>(p);
+}
 
 template <int BN, int NP>
 void u2_launch(const U2Params& p, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(umma2_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
-  umma2_kernel<BN, NP><<<grid, U2_THREADS, smem, st>>>(p);
+  const int n_a = p.rs * (p.CK / 4);  // float4 units per staged chunk
+  if (n_a <= 4 * U2_CONVERTERS) u2_launch_v<BN, NP, 4, 3>(p, grid, smem, st);
+  else u2_launch_v<BN, NP, U2_MAX_UNITS, 2>(p, grid, smem, st);
 }
 
 }  // namespace
@@ -486,9 +527,9 @@ void umma2_conv(Umma2Cache* cache, const ConvA& a, const float* W, int N, const 
   // ---- split over (chunk, tap) units when the tile grid cannot fill the GPU
   const int m_tiles = (M + U2_BM - 1) / U2_BM;
   const long base = (long)m_tiles * n_tiles;
-  const int min_units = 4;
+  const int min_units = std::max(1, g_umma2_min_units);
   int splits = 1;
-  if (base < 148 && p.units_total >= 2 * min_units) {
+  if (base < g_umma2_split_below && p.units_total >= 2 * min_units) {
     splits = (int)std::min<long>((148 + base - 1) / base, p.units_total / min_units);
     while (splits > 1 && (size_t)splits * M * N * sizeof(float) > (32u << 20)) --splits;
   }
@@ -504,6 +545,7 @@ void umma2_conv(Umma2Cache* cache, const ConvA& a, const float* W, int N, const 
   }
   p.units_per_split = ups;
   p.ws = ws;
+  p.dbg = g_umma2_dbg;
   const size_t a_bytes = (size_t)2 * NP * (CK >> 3) * p.rs_pad * 16;
   const size_t b_unit = (size_t)NP * BN * CK * 2;
   p.SB = (((a_bytes + 127) & ~(size_t)127) + 4 * b_unit <= 110 * 1024) ? 4 : 3;

@@ -71,6 +71,7 @@ def load_library() -> ctypes.CDLL:
     lib.ss_ctc_greedy.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
     lib.ss_ctc_greedy_rows.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
     lib.ss_mt_greedy.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, i32, ctypes.POINTER(i32), vp]
+    lib.ss_mt_stable_rows.argtypes = [vp, i32]
     lib.ss_mt_features.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp]
     lib.ss_t2u_unit_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.ss_vocoder_durations.argtypes = [vp, vp, vp, i32, i32, vp, vp]
@@ -92,7 +93,7 @@ def load_library() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_ctc_greedy_rows", "ss_mt_greedy",
-    "ss_mt_features", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
+    "ss_mt_features", "ss_mt_stable_rows", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
     "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count",
 ]
 
@@ -173,13 +174,19 @@ class Engine:
             raise
         # tensor-core routing (kernels_umma.cu): vocoder convs tolerate the 3-MMA split (1e-3 waveform bar, measured 7e-6);
         # linears that feed an arg-max stay on the exact fp32 kernels unless explicitly switched on
-        self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "0")))
-        self.set_option("umma_linear", int(os.environ.get("SS_UMMA_LINEAR", "0")))
+        self.set_option("prefer_shared", int(os.environ.get("SS_PREFER_SHARED", "1")))
+        self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "12")))
+        self.set_option("umma_linear", int(os.environ.get("SS_UMMA_LINEAR", "13")))
         self.set_option("umma_min_rows", int(os.environ.get("SS_UMMA_MIN_ROWS", "128")))
         self.set_option("umma_min_channels", int(os.environ.get("SS_UMMA_MIN_CHANNELS", "16")))
         self.set_option("persistent_encoder", int(os.environ.get("SS_PERSISTENT_ENCODER", "1")))
         self.set_option("persistent_mt", int(os.environ.get("SS_PERSISTENT_MT", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))
+        self.set_option("vocoder_graph", int(os.environ.get("SS_VOCODER_GRAPH", "0")))
+        self.set_option("graph_pdl", int(os.environ.get("SS_GRAPH_PDL", "0")))
+        self.set_option("persistent_prefetch", int(os.environ.get("SS_PERSISTENT_PREFETCH", "0")))
+        self.set_option("umma2_split_below", int(os.environ.get("SS_UMMA2_SPLIT_BELOW", "148")))
+        self.set_option("umma2_min_units", int(os.environ.get("SS_UMMA2_MIN_UNITS", "4")))
         self.set_option("persistent_barrier", int(os.environ.get("SS_PERSISTENT_BARRIER", "1")))
         self.hop = self.lib.ss_vocoder_hop(self._h)
         self.vocoder_receptive_field = self.lib.ss_vocoder_receptive_field(self._h)
@@ -301,9 +308,13 @@ class Engine:
         n = int(host[:1].view(torch.int32)[0])
         return host[1:1 + n].tolist(), host[1 + T:].view(torch.int32)[:n].tolist()
 
-    def mt_greedy(self, enc: torch.Tensor, prefix: Optional[Sequence[int]], max_new_tokens: int, max_len_b: int = 100) -> Tuple[List[int], torch.Tensor]:
-        """Returns (tokens without the trailing eos, decoder features of [eos]+tokens as [n+1, mt_dim])."""
+    def mt_greedy(self, enc: torch.Tensor, prefix: Optional[Sequence[int]], max_new_tokens: int, max_len_b: int = 100,
+                  stable_rows: int = 0) -> Tuple[List[int], torch.Tensor]:
+        """Returns (tokens without the trailing eos, decoder features of [eos]+tokens as [n+1, mt_dim]).
+        stable_rows: leading rows of `enc` that are final for this utterance (ss_mt_stable_rows); 0 = project every row."""
         assert enc.is_cuda and enc.is_contiguous() and enc.dim() == 2
+        if stable_rows > 0:
+            self._check(self.lib.ss_mt_stable_rows(self._h, int(stable_rows)))
         prefix = list(prefix) if prefix is not None else []
         cap = self.max_mt_positions
         pfx = (ctypes.c_int64 * max(len(prefix), 1))(*prefix)
@@ -315,7 +326,9 @@ class Engine:
         n = n_out.value
         return [int(out[i]) for i in range(n)], feats[: n + 1]
 
-    def mt_features(self, enc: torch.Tensor, tokens: Sequence[int], want_logits: bool = False):
+    def mt_features(self, enc: torch.Tensor, tokens: Sequence[int], want_logits: bool = False, stable_rows: int = 0):
+        if stable_rows > 0:
+            self._check(self.lib.ss_mt_stable_rows(self._h, int(stable_rows)))
         toks = (ctypes.c_int64 * len(tokens))(*[int(t) for t in tokens])
         feats = self._f32(len(tokens), self.cfg.mt_dim)
         logits = self._f32(self.cfg.tgt_vocab) if want_logits else None
@@ -372,6 +385,13 @@ class Engine:
         self._check(self.lib.ss_op_conv1d(self._h, self._stream(), x.data_ptr(), L, C, w.data_ptr(), self._ptr(b), N, ksize, dil, pad_left,
                                           float(pre_lrelu), mode, out.data_ptr()))
         return out
+
+    def persistent_time(self):
+        """(summed ms, launches, summed algorithmic bytes) of the persistent encoder kernel since the last query
+        (CUDA events on the launching stream; enable with set_option('persistent_time', 1))"""
+        buf = (ctypes.c_double * 3)()
+        self._check(self.lib.ss_debug_copy(self._h, b"persist_time", buf, ctypes.sizeof(buf)))
+        return float(buf[0]), int(buf[1]), float(buf[2])
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.ss_set_option(self._h, name.encode(), int(value)))

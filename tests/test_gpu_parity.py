@@ -287,6 +287,79 @@ def test_vocoder_golden(eng3, gold):
     assert dur1.tolist() == [1] * codes.numel() and int(cum1[-1].item()) == codes.numel()
 
 
+def test_vocoder_graph_replay_is_identical(eng3, gold):
+    """The generator runs eagerly the first time a frame count is seen and as a CUDA-graph replay afterwards: same kernels,
+    same split decisions, so the samples must be bit-identical; and identical to the eager path with the option off."""
+    g = gold["vocoder"]
+    codes = cuda(g["code"][0].astype(np.int64))
+    dur, cum = eng3.vocoder_durations(codes, True)
+    total = int(cum[-1].item())
+    eng3.set_option("vocoder_graph", 1)
+    first = eng3.vocoder_generate(total, total - 21, 21, -1).clone()   # eager + capture
+    l0 = eng3.launch_count()
+    second = eng3.vocoder_generate(total, total - 21, 21, -1).clone()  # replay
+    replay_launches = eng3.launch_count() - l0
+    third = eng3.vocoder_generate(total, total - 21, 21, -1).clone()
+    eng3.set_option("vocoder_graph", 0)
+    l0 = eng3.launch_count()
+    eager = eng3.vocoder_generate(total, total - 21, 21, -1).clone()
+    eager_launches = eng3.launch_count() - l0
+    eng3.set_option("vocoder_graph", 1)
+    report("vocoder_graph", replay_vs_first=maxdiff(second, first), eager_vs_replay=maxdiff(eager, second), replay_launches=replay_launches,
+           eager_launches=eager_launches)
+    assert torch.equal(first, second) and torch.equal(second, third) and torch.equal(eager, second)
+    assert replay_launches == eager_launches  # the replay accounts for every kernel node it runs
+
+
+# --------------------------------------------------------------------------------------------- tcgen05 kernels
+@pytest.mark.parametrize("shape", [(128, 32, 16, 1, 1, 0, 1.0), (100, 64, 128, 3, 1, 1, 0.1), (260, 256, 256, 11, 5, 25, 0.1),
+                                   (1040, 128, 128, 7, 3, 9, 0.1), (16640, 16, 16, 7, 5, 15, 0.1), (300, 128, 512, 7, 1, 3, 1.0),
+                                   (775, 512, 2048, 1, 1, 0, 1.0), (200, 512, 1005, 1, 1, 0, 1.0), (130, 48, 48, 5, 2, 4, 0.1)])
+def test_tcgen05_conv_vs_fp64_reference(eng3, shape):
+    """kernels_umma2.cu (tap-shift implicit GEMM, bf16x3 / bf16x6 operand splitting) against torch conv1d in fp64 and against
+    the fp32 CUDA-core kernel: 2 pieces within 2e-3 (vocoder path, waveform bar 1e-3 after 40 layers is checked by the
+    vocoder tests), 3 pieces within 2e-4 (same bar as the fp32 kernels)."""
+    import torch.nn.functional as F
+
+    L, C, N, k, dil, pad, slope = shape
+    g = torch.Generator().manual_seed(L + C + N + k)
+    x = torch.randn(L, C, generator=g)
+    w = torch.randn(N, k * C, generator=g) / (k * C) ** 0.5
+    b = torch.randn(N, generator=g)
+    xx = x.double()
+    if slope != 1.0:
+        xx = torch.where(xx > 0, xx, xx * slope)
+    wt = w.double().view(N, k, C).permute(0, 2, 1).contiguous()
+    ref = F.conv1d(F.pad(xx.t().unsqueeze(0), (pad, (k - 1) * dil - pad)), wt, b.double(), dilation=dil)[0].t().float()
+    xd, wd, bd = cuda(x), cuda(w), cuda(b)
+    d0 = maxdiff(eng3.op_conv1d(xd, wd, bd, k, dil, pad, slope, 0), ref)
+    eng3.set_option("umma2_cache_clear", 1)  # weights of an earlier case may have lived at the same address
+    d2 = maxdiff(eng3.op_conv1d(xd, wd, bd, k, dil, pad, slope, 12), ref)
+    eng3.set_option("umma2_cache_clear", 1)
+    d3 = maxdiff(eng3.op_conv1d(xd, wd, bd, k, dil, pad, slope, 13), ref)
+    eng3.set_option("umma2_cache_clear", 1)
+    report("tcgen05_conv", shape=list(shape), fp32=d0, bf16x3=d2, bf16x6=d3)
+    assert d0 < FP_TOL and d2 < 2e-3 and d3 < FP_TOL, (d0, d2, d3)
+
+
+def test_mt_cross_kv_reuse_of_final_rows(full):
+    """ss_mt_stable_rows: cross-attention K / V of encoder rows declared final are projected once.  Two calls on a growing
+    encoder buffer (the non-final tail changes between them) must give the tokens / features of hint-free calls."""
+    cfg, e, o = full
+    g = torch.Generator().manual_seed(3)
+    buf = torch.randn(64, cfg.enc_dim, generator=g).cuda()
+    e.encoder_stream_reset()
+    t1, f1 = e.mt_greedy(buf[:24], None, 2, stable_rows=16)
+    buf[16:40] = torch.randn(24, cfg.enc_dim, generator=g).cuda()  # rows >= 16 were provisional; 16 more arrive
+    t2, f2 = e.mt_greedy(buf[:40], t1, 2, stable_rows=32)
+    f2 = f2.clone()
+    e.encoder_stream_reset()
+    r2, g2 = e.mt_greedy(buf[:40].clone(), t1, 2)  # different buffer, no hint: every row projected
+    d = maxdiff(f2, g2)
+    report("mt_cross_reuse", feats=d)
+    assert t2 == r2 and d < FP_TOL, (t2, r2, d)
+
+
 # --------------------------------------------------------------------------------------------- end to end
 def agent_args(**kw):
     d = dict(model_path="synthetic", data_bin=".", config_yaml=None, multitask_config_yaml=None, global_stats=None,

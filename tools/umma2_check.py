@@ -75,6 +75,23 @@ elif part == "time":
         row["gflop"] = 2.0 * L * C * k * N / 1e9
         res[f"time_L{L}_C{C}_N{N}_k{k}"] = row
         print(L, C, N, k, {kk: round(v, 2) for kk, v in row.items()}, flush=True)
+elif part == "stamps":
+    import ctypes
+    e.set_option("umma2_debug", 1)
+    names = ["start", "setup_done", "first_A_ready", "issuer_saw_A", "issuer_saw_B", "last_commit", "last_A_ready", "acc_full_seen", "epilogue_done"]
+    for (L, C, N, k, dil, pad, slope, mode) in [(160, 256, 1024, 1, 1, 0, 1.0, 13), (775, 512, 2048, 1, 1, 0, 1.0, 13), (775, 2048, 512, 1, 1, 0, 1.0, 13),
+                                                (260, 256, 256, 11, 5, 25, 0.1, 12), (260, 256, 256, 3, 1, 1, 0.1, 12), (4160, 64, 64, 7, 1, 3, 0.1, 12)]:
+        x = torch.randn(L, C, device="cuda"); w = torch.randn(N, k * C, device="cuda") / (k * C) ** 0.5; b = torch.zeros(N, device="cuda")
+        e.set_option("umma2_cache_clear", 1)
+        for _ in range(3): e.op_conv1d(x, w, b, k, dil, pad, slope, mode)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_uint64 * 16)()
+        e._check(e.lib.ss_debug_copy(e._h, b"umma2_ts", buf, ctypes.sizeof(buf)))
+        t = [int(v) for v in buf[:9]]
+        rel = {n: (t[i] - t[0]) for i, n in enumerate(names)}
+        res[f"stamps_L{L}_C{C}_N{N}_k{k}"] = rel
+        print(L, C, N, k, "ns from CTA start:", rel, flush=True)
+    e.set_option("umma2_debug", 0)
 else:
     gold = np.load(os.path.join(ROOT, "tests", "golden", "vocoder.npz"))
     codes = torch.from_numpy(gold["code"][0].astype(np.int64)).cuda()
