@@ -173,6 +173,37 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
   const int n_local = c_last - c_first + 1;
 
   if (tid == 0) u2_stamp(p, 0);
+  // ---- converter set-up (every warp computes the addresses; only warps 0-7 load)
+  const int upr_shift = (CK == 32) ? 3 : 2;  // float4 units per row = CK / 4
+  const int upr = 1 << upr_shift;
+  const int n_a = p.rs * upr;
+  int64_t goff[UPT];
+  uint32_t soff[UPT];
+#pragma unroll
+  for (int i = 0; i < UPT; ++i) {
+    const int idx = tid + i * U2_CONVERTERS;
+    const int r = idx >> upr_shift, q = idx & (upr - 1);
+    const int pos = m0 + r - p.a.pad_left;
+    const bool inb = idx < n_a && pos >= 0 && pos < p.a.L_in;
+    goff[i] = inb ? (int64_t)pos * p.a.ldx + q * 4 : (int64_t)-1;
+    soff[i] = (uint32_t)(q >> 1) * a_plane + (uint32_t)r * 16u + (uint32_t)(q & 1) * 8u;
+  }
+  const float slope = p.a.pre_lrelu;
+  // register ring of SETS chunk loads: while chunk cl is converted, the loads of chunks cl+1 .. cl+SETS-1 are in flight
+  // (UPT = 6, SETS = 2 for convolutions with a halo; UPT = 4, SETS = 3 for linears, whose chunks carry few MMAs)
+  float4 pf[SETS][UPT];
+  auto issue = [&](int c, float4* dst) {
+    const float* xc = p.a.x + (int64_t)c * CK;
+#pragma unroll
+    for (int i = 0; i < UPT; ++i)
+      dst[i] = goff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(xc + goff[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (warp < 8) {  // the first chunk loads do not depend on the barriers: they fly while TMEM / mbarriers are set up
+#pragma unroll
+    for (int d = 0; d < SETS - 1; ++d)
+      if (d < n_local) issue(c_first + d, pf[d]);
+  }
+
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -197,33 +228,6 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
 
   if (warp < 8) {
     // ---------------- converters: activation rows -> bf16 pieces, one channel chunk per stage
-    const int upr_shift = (CK == 32) ? 3 : 2;  // float4 units per row = CK / 4
-    const int upr = 1 << upr_shift;
-    const int n_a = p.rs * upr;
-    int64_t goff[UPT];
-    uint32_t soff[UPT];
-#pragma unroll
-    for (int i = 0; i < UPT; ++i) {
-      const int idx = tid + i * U2_CONVERTERS;
-      const int r = idx >> upr_shift, q = idx & (upr - 1);
-      const int pos = m0 + r - p.a.pad_left;
-      const bool inb = idx < n_a && pos >= 0 && pos < p.a.L_in;
-      goff[i] = inb ? (int64_t)pos * p.a.ldx + q * 4 : (int64_t)-1;
-      soff[i] = (uint32_t)(q >> 1) * a_plane + (uint32_t)r * 16u + (uint32_t)(q & 1) * 8u;
-    }
-    const float slope = p.a.pre_lrelu;
-    // register ring of SETS chunk loads: while chunk cl is converted, the loads of chunks cl+1 .. cl+SETS-1 are in flight
-    // (UPT = 6, SETS = 2 for convolutions with a halo; UPT = 4, SETS = 3 for linears, whose chunks carry few MMAs)
-    float4 pf[SETS][UPT];
-    auto issue = [&](int c, float4* dst) {
-      const float* xc = p.a.x + (int64_t)c * CK;
-#pragma unroll
-      for (int i = 0; i < UPT; ++i)
-        dst[i] = goff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(xc + goff[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-#pragma unroll
-    for (int d = 0; d < SETS - 1; ++d)
-      if (d < n_local) issue(c_first + d, pf[d]);
     for (int clb = 0; clb < n_local; clb += SETS) {
 #pragma unroll
       for (int d = 0; d < SETS; ++d) {
@@ -316,7 +320,11 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
     }
   }
 
-  // ---------------- epilogue (warps 0-7): warp w owns TMEM lanes 32*(w&3).., the two warpgroups split the columns
+  // ---------------- epilogue (warps 0-7): warp w owns TMEM lanes 32*(w&3).. (= 32 output rows); with BN >= 64 the two
+  // warpgroups split the columns.  tcgen05.ld hands every lane ONE row (registers = columns); written out like that, each
+  // store instruction would touch 32 rows x 4 bytes = 32 sectors (measured: 10.7 us of a 15 us CTA).  So each 32 x CW
+  // block goes through a padded shared-memory tile (the operand stages are free once acc_full has completed) and is
+  // written row by row with lanes = consecutive columns: full 128-byte segments, bias / residual reads coalesced too.
   if (warp < 8) {
     u2_wait(acc_full, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -324,59 +332,74 @@ __global__ void __launch_bounds__(U2_THREADS) umma2_kernel(const __grid_constant
     const Epilogue& ep = p.ep;
     const int M = p.M, N = p.N;
     const int quad = warp & 3;
-    const int m = m0 + quad * 32 + lane;
-    constexpr int COLS_PER_GROUP = BN >= 32 ? BN / 2 : BN;
-    const int c_begin = (BN >= 32) ? (warp >> 2) * COLS_PER_GROUP : 0;
-    const bool epi_active = (BN >= 32) || warp < 4;
-    int64_t orow = m;
-    if (ep.out_L > 0 && m < M) orow = (int64_t)m * ep.out_row_stride + ep.out_row_offset;  // B == 1
+    constexpr int GROUPS = BN >= 64 ? 2 : 1;
+    constexpr int COLS_PER_GROUP = BN / GROUPS;
+    constexpr int CW = COLS_PER_GROUP >= 32 ? 32 : 16;  // columns per tcgen05.ld
+    constexpr int RPI = 32 / CW;                         // rows written per store instruction
+    const int c_begin = (warp >> 2) * COLS_PER_GROUP;
+    const bool epi_active = warp < 4 * GROUPS;
+    float* tbuf = reinterpret_cast<float*>(a_smem) + warp * (32 * 33);
+    const int cc = lane % CW, rsub = lane / CW;
 #pragma unroll 1
-    for (int c0 = c_begin; epi_active && c0 < c_begin + COLS_PER_GROUP; c0 += 16) {
-      uint32_t r[16];
+    for (int c0 = c_begin; epi_active && c0 < c_begin + COLS_PER_GROUP; c0 += CW) {
+      uint32_t r[CW];
       const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m >= M) continue;
-      if (p.ws != nullptr) {  // split: raw partial sums
-        float* wz = p.ws + ((int64_t)blockIdx.z * M + m) * N;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          int n = n0 + c0 + j;
-          if (n < N) wz[n] = __uint_as_float(r[j]);
-        }
-        continue;
-      }
-      float* orow_p = ep.out + orow * ep.ldo;
-      const float* rrow_p = ep.residual ? ep.residual + orow * ep.ldo : nullptr;
-      if (ep.glu) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          int n = n0 + c0 + j;
-          if (n >= N) continue;
-          float av = __uint_as_float(r[j]) + (ep.bias ? ep.bias[n] : 0.f);
-          float gv = __uint_as_float(r[j + 1]) + (ep.bias ? ep.bias[n + 1] : 0.f);
-          float y = ep.alpha * (av * (1.0f / (1.0f + expf(-gv))));
-          int oc = n >> 1;
-          if (rrow_p) y += ep.res_scale * rrow_p[oc];
-          if (ep.accumulate) y += orow_p[oc];
-          orow_p[oc] = y;
-        }
+      if (CW == 32) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16 % CW]), "=r"(r[17 % CW]),
+              "=r"(r[18 % CW]), "=r"(r[19 % CW]), "=r"(r[20 % CW]), "=r"(r[21 % CW]), "=r"(r[22 % CW]), "=r"(r[23 % CW]), "=r"(r[24 % CW]),
+              "=r"(r[25 % CW]), "=r"(r[26 % CW]), "=r"(r[27 % CW]), "=r"(r[28 % CW]), "=r"(r[29 % CW]), "=r"(r[30 % CW]), "=r"(r[31 % CW])
+            : "r"(taddr)
+            : "memory");
       } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (tid == 0 && c0 == c_begin) u2_stamp(p, 9);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          int n = n0 + c0 + j;
-          if (n >= N) continue;
-          float y = ep.alpha * u2_act(__uint_as_float(r[j]) + (ep.bias ? ep.bias[n] : 0.f), ep.act);
-          if (rrow_p) y += ep.res_scale * rrow_p[n];
-          if (ep.accumulate) y += orow_p[n];
-          orow_p[n] = y;
+      for (int j = 0; j < CW; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      if (tid == 0 && c0 == c_begin) u2_stamp(p, 10);
+      const int n = n0 + c0 + cc;
+      const bool n_ok = n < N;
+      const float bias_n = (ep.bias != nullptr && n_ok && p.ws == nullptr) ? ep.bias[n] : 0.f;
+#pragma unroll 4
+      for (int it = 0; it < CW; ++it) {  // CW iterations x RPI rows = 32 rows
+        const int rr = it * RPI + rsub;
+        const int m = m0 + quad * 32 + rr;
+        const float v = tbuf[rr * 33 + cc];
+        if (p.ws != nullptr) {  // split: raw partial sums
+          if (m < M && n_ok) p.ws[((int64_t)blockIdx.z * M + m) * N + n] = v;
+          continue;
+        }
+        const int64_t orow = ep.out_L > 0 ? (int64_t)m * ep.out_row_stride + ep.out_row_offset : (int64_t)m;  // B == 1
+        if (ep.glu) {
+          const float gate = __shfl_down_sync(0xffffffffu, v + bias_n, 1);  // columns are interleaved (a, gate) pairs
+          if (m < M && n_ok && (n & 1) == 0) {
+            float y = ep.alpha * ((v + bias_n) * (1.0f / (1.0f + expf(-gate))));
+            const int64_t o = orow * ep.ldo + (n >> 1);
+            if (ep.residual) y += ep.res_scale * ep.residual[o];
+            if (ep.accumulate) y += ep.out[o];
+            ep.out[o] = y;
+          }
+        } else if (m < M && n_ok) {
+          float y = ep.alpha * u2_act(v + bias_n, ep.act);
+          const int64_t o = orow * ep.ldo + n;
+          if (ep.residual) y += ep.res_scale * ep.residual[o];
+          if (ep.accumulate) y += ep.out[o];
+          ep.out[o] = y;
         }
       }
+      if (tid == 0 && c0 == c_begin) u2_stamp(p, 11);
+      __syncwarp();  // the tile is rewritten by the next column block
     }
   }
   if (tid == 0) u2_stamp(p, 8);
@@ -549,7 +572,7 @@ void umma2_conv(Umma2Cache* cache, const ConvA& a, const float* W, int N, const 
   const size_t a_bytes = (size_t)2 * NP * (CK >> 3) * p.rs_pad * 16;
   const size_t b_unit = (size_t)NP * BN * CK * 2;
   p.SB = (((a_bytes + 127) & ~(size_t)127) + 4 * b_unit <= 110 * 1024) ? 4 : 3;
-  const size_t smem = ((a_bytes + 127) & ~(size_t)127) + p.SB * b_unit + 256;
+  const size_t smem = std::max<size_t>(((a_bytes + 127) & ~(size_t)127) + p.SB * b_unit, 8 * 32 * 33 * sizeof(float)) + 256;  // >= the epilogue's transpose tiles
   dim3 grid(n_tiles, m_tiles, splits);
   if (NP == 3) {
     switch (BN) {

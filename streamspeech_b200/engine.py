@@ -174,7 +174,7 @@ class Engine:
             raise
         # tensor-core routing (kernels_umma.cu): vocoder convs tolerate the 3-MMA split (1e-3 waveform bar, measured 7e-6);
         # linears that feed an arg-max stay on the exact fp32 kernels unless explicitly switched on
-        self.set_option("prefer_shared", int(os.environ.get("SS_PREFER_SHARED", "1")))
+        self.set_option("prefer_shared", int(os.environ.get("SS_PREFER_SHARED", "0")))
         self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "12")))
         self.set_option("umma_linear", int(os.environ.get("SS_UMMA_LINEAR", "13")))
         self.set_option("umma_min_rows", int(os.environ.get("SS_UMMA_MIN_ROWS", "128")))

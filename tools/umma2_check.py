@@ -78,7 +78,7 @@ elif part == "time":
 elif part == "stamps":
     import ctypes
     e.set_option("umma2_debug", 1)
-    names = ["start", "setup_done", "first_A_ready", "issuer_saw_A", "issuer_saw_B", "last_commit", "last_A_ready", "acc_full_seen", "epilogue_done"]
+    names = ["start", "setup_done", "first_A_ready", "issuer_saw_A", "issuer_saw_B", "last_commit", "last_A_ready", "acc_full_seen", "epilogue_done", "tmem_ld_done", "transpose_written", "first_block_stored"]
     for (L, C, N, k, dil, pad, slope, mode) in [(160, 256, 1024, 1, 1, 0, 1.0, 13), (775, 512, 2048, 1, 1, 0, 1.0, 13), (775, 2048, 512, 1, 1, 0, 1.0, 13),
                                                 (260, 256, 256, 11, 5, 25, 0.1, 12), (260, 256, 256, 3, 1, 1, 0.1, 12), (4160, 64, 64, 7, 1, 3, 0.1, 12)]:
         x = torch.randn(L, C, device="cuda"); w = torch.randn(N, k * C, device="cuda") / (k * C) ** 0.5; b = torch.zeros(N, device="cuda")
@@ -87,7 +87,7 @@ elif part == "stamps":
         torch.cuda.synchronize()
         buf = (ctypes.c_uint64 * 16)()
         e._check(e.lib.ss_debug_copy(e._h, b"umma2_ts", buf, ctypes.sizeof(buf)))
-        t = [int(v) for v in buf[:9]]
+        t = [int(v) for v in buf[:12]]
         rel = {n: (t[i] - t[0]) for i, n in enumerate(names)}
         res[f"stamps_L{L}_C{C}_N{N}_k{k}"] = rel
         print(L, C, N, k, "ns from CTA start:", rel, flush=True)
