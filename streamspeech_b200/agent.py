@@ -178,6 +178,16 @@ class _EngineAgentMixin:
         self._ctc_valid[head] = min(self._enc_final, enc.shape[0])  # arg-max of rows that are final now is reusable
         return out
 
+    def _ctc_pair(self, enc: torch.Tensor):
+        """ASR and ST CTC heads of one policy() call with a single device->host read (see _ctc)."""
+        if not hasattr(self, "_ctc_am") or self._ctc_am.shape[1] < self.enc_buf.shape[0]:
+            self._ctc_am = torch.zeros(2, self.enc_buf.shape[0], dtype=torch.int64, device=self.enc_buf.device)
+        cached = self.encoder_mode == "cached"
+        row0s = [min(self._ctc_valid[h], enc.shape[0]) if cached else 0 for h in (0, 1)]
+        a, b = self.engine.ctc_greedy_rows_pair(enc, row0s, [self._ctc_am[0], self._ctc_am[1]])
+        self._ctc_valid = [min(self._enc_final, enc.shape[0])] * 2
+        return a, b
+
 
 @entrypoint
 class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
@@ -275,8 +285,7 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
             return READ
         enc = self._encode(feature)  # [T, 256]
         self.encoder_out = enc
-        src_ctc_indices, _ = self._ctc(0, enc)
-        tgt_ctc_indices, _ = self._ctc(1, enc)
+        (src_ctc_indices, _), (tgt_ctc_indices, _) = self._ctc_pair(enc)  # agent:437, 461
         tr["asr_tokens"], tr["st_tokens"] = src_ctc_indices, tgt_ctc_indices
 
         if not self.states.source_finished:  # agent:480-509
@@ -337,12 +346,11 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
             feats = feats[: len(prev_output_tokens_mt)]
         # 2./3. T2U encoder + CTC unit decoder (agent:662-689)
         r = eng.t2u_unit_decode(feats.contiguous(), n_pad_tail=n_pad_tail)
-        n_units = int(r["count"].item())
-        if n_units == 0:
+        tmp = eng.units_to_host(r)
+        if len(tmp) == 0:
             if not self.states.source_finished:
                 return READ
             return self._finished_write_tuple()
-        tmp = r["units"][:n_units].tolist()
         if tmp[-1] == self.eos:
             tmp = tmp[:-1]
         unit = []

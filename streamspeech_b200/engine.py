@@ -308,6 +308,25 @@ class Engine:
         n = int(host[:1].view(torch.int32)[0])
         return host[1:1 + n].tolist(), host[1 + T:].view(torch.int32)[:n].tolist()
 
+    def ctc_greedy_rows_pair(self, enc: torch.Tensor, row0s: Sequence[int], argmaxes: Sequence[torch.Tensor]):
+        """Both CTC heads (0 = ASR, 1 = ST) of one policy() call: the two launches are enqueued back to back and read with
+        ONE device->host copy.  Returns ((tokens0, index0), (tokens1, index1))."""
+        assert enc.is_cuda and enc.is_contiguous() and enc.dim() == 2
+        T = enc.shape[0]
+        W = 2 * T + 2
+        out = torch.zeros(2 * W, dtype=torch.int64, device=self.device)  # per head: [count | tokens[T] | index (int32 pairs)]
+        for hd in (0, 1):
+            o = out[hd * W:(hd + 1) * W]
+            self._check(self.lib.ss_ctc_greedy_rows(self._h, self._stream(), hd, enc.data_ptr(), T, int(row0s[hd]), argmaxes[hd].data_ptr(),
+                                                    o[1:1 + T].data_ptr(), o[1 + T:].view(torch.int32)[:T].data_ptr(), o[:1].view(torch.int32).data_ptr()))
+        host = out.cpu()
+        res = []
+        for hd in (0, 1):
+            hrow = host[hd * W:(hd + 1) * W]
+            n = int(hrow[:1].view(torch.int32)[0])
+            res.append((hrow[1:1 + n].tolist(), hrow[1 + T:].view(torch.int32)[:n].tolist()))
+        return res[0], res[1]
+
     def mt_greedy(self, enc: torch.Tensor, prefix: Optional[Sequence[int]], max_new_tokens: int, max_len_b: int = 100,
                   stable_rows: int = 0) -> Tuple[List[int], torch.Tensor]:
         """Returns (tokens without the trailing eos, decoder features of [eos]+tokens as [n+1, mt_dim]).
@@ -340,13 +359,21 @@ class Engine:
         S = mt_feats.shape[0]
         L = S * self.cfg.ctc_upsample_rate
         am = torch.empty(L, dtype=torch.int64, device=self.device)
-        units = torch.empty(L, dtype=torch.int64, device=self.device)
-        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        packed = torch.zeros(L + 1, dtype=torch.int64, device=self.device)  # [count | units]: one device->host copy reads both
+        units = packed[1:]
+        cnt = packed[:1].view(torch.int32)[:1]
         t2u = self._f32(S, self.cfg.unit_dim) if debug else None
         logits = self._f32(L, self.cfg.unit_vocab) if debug else None
         self._check(self.lib.ss_t2u_unit_decode(self._h, self._stream(), mt_feats.data_ptr(), S, n_pad_tail, int(mask_eos), am.data_ptr(),
                                                 units.data_ptr(), cnt.data_ptr(), self._ptr(t2u), self._ptr(logits)))
-        return {"argmax": am, "units": units, "count": cnt, "t2u_out": t2u, "logits": logits}
+        return {"argmax": am, "units": units, "count": cnt, "t2u_out": t2u, "logits": logits, "packed": packed}
+
+    @staticmethod
+    def units_to_host(r) -> List[int]:
+        """the collapsed unit sequence of a t2u_unit_decode result as a python list (one device->host copy)"""
+        host = r["packed"].cpu()
+        n = int(host[:1].view(torch.int32)[0])
+        return host[1:1 + n].tolist()
 
     def vocoder_durations(self, codes: torch.Tensor, dur_prediction: bool = True):
         assert codes.is_cuda and codes.dtype == torch.int64 and codes.is_contiguous()

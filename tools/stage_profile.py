@@ -26,7 +26,7 @@ def main():
     agent = StreamSpeechS2STAgent(bench.agent_args(0, a.encoder_mode))
     eng = agent.engine
     stats = collections.defaultdict(lambda: [0, 0.0, 0])
-    for name in ("fbank", "encoder", "encoder_stream_step", "ctc_greedy", "mt_greedy", "mt_features", "t2u_unit_decode",
+    for name in ("fbank", "encoder", "encoder_stream_step", "ctc_greedy", "ctc_greedy_rows_pair", "mt_greedy", "mt_features", "t2u_unit_decode",
                  "vocoder_durations", "vocoder_generate"):
         fn = getattr(eng, name)
 
