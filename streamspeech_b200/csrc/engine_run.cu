@@ -131,9 +131,15 @@ struct DecScratch {
 // layer's own fused qkv (full sequence, cache == nullptr) or from an external KV cache that already holds `past` rows.
 void dec_layer(const DecLayerW& L, float* x, int n, int dim, int ffn, int heads, bool causal, int self_kv_len_limit,
                const int* self_kv_len_dev, float* cache_k, float* cache_v, int past, const float* cross_kv, int Tk,
-               const int* cross_len_dev, DecScratch& s, cudaStream_t st) {
+               const int* cross_len_dev, DecScratch& s, cudaStream_t st, int group_R = 0, const int* group_len_dev = nullptr) {
   const float scale = 0.125f;  // head_dim ** -0.5, head_dim = 64
-  if (cache_k) {
+  if (group_R > 1 && !cache_k && causal && n % group_R == 0) {
+    // rows come in groups of group_R identical consecutive rows (unit decoder layer 1): project the n / group_R distinct
+    // rows only and collapse the causal softmax over the copies analytically (grouped_causal_attn_kernel)
+    const int S = n / group_R;
+    ln_linear(x, dim * group_R, S, L.self_ln, L.qkv, ep_out(s.qkv, 3 * dim), s.y, st);
+    grouped_causal_attention(s.qkv, 3 * dim, s.qkv + dim, 3 * dim, s.qkv + 2 * dim, 3 * dim, s.attn, dim, S, group_R, heads, scale, group_len_dev, st);
+  } else if (cache_k) {
     ln_qkv_routed(x, dim, n, L.self_ln, L.qkv, dim, s.q, dim, cache_k + (size_t)past * dim, dim, cache_v + (size_t)past * dim, dim, s.y, st);
     mha_attention(s.q, dim, cache_k, dim, cache_v, dim, s.attn, dim, 1, n, past + n, heads, scale, 1, past, self_kv_len_dev, st);
   } else {
@@ -632,7 +638,9 @@ int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, in
   repeat_rows_add(t2u, Slen, R, dim, h->unit_pos_row, xu, st);
   for (int l = 0; l < c.unit_layers; ++l) {
     linear(t2u, dim, Slen, h->unit[l].ckv, ep_out(ckv, 2 * dim), st);
-    dec_layer(h->unit[l], xu, L, dim, c.unit_ffn, c.unit_heads, true, 0, kvlen_up, nullptr, nullptr, 0, ckv, Slen, kvlen, s2, st);
+    // layer 0 sees R identical copies of every T2U state (same positional row for every step, N1): grouped self-attention
+    const int gR = (l == 0 && h->unit_grouped) ? R : 0;
+    dec_layer(h->unit[l], xu, L, dim, c.unit_ffn, c.unit_heads, true, 0, kvlen_up, nullptr, nullptr, 0, ckv, Slen, kvlen, s2, st, gR, kvlen);
   }
   layer_norm(xu, dim, xu, dim, h->unit_ln.g, h->unit_ln.b, L, dim, st);
   Linear outp;
@@ -912,6 +920,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
     }
   }
   else if (n == "prefer_shared") g_prefer_shared = value;  // takes effect for kernels that have not been launched yet
+  else if (n == "unit_grouped") h->unit_grouped = value;
   else if (n == "vocoder_graph") h->vocoder_graph = value;
   else if (n == "graph_pdl") h->graph_pdl = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;

@@ -116,6 +116,11 @@ void mha_attention(const float* q, int ldq, const float* k, int ldk, const float
                    int Tq, int Tk, int H, float scale, int causal, int causal_offset, const int* kv_len_dev,
                    cudaStream_t st);
 
+// Causal self-attention over S groups of R identical consecutive rows (unit decoder layer 1, see kernels_attn.cu): q / k / v
+// hold the S distinct rows, out gets S*R rows.  kv_len[0] (device, optional) = number of valid (non-pad) groups.
+void grouped_causal_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int S, int R,
+                              int H, float scale, const int* kv_len_dev, cudaStream_t st);
+
 // depthwise chunk-causal conv (k taps, left context (k-1)/2) + folded BatchNorm + SiLU, channels-last.
 // x: [B*T][C] (absolute positions 0..T-1); computes positions t0..t0+n-1 into y rows 0..n-1 per batch element.
 void depthwise_bn_silu(const float* x, int ldx, const float* w /*[k][C]*/, const float* scale, const float* shift,

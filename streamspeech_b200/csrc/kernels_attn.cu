@@ -256,6 +256,65 @@ __global__ void __launch_bounds__(ATT_NT) attn_row_kernel(const float* __restric
   }
 }
 
+// Causal self-attention over a sequence in which every key / value / query row is repeated R times in a row (the first layer
+// of the CTC unit decoder: each T2U state is upsampled x25 and, because the reference's positional embedding indexes the
+// batch axis there, all R copies of a token carry identical inputs, hence identical q, k, v).  For the copy
+// r of group g the softmax over the R*g + r + 1 visible positions collapses to a softmax over g + 1 distinct keys with
+// multiplicities R (earlier groups) and r + 1 (own group):
+//     out[g, r] = (R * A_g + c * e_g * v_g) / (R * a_g + c * e_g),   A_g = sum_{j < g'} e_j v_j,  a_g = sum_{j < g'} e_j,
+// e_j = exp(s_j - max), g' = min(g, n_valid), c = r + 1 if g < n_valid else 0 (keys of padded groups are masked).
+// One CTA per (group, head); q / k / v are the S group rows.  out: [S*R][ldo].
+__global__ void __launch_bounds__(ATT_NT) grouped_causal_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                                      const float* __restrict__ v, int ldv, float* __restrict__ out, int ldo,
+                                                                      int S, int R, float scale, const int* __restrict__ kv_len) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float smem[];  // [S] scores
+  __shared__ __align__(16) float qs[HD];
+  __shared__ float red[4];
+  __shared__ float part[2][HD];
+  const int g = blockIdx.x, h = blockIdx.y;
+  const int n_valid = kv_len ? min(kv_len[0], S) : S;
+  const int n_prev = min(g, n_valid);           // earlier groups, every one of their R copies is visible
+  const bool own = g < n_valid;
+  const int n = n_prev + (own ? 1 : 0);         // distinct visible keys (own group last)
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < HD) qs[threadIdx.x] = q[(int64_t)g * ldq + h * HD + threadIdx.x] * scale;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += ATT_NT) {
+    const int key = (j < n_prev) ? j : g;
+    float sc = dot64(qs, k + (int64_t)key * ldk + h * HD);
+    smem[j] = sc;
+    mx = fmaxf(mx, sc);
+  }
+  mx = block_max128(mx, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < n; j += ATT_NT) {
+    float e = expf(smem[j] - mx);
+    smem[j] = e;
+    if (j < n_prev) sum += e;
+  }
+  sum = block_sum128(sum, red);  // a_g
+  __syncthreads();
+  // A_g[d]: two halves of the earlier keys per dimension
+  {
+    const int d = threadIdx.x & (HD - 1), half = threadIdx.x >> 6;
+    float a = 0.f;
+    for (int j = half; j < n_prev; j += 2) a = fmaf(smem[j], v[(int64_t)j * ldv + h * HD + d], a);
+    part[half][d] = a;
+  }
+  __syncthreads();
+  const float e_own = own ? smem[n_prev] : 0.f;
+  for (int idx = threadIdx.x; idx < R * HD; idx += ATT_NT) {
+    const int r = idx >> 6, d = idx & (HD - 1);
+    const float c = own ? (float)(r + 1) : 0.f;
+    const float num = (float)R * (part[0][d] + part[1][d]) + c * e_own * (own ? v[(int64_t)g * ldv + h * HD + d] : 0.f);
+    const float den = (float)R * sum + c * e_own;
+    out[((int64_t)g * R + r) * ldo + h * HD + d] = num / den;
+  }
+}
+
 template <bool RELPOS>
 void launch_attn(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* pos, int Tpos, int ldp,
                  const float* bias_u, const float* bias_v, float* out, int ldo, int B, int nQ, int q_offset, int T, int H, float scale,
@@ -290,6 +349,14 @@ void relpos_attention(const float* q, int ldq, const float* k, int ldk, const fl
   ++g_launches;
   if (B <= 0 || T <= 0 || nQ <= 0) return;
   launch_attn<true>(q, ldq, k, ldk, v, ldv, pos, Tpos, D, bias_u, bias_v, out, D, B, nQ, q_offset, T, H, 0.125f, chunk, 0, 0, lengths_dev, st);
+}
+
+void grouped_causal_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int S, int R,
+                              int H, float scale, const int* kv_len_dev, cudaStream_t st) {
+  ++g_launches;
+  if (S <= 0 || R <= 0) return;
+  launch_pdl(grouped_causal_attn_kernel, dim3(S, H), dim3(ATT_NT), (size_t)((S + 3) & ~3) * sizeof(float), st, q, ldq, k, ldk, v, ldv, out, ldo, S, R,
+             scale, kv_len_dev);
 }
 
 void mha_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int B,

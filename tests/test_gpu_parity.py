@@ -440,3 +440,34 @@ def test_missing_weight_fails_loudly():
     del sd["encoder.conformer_layers.1.ffn2.w_2.weight"]
     with pytest.raises(EngineError, match="ffn2.w_2.weight"):
         Engine(cfg, sd, None, None)
+
+
+def test_unit_decoder_grouped_first_layer(eng3, gold):
+    """Option unit_grouped: layer 1 of the unit decoder attends over the S distinct T2U rows with multiplicities instead of the
+    25*S identical copies (reference quirk N1 makes the copies identical).  Must reproduce the full computation: fixture
+    logits / arg-max, a long sequence, and the padded-tail variant."""
+    g = gold["decoders"]
+    feats = cuda(g["mt_feats"])
+    big = feats.repeat(7, 1).contiguous() * torch.linspace(0.8, 1.2, 7 * feats.shape[0], device="cuda").unsqueeze(1)  # 49 tokens -> 1225 positions
+    ref_small = eng3.t2u_unit_decode(feats, debug=True)
+    ref_big = eng3.t2u_unit_decode(big, debug=True)
+    ref_pad = eng3.t2u_unit_decode(cuda(g["mt_feats_pad"]), n_pad_tail=1, debug=True)
+    ref_small = {k: v.clone() for k, v in ref_small.items() if v is not None}
+    ref_big = {k: v.clone() for k, v in ref_big.items() if v is not None}
+    ref_pad = {k: v.clone() for k, v in ref_pad.items() if v is not None}
+    eng3.set_option("unit_grouped", 1)
+    try:
+        r = eng3.t2u_unit_decode(feats, debug=True)
+        d1 = maxdiff(r["logits"], ref_small["logits"])
+        d0 = maxdiff(r["logits"][:4], g["unit_logits_first"])
+        assert r["argmax"].tolist() == g["unit_argmax"].tolist()
+        rb = eng3.t2u_unit_decode(big, debug=True)
+        d2 = maxdiff(rb["logits"], ref_big["logits"])
+        assert rb["argmax"].tolist() == ref_big["argmax"].tolist()
+        rp = eng3.t2u_unit_decode(cuda(g["mt_feats_pad"]), n_pad_tail=1, debug=True)
+        d3 = maxdiff(rp["logits"], ref_pad["logits"])
+        assert rp["argmax"].tolist() == g["unit_argmax_pad"].tolist()
+    finally:
+        eng3.set_option("unit_grouped", 0)
+    report("unit_grouped", vs_full=d1, vs_fixture=d0, long_vs_full=d2, pad_vs_full=d3)
+    assert d1 < 5e-5 and d0 < 5e-4 and d2 < 1e-4 and d3 < 5e-5, (d1, d0, d2, d3)
