@@ -90,7 +90,7 @@ struct ss_engine {
   int umma_vocoder = 0;   // 0 = fp32 CUDA-core convs, 2 / 3 = tcgen05 with that many bf16 pieces per operand
   int umma_linear = 0;    // same for large-M linears (unit decoder, T2U, MT prefill, full-prefix encoder)
                           // 12 / 13: second-generation kernel (kernels_umma2.cu) with 2 / 3 pieces
-  int unit_grouped = 0;         // unit decoder layer 1: self-attention over the S distinct rows instead of the 25*S copies
+  int unit_grouped = 1;         // unit decoder layer 1: self-attention over the S distinct rows instead of the 25*S copies
   int umma_min_rows = 128;      // GEMMs with fewer rows stay on the fp32 CUDA-core kernels
   int umma_min_channels = 16;   // convs with fewer input channels stay on the fp32 CUDA-core kernel
   ss::Umma2Cache* umma2_cache = nullptr;  // packed bf16-split weights of kernels_umma2.cu

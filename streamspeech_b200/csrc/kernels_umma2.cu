@@ -483,7 +483,8 @@ __global__ void umma2_pack_kernel(const float* __restrict__ W, int N, int C_in, 
 }
 
 }  // namespace
-int g_umma2_split_below = 148;  // tile grids smaller than this are split over (chunk, tap) units (ss_set_option umma2_split_below)
+int g_umma2_split_below = 60;   // tile grids smaller than this are split over (chunk, tap) units (ss_set_option umma2_split_below;
+                                // measured: 60 beats 148 by 0.9 ms per utterance, the reduce launch costs more than the idle SMs)
 int g_umma2_min_units = 4;      // ... into slices of at least this many units
 unsigned long long* g_umma2_dbg = nullptr;  // device buffer of 16 stamps when the debug option is on
 namespace {

@@ -182,11 +182,11 @@ class Engine:
         self.set_option("persistent_encoder", int(os.environ.get("SS_PERSISTENT_ENCODER", "1")))
         self.set_option("persistent_mt", int(os.environ.get("SS_PERSISTENT_MT", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))
-        self.set_option("unit_grouped", int(os.environ.get("SS_UNIT_GROUPED", "0")))
+        self.set_option("unit_grouped", int(os.environ.get("SS_UNIT_GROUPED", "1")))
         self.set_option("vocoder_graph", int(os.environ.get("SS_VOCODER_GRAPH", "0")))
         self.set_option("graph_pdl", int(os.environ.get("SS_GRAPH_PDL", "0")))
         self.set_option("persistent_prefetch", int(os.environ.get("SS_PERSISTENT_PREFETCH", "0")))
-        self.set_option("umma2_split_below", int(os.environ.get("SS_UMMA2_SPLIT_BELOW", "148")))
+        self.set_option("umma2_split_below", int(os.environ.get("SS_UMMA2_SPLIT_BELOW", "60")))
         self.set_option("umma2_min_units", int(os.environ.get("SS_UMMA2_MIN_UNITS", "4")))
         self.set_option("persistent_barrier", int(os.environ.get("SS_PERSISTENT_BARRIER", "1")))
         self.hop = self.lib.ss_vocoder_hop(self._h)
