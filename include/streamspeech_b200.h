@@ -136,6 +136,12 @@ int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, cons
 int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, int S, int n_pad_tail, int mask_eos,
                        int64_t* argmax_dev, int64_t* units_dev, int32_t* count_dev, float* t2u_out_dev, float* logits_dev);
 
+/* Positional-embedding row (unit_dim floats, host memory) the CTC unit decoder adds to every upsampled T2U state.  The
+ * reference computes positions from x[:, :, 0] viewed as [bsz, seq] (ctc_transformer_unit_decoder.py:176-181), so
+ * every time step of batch element b gets the sinusoidal row pad + 1 + b.  The engine is created with the row of b = 0 (the
+ * streaming agents); the offline batched generator (streamspeech_b200/offline.py) sets the row of each sample before decoding
+ * it.  Synchronises the device. */
+int ss_unit_position_row(ss_engine* h, const float* row_host);
 /* ---- V1: CodeGenerator.forward front half (agent/tts/codehifigan.py:56-66): embedding + duration predictor.
  * codes_dev[U] int64 unit ids (0..num_embeddings-1); dur_out_dev[U] int64; cumsum_out_dev[U+1] int32 (frame offsets).
  * dur_prediction=0 -> every duration is 1.  The expanded frame sequence stays cached in the handle for ss_vocoder_generate. enqueue only */

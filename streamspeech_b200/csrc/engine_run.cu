@@ -652,6 +652,14 @@ int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, in
   return check_launch(h, "ss_t2u_unit_decode");
 }
 
+int ss_unit_position_row(ss_engine* h, const float* row_host) {
+  if (!h || !h->finalized || !row_host) return h ? h->fail(SS_ERR_STATE, "engine not finalized / null row") : SS_ERR_INVALID;
+  cudaDeviceSynchronize();  // earlier unit-decoder launches may still read the old row
+  if (cudaMemcpy(h->unit_pos_row, row_host, (size_t)h->cfg.unit_dim * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    return h->fail(SS_ERR_CUDA, "cudaMemcpy(unit positional row) failed");
+  return SS_OK;
+}
+
 int ss_vocoder_durations(ss_engine* h, void* stream, const int64_t* codes_dev, int U, int dur_prediction, int64_t* dur_out_dev,
                          int32_t* cumsum_out_dev) {
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;

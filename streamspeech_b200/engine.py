@@ -74,6 +74,7 @@ def load_library() -> ctypes.CDLL:
     lib.ss_mt_stable_rows.argtypes = [vp, i32]
     lib.ss_mt_features.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp]
     lib.ss_t2u_unit_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.ss_unit_position_row.argtypes = [vp, vp]
     lib.ss_vocoder_durations.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.ss_vocoder_generate.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.ss_vocoder_hop.argtypes = [vp]
@@ -93,7 +94,7 @@ def load_library() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_ctc_greedy_rows", "ss_mt_greedy",
-    "ss_mt_features", "ss_mt_stable_rows", "ss_t2u_unit_decode", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
+    "ss_mt_features", "ss_mt_stable_rows", "ss_t2u_unit_decode", "ss_unit_position_row", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
     "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count",
 ]
 
@@ -375,6 +376,12 @@ class Engine:
         host = r["packed"].cpu()
         n = int(host[:1].view(torch.int32)[0])
         return host[1:1 + n].tolist()
+
+    def set_unit_batch_index(self, b: int):
+        """Batch element b of the reference's unit decoder gets positional row pad + 1 + b at every time step.
+        b = 0 is what the streaming agents use (and what the engine is created with)."""
+        row = constants.sinusoidal_table(self.cfg.pad + 4 + int(b), self.cfg.unit_dim, self.cfg.pad)[self.cfg.pad + 1 + int(b)].contiguous().float()
+        self._check(self.lib.ss_unit_position_row(self._h, row.data_ptr()))
 
     def vocoder_durations(self, codes: torch.Tensor, dur_prediction: bool = True):
         assert codes.is_cuda and codes.dtype == torch.int64 and codes.is_contiguous()
