@@ -119,3 +119,56 @@ def test_mt_greedy_semantics():
     assert h2[: len(h) - 1] == h[:-1] and h2[-1] == cfg.eos and len(h2) <= len(h) - 1 + 3
     h0 = o.mt_greedy(eo, h[:-1], 0)  # no new tokens allowed: eos is forced immediately
     assert h0 == h[:-1] + [cfg.eos]
+
+
+def test_unit_decoder_first_layer_grouped_attention_identity(gold):
+    """What the engine's grouped first layer (kernels_attn.cu: grouped_causal_attn_kernel) relies on, checked on the oracle:
+    (1) quirk N1 gives every one of the 25 upsampled copies of a T2U state the same positional row, so the copies enter
+    layer 1 identical; (2) causal self-attention over such a sequence equals attention over the S distinct keys with
+    multiplicities 25 (earlier groups) and r + 1 (own group) -- including the padded-tail variant."""
+    import torch.nn.functional as F
+
+    from oracle.streamspeech_oracle import StreamSpeechOracle, _lin, _ln, make_positions, mha, sinusoidal_table
+    from streamspeech_b200 import synth as synth_
+    from streamspeech_b200.config import ModelConfig as MC
+
+    cfg = MC()
+    cfg.enc_layers = 3
+    sd = synth_.make_model_state_dict(cfg, 0)
+    o = StreamSpeechOracle(cfg, sd, None, synth_.make_gcmvn(cfg), chunk_size=8)
+    t2u = torch.from_numpy(gold["decoders"]["t2u_out"]).unsqueeze(1)  # [S, 1, 512]
+    S, R, H, E = t2u.shape[0], cfg.ctc_upsample_rate, cfg.unit_heads, cfg.unit_dim
+    x = t2u.unsqueeze(1).repeat(1, R, 1, 1).contiguous().view(S * R, 1, E)
+    table = sinusoidal_table(cfg.pad + 4, E, cfg.pad)
+    x = x + table.index_select(0, make_positions(x[:, :, 0], cfg.pad).view(-1)).view(S * R, 1, -1)
+    assert torch.equal(x.view(S, R, E), x.view(S, R, E)[:, :1].expand(S, R, E))  # (1)
+    p = "decoder.layers.0"
+    y = _ln(x, o.sd, p + ".self_attn_layer_norm")
+    L = S * R
+    causal = torch.triu(torch.ones(L, L, dtype=torch.bool), 1)
+    for n_valid in (S, S - 1):
+        pad = None
+        if n_valid < S:
+            pad = (torch.arange(S) >= n_valid).unsqueeze(0).unsqueeze(2).repeat(1, 1, R).view(1, L)
+        full = mha(o.sd, p + ".self_attn", y, y, H, causal, pad)
+        # grouped: S distinct rows, multiplicities
+        yg = y.view(S, R, E)[:, 0]
+        hd = E // H
+        q = (_lin(yg, o.sd, p + ".self_attn.q_proj") * hd ** -0.5).view(S, H, hd)
+        k = _lin(yg, o.sd, p + ".self_attn.k_proj").view(S, H, hd)
+        v = _lin(yg, o.sd, p + ".self_attn.v_proj").view(S, H, hd)
+        out = torch.zeros(S, R, H, hd)
+        for g in range(S):
+            n_prev, own = min(g, n_valid), g < n_valid
+            keys = list(range(n_prev)) + ([g] if own else [])
+            for h in range(H):
+                s = torch.stack([q[g, h] @ k[j, h] for j in keys])
+                e = torch.exp(s - s.max())
+                a = e[:n_prev].sum()
+                A = (e[:n_prev, None] * v[:n_prev, h]).sum(0) if n_prev else torch.zeros(hd)
+                for r in range(R):
+                    c = float(r + 1) if own else 0.0
+                    e_own = e[n_prev] if own else torch.tensor(0.0)
+                    out[g, r, h] = (R * A + c * e_own * (v[g, h] if own else 0)) / (R * a + c * e_own)
+        grouped = _lin(out.view(L, 1, E), o.sd, p + ".self_attn.out_proj")
+        assert float((grouped - full).abs().max()) < 2e-5, n_valid
