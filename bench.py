@@ -171,8 +171,8 @@ def gemm_rooflines(engine, peaks):
     w = torch.randn(C, C * k, device=engine.device) / (C * k) ** 0.5
     b = torch.zeros(C, device=engine.device)
     out = {}
-    for name, mode in (("gemm_kernel<128,64> fp32 CUDA cores", 0), ("umma_gemm_kernel tcgen05 bf16x3, im2col gather (v1)", 2),
-                       ("umma2_kernel tcgen05 bf16x3, tap-shift + cp.async.bulk weights (default path)", 12)):
+    for name, mode, mmas in (("gemm_kernel<128,64> fp32 CUDA cores", 0, 0), ("umma_gemm_kernel tcgen05 bf16x3, im2col gather (v1)", 2, 3),
+                             ("umma2_kernel tcgen05 bf16x3, tap-shift + cp.async.bulk weights (default path)", 12, 3)):
         fn = lambda: engine.op_conv1d(x, w, b, k, 1, k // 2, 0.1, mode)
         for _ in range(3):
             fn()
@@ -188,6 +188,9 @@ def gemm_rooflines(engine, peaks):
         peak = peaks.get("bf16_tflops", 1590.0)
         out[name] = {"bound": "tensor", "achieved_fp32_equivalent": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                      "us_per_launch": ms * 1e3, "shape": {"L": L, "C_in": C, "C_out": C, "k": k}}
+        if mmas:  # every fp32-grade product is `mmas` bf16 MMAs: the tensor pipe itself runs at mmas x the fp32-equivalent rate
+            out[name]["bf16_mmas_per_product"] = mmas
+            out[name]["tensor_pipe_frac"] = mmas * ach / peak
     return out
 
 
