@@ -87,6 +87,14 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """host cores this process may use (affinity mask when the platform has one)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     """CPU arm: the reference agent's semantics (full-prefix recompute every chunk) in PyTorch fp32 on the host cores."""
     import torch
@@ -100,6 +108,9 @@ def run_reference(args):
     from streamspeech_b200.config import ModelConfig
 
     torch.set_grad_enabled(False)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone (the other ranks have exited), so it
+    # takes every host core explicitly -- the thread count actually used is reported as `cores`
+    torch.set_num_threads(host_threads())
     cores = torch.get_num_threads()
     cfg = ModelConfig()
     o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), synth.make_vocoder_state_dict(cfg.vocoder, 1), synth.make_gcmvn(cfg))
@@ -224,18 +235,42 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    agent = StreamSpeechS2STAgent(agent_args(local, args.encoder_mode))
-    eng = agent.engine
+    a_args = agent_args(local, args.encoder_mode)
     if world > 1:
-        # the one collective of the path: initial weight broadcast over NVLink.  Every rank built the
-        # same seeded checkpoint; broadcasting rank 0's packed copy is what a real deployment does and costs ~0.3 s once.
+        # The one collective of the path: the initial weight broadcast over NVLink.  Rank 0 owns the
+        # checkpoint (model + vocoder, packed into one fp32 blob); the other ranks allocate the blob, receive it with NCCL and
+        # build their engine FROM THE RECEIVED BYTES (their own tensors are zero-filled before the broadcast).
         from streamspeech_b200.config import ModelConfig
 
-        sd = synth.make_model_state_dict(ModelConfig(), 0)
-        flat = torch.cat([v.flatten() for v in sd.values() if v.is_floating_point()]).cuda()
+        cfg0 = ModelConfig()
+        if rank == 0:
+            sd = synth.make_model_state_dict(cfg0, 0)
+            vsd = synth.make_vocoder_state_dict(cfg0.vocoder, 1)
+            meta = [[(k, tuple(v.shape)) for k, v in d.items() if v.is_floating_point()] for d in (sd, vsd)]
+        else:
+            sd, vsd, meta = None, None, None
+        box = [meta]
+        dist.broadcast_object_list(box, src=0)
+        meta = box[0]
+        total = sum(int(torch.Size(shp).numel()) for part in meta for _, shp in part)
+        flat = torch.zeros(total, dtype=torch.float32, device="cuda")
+        if rank == 0:
+            flat.copy_(torch.cat([d[k].float().flatten() for d, part in ((sd, meta[0]), (vsd, meta[1])) for k, _ in part]))
         dist.broadcast(flat, src=0)
         torch.cuda.synchronize()
-        del flat
+        host = flat.cpu()
+        parts, off = [], 0
+        for part in meta:
+            d = {}
+            for k, shp in part:
+                nel = int(torch.Size(shp).numel())
+                d[k] = host[off:off + nel].view(shp).clone()
+                off += nel
+            parts.append(d)
+        a_args.checkpoint_override = (cfg0, parts[0], parts[1], synth.make_gcmvn(cfg0))
+        del flat, host
+    agent = StreamSpeechS2STAgent(a_args)
+    eng = agent.engine
 
     n = SAMPLE_RATE * CHUNK_MS // 1000
     utts = [synth.make_audio(UTT_SECONDS, seed=1234 + 7 * rank + i) for i in range(2)]  # rank-specific utterances
@@ -334,7 +369,8 @@ def main():
         cfg = ModelConfig()
         o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), synth.make_vocoder_state_dict(cfg.vocoder, 1), synth.make_gcmvn(cfg))
         ag = OracleS2STAgent(o, CHUNK_MS)
-        secs = 4.0
+        torch.set_num_threads(host_threads())
+        secs = UTT_SECONDS  # the whole workload utterance: ~15-25 s of CPU work
         w = utts[0][: int(secs * SAMPLE_RATE)]
         t0 = time.perf_counter()
         for i in range(0, len(w), n):
@@ -342,7 +378,7 @@ def main():
             ag.policy()
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": secs / dt, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"first {secs:.0f} s of the same utterance, {CHUNK_MS} ms chunks, oracle agent (reference semantics: full-prefix recompute)"}
+                                "sample": f"one pass over the {secs:.0f} s workload utterance, {CHUNK_MS} ms chunks, oracle agent (reference semantics: full-prefix recompute), {torch.get_num_threads()} threads"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -12,7 +12,9 @@
  *    workspaces and per-stream caches only;
  *  - `stream` is a cudaStream_t (as void*).  Work is enqueued on it; functions documented as
  *    "enqueue only" never synchronise, the others synchronise that stream where stated;
- *  - one handle may be used from one host thread at a time; distinct handles are independent.
+ *  - one handle may be used from one host thread at a time; distinct handles share no device state (weights, caches,
+ *    workspaces, barrier counters are per handle).  Process-wide: the launch counter (ss_launch_count), the tuning options
+ *    "umma2_split_below" / "umma2_min_units" / "prefer_shared", and the per-device kernel attribute cache.
  */
 #ifndef STREAMSPEECH_B200_H_
 #define STREAMSPEECH_B200_H_
@@ -128,6 +130,20 @@ int ss_mt_stable_rows(ss_engine* h, int rows);
 int ss_mt_features(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* tokens_host, int n,
                    float* feats_out_dev, float* logits_last_dev);
 
+/* ---- M1 with the reference's incremental states (use_incremental_states=True: speech_to_text.s2tt.streamspeech.agent.py:136,178;
+ * SURVEY.md N12).  The decoder state lives in the handle ACROSS calls until ss_mt_incremental_reset (the agent's reset()):
+ *  - self-attention K / V of every token fed so far are kept; each call feeds only tokens it has not fed -- except that its first
+ *    step feeds the last prefix token again (fairseq slices prev_output_tokens[:, -1:], ctc_unity/modules/transformer_decoder.py:
+ *    305-308, and the previous call's final, eos-forcing step had already fed it), which leaves a duplicate cache entry per call;
+ *  - cross-attention K / V are projected only for encoder rows beyond those cached by earlier calls (transformer_layer.py:
+ *    492-505) and never refreshed, i.e. early rows keep the projections of the then-provisional encoder output.
+ * Both quirks change the hypothesis and are reproduced.  max_len_b = the caller's max_len for max_new_tokens == -1
+ * (min(int(max_len_a * src_len + max_len_b), max_decoder_positions - 1), sequence_generator.py:205-215).  Requires the
+ * persistent MT kernel (option persistent_mt = 1).  Synchronises `stream` once per burst. */
+int ss_mt_incremental_reset(ss_engine* h);
+int ss_mt_greedy_incremental(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* prefix_host, int n_prefix,
+                             int max_new_tokens, int max_len_b, int64_t* tokens_out_host, int max_out, int* n_out);
+
 /* ---- T1/U1/U2: synthesizer_encoder -> CTCTransformerUnitDecoder -> CTCSequenceGenerator.generate
  * (ctc_unity/modules/transformer_encoder.py:32-77, ctc_transformer_unit_decoder.py:53-260, agent/ctc_generator.py:41-123).
  * mt_feats_dev [S][mt_dim]; n_pad_tail = number of trailing <pad> positions of prev_output_tokens_mt (whole_word).
@@ -182,8 +198,15 @@ int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes);
 int ss_op_layer_norm(ss_engine* h, void* stream, const float* x_dev, int rows, int C, const float* g_dev, const float* b_dev,
                      float* out_dev);
 
-/* number of kernels this handle has launched since creation (bench.py reports it as gpu_launches) */
+/* number of kernels this library has launched in this process (bench.py reports the difference over the timed region as
+ * gpu_launches; the counter is process-wide, not per handle) */
 int64_t ss_launch_count(const ss_engine* h);
+/* The persistent cooperative kernels (encoder layer stack, MT decode steps) separate their phases with a counter-based grid
+ * barrier.  A barrier that times out (lost arrival, pre-empted CTA) raises a device flag instead of hanging or passing
+ * silently; this call synchronises the device, returns SS_ERR_CUDA if the flag was raised since the last check (results of
+ * the enqueue-only calls since then are invalid) and re-arms the barrier.  ss_mt_greedy performs the same check at its own
+ * synchronisation point. */
+int ss_async_error(ss_engine* h);
 
 #ifdef __cplusplus
 }

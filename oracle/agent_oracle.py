@@ -28,8 +28,11 @@ class OracleAction:
 
 class OracleS2STAgent:
     def __init__(self, oracle: StreamSpeechOracle, segment_ms: int = 320, lagging_k1: int = 0, stride_n: int = 1,
-                 dur_prediction: bool = True, max_len_b: int = 100):
+                 dur_prediction: bool = True, max_len_b: int = 100, is_word_start=None):
+        """is_word_start(token_id) -> bool: `generator_mt.tgt_dict[id].startswith("\u2581")` (agent:545-548), needed by the
+        whole-word path (segment >= 640 ms); pass the predicate of the dictionary in use."""
         self.o = oracle
+        self.is_word_start = is_word_start
         self.segment_ms = segment_ms
         self.lagging_k1 = lagging_k1
         self.stride_n = stride_n
@@ -92,9 +95,18 @@ class OracleS2STAgent:
         hyp = o.mt_greedy(eo, self.tgt_subwords_indices, new_subword_tokens, max_len_b=self.max_len_b)
         tgt = hyp[:-1] if hyp[-1] == c.eos else hyp
         finalized_tokens = hyp
-        if self.whole_word and not self.source_finished:
-            raise NotImplementedError("whole_word trimming needs the SPM dictionary strings (agent:540-574); "
-                                      "use the token-id predicate in streamspeech_b200.agent for synthetic dictionaries")
+        if self.whole_word:  # agent:540-574 (the incremental-state surgery there is dead: use_incremental_states=False, agent:179)
+            j = 999999
+            if not self.source_finished:
+                if self.is_word_start is None:
+                    raise ValueError("whole_word path needs is_word_start (dictionary predicate)")
+                for j in range(len(tgt) - 1, -1, -1):
+                    if self.is_word_start(tgt[j]):
+                        break
+                tgt = tgt[:j]
+                finalized_tokens = finalized_tokens[:j]
+                if j == 0:
+                    return OracleAction("read", trace=trace)
         max_tgt_len = len(finalized_tokens) + (1 if self.whole_word else 0)
         prev = [c.pad] * max_tgt_len
         prev[0] = c.eos
@@ -167,3 +179,78 @@ class OracleASRAgent:
         new = toks[self.emitted:]
         self.emitted = len(toks)
         return OracleAction("write", trace={"asr_tokens": toks, "new": new}, finished=self.source_finished)
+
+
+class OracleS2TTAgent:
+    """agent/speech_to_text.s2tt.streamspeech.agent.py:381-545: fbank -> encoder -> ASR / ST CTC -> policy gate -> MT decoder
+    WITH incremental states across policy() calls (generator_mt: use_incremental_states=True, max_len_a=1, max_len_b=200,
+    :161-179) -> text delta."""
+
+    def __init__(self, oracle: StreamSpeechOracle, segment_ms: int = 320, lagging_k1: int = 0, stride_n: int = 1, symbols=None,
+                 max_decoder_positions: int = 1200):
+        """symbols(token_id) -> dictionary string (generator_mt.tgt_dict[c])."""
+        self.o = oracle
+        self.lagging_k1, self.stride_n = lagging_k1, stride_n
+        self.symbols = symbols if symbols is not None else (lambda t: str(t))
+        self.max_decoder_positions = max_decoder_positions
+        ch = segment_ms // 40
+        oracle.set_chunk(ch, min(ch, 16))  # :359-366 (the ASR agent's rule, N8)
+        self.reset()
+
+    def reset(self):  # :300-321 (reset_incremental_states inside the try)
+        self.source: List[float] = []
+        self.source_finished = False
+        self.target_finished = False
+        self.tgt_subwords_indices: Optional[List[int]] = None
+        self.src_ctc_prefix_length = 0
+        self.tgt_ctc_prefix_length = 0
+        self.tgt_text = ""
+        self.state = self.o.mt_incremental_state()
+
+    def push(self, samples, finished: bool = False):
+        self.source.extend(samples)
+        self.source_finished = finished
+
+    def policy(self) -> OracleAction:
+        o, c = self.o, self.o.cfg
+        trace = {}
+        feature = online_features(torch.tensor(self.source, dtype=torch.float32), o.gcmvn)
+        if feature.size(0) == 0 and not self.source_finished:
+            return OracleAction("read", trace=trace)
+        enc = o.encoder(feature.unsqueeze(0), torch.tensor([feature.size(0)]))
+        eo = enc["encoder_out"][0]
+        asr = o.ctc_greedy("source_unigram", eo)[0]
+        st = o.ctc_greedy("ctc_target_unigram", eo)[0]
+        trace["asr_tokens"], trace["st_tokens"] = asr["tokens"], st["tokens"]
+        if not self.source_finished:  # :437-465
+            src_len, tgt_len = len(asr["tokens"]), len(st["tokens"])
+            if src_len < self.src_ctc_prefix_length + self.stride_n or tgt_len < self.tgt_ctc_prefix_length + self.stride_n:
+                return OracleAction("read", trace=trace)
+            self.src_ctc_prefix_length = max(src_len, self.src_ctc_prefix_length)
+            self.tgt_ctc_prefix_length = max(tgt_len, self.tgt_ctc_prefix_length)
+            subword_tokens = ((tgt_len - self.lagging_k1) // self.stride_n) * self.stride_n
+            new_subword_tokens = subword_tokens - len(self.tgt_subwords_indices) if self.tgt_subwords_indices is not None else subword_tokens
+            if new_subword_tokens < 1:
+                return OracleAction("read", trace=trace)
+        else:
+            new_subword_tokens = -1
+        new_subword_tokens = int(new_subword_tokens)
+        trace["new_subword_tokens"] = new_subword_tokens
+        # max_len for -1: min(int(max_len_a * src_len + max_len_b), self.max_len - 1) with max_len_a = 1, max_len_b = 200 and
+        # src_len = src_tokens.size(1) = number of fbank frames (sequence_generator.py:197-215)
+        max_len_full = min(int(1 * feature.size(0) + 200), self.max_decoder_positions - 1)
+        hyp = o.mt_greedy_incremental(self.state, eo, self.tgt_subwords_indices, new_subword_tokens, max_len_full)
+        tgt = hyp[:-1] if hyp[-1] == c.eos else hyp
+        trace["mt_tokens"] = list(tgt)
+        if self.tgt_subwords_indices is not None and self.tgt_subwords_indices == tgt:  # :519-529
+            if not self.source_finished:
+                return OracleAction("read", trace=trace)
+            return OracleAction("write", wav="", finished=True, trace=trace)
+        self.tgt_subwords_indices = tgt
+        text = " ".join(self.symbols(t) for t in tgt)  # :532-535
+        new_text = text[len(self.tgt_text):]
+        self.tgt_text = text
+        if self.source_finished and new_subword_tokens == -1:
+            self.target_finished = True
+            self.reset()
+        return OracleAction("write", wav=new_text, finished=self.target_finished, trace=trace)

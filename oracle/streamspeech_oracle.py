@@ -399,6 +399,86 @@ class StreamSpeechOracle:
             tokens.append(best)
         raise AssertionError("unreachable: eos is forced at step == max_len")
 
+    # ---- M1 with incremental states (use_incremental_states=True: S2TT / ASR agents)
+    def mt_incremental_state(self):
+        """fresh `incremental_states[0]` of SequenceGenerator (agent/sequence_generator.py:180-195): per layer the self-attention
+        prev_key / prev_value and the encoder-attention prev_key / prev_value."""
+        L = self.cfg.mt_layers
+        return {"self_k": [None] * L, "self_v": [None] * L, "cross_k": [None] * L, "cross_v": [None] * L}
+
+    def _mt_step_incremental(self, state, token: int, step: int, enc_out: torch.Tensor) -> torch.Tensor:
+        """One `decoder.forward(tokens[:, :step+1], encoder_out, incremental_state)` (transformer_decoder.py:257-403): only the
+        LAST token is embedded (:305-308) at sinusoidal position pad + 1 + step; self-attention appends its k / v to the saved
+        state (multihead_attention.py:599-640, no mask); encoder attention projects only encoder rows beyond the cached
+        prev_key length and concatenates (transformer_layer.py:492-505, static_kv otherwise).  Returns logits [vocab]."""
+        c = self.cfg
+        pfx = "target_unigram_decoder"
+        table = sinusoidal_table(max(1024, c.pad + 1 + step + 2), c.mt_dim, c.pad)
+        p = c.pad if token == c.pad else c.pad + 1 + step
+        x = math.sqrt(c.mt_dim) * self.sd[pfx + ".embed_tokens.weight"][token] + table[p]
+        x = x.view(1, 1, -1)
+        H, hd = c.mt_heads, c.mt_dim // c.mt_heads
+
+        def attend(q, k, v, prefix):
+            q = (q * hd ** -0.5).view(1, H, hd).transpose(0, 1)         # [H,1,hd]
+            kk = k.view(-1, H, hd).transpose(0, 1)                       # [H,n,hd]
+            vv = v.view(-1, H, hd).transpose(0, 1)
+            w = F.softmax(torch.bmm(q, kk.transpose(1, 2)), dim=-1, dtype=torch.float32)
+            a = torch.bmm(w, vv).transpose(0, 1).contiguous().view(1, 1, c.mt_dim)
+            return _lin(a, self.sd, prefix + ".out_proj")
+
+        for i in range(c.mt_layers):
+            lp = f"{pfx}.layers.{i}"
+            res = x
+            y = _ln(x, self.sd, lp + ".self_attn_layer_norm")
+            k = _lin(y, self.sd, lp + ".self_attn.k_proj").view(1, -1)
+            v = _lin(y, self.sd, lp + ".self_attn.v_proj").view(1, -1)
+            state["self_k"][i] = k if state["self_k"][i] is None else torch.cat([state["self_k"][i], k], 0)
+            state["self_v"][i] = v if state["self_v"][i] is None else torch.cat([state["self_v"][i], v], 0)
+            x = res + attend(_lin(y, self.sd, lp + ".self_attn.q_proj"), state["self_k"][i], state["self_v"][i], lp + ".self_attn")
+            res = x
+            y = _ln(x, self.sd, lp + ".encoder_attn_layer_norm")
+            have = 0 if state["cross_k"][i] is None else state["cross_k"][i].size(0)
+            if enc_out.size(0) > have:  # static_kv = False: only the new encoder rows are projected and appended
+                e = enc_out[have:, 0]
+                k = _lin(e, self.sd, lp + ".encoder_attn.k_proj")
+                v = _lin(e, self.sd, lp + ".encoder_attn.v_proj")
+                state["cross_k"][i] = k if have == 0 else torch.cat([state["cross_k"][i], k], 0)
+                state["cross_v"][i] = v if have == 0 else torch.cat([state["cross_v"][i], v], 0)
+            x = res + attend(_lin(y, self.sd, lp + ".encoder_attn.q_proj"), state["cross_k"][i], state["cross_v"][i], lp + ".encoder_attn")
+            res = x
+            y = _ln(x, self.sd, lp + ".final_layer_norm")
+            x = res + _lin(F.relu(_lin(y, self.sd, lp + ".fc1")), self.sd, lp + ".fc2")
+        x = _ln(x, self.sd, pfx + ".layer_norm")
+        return F.linear(x.view(-1), self.sd[pfx + ".output_projection.weight"])
+
+    def mt_greedy_incremental(self, state, enc_out: torch.Tensor, prefix: Optional[List[int]], max_new_tokens: int, max_len_full: int,
+                              min_len: int = 1) -> List[int]:
+        """generate_decoder (agent/sequence_generator.py:165-582) with use_incremental_states=True and beam 1: `state` persists
+        across calls; step `start` feeds tokens[start] = the last prefix token AGAIN (it was fed by the previous call's final
+        step), every step feeds exactly one token.  max_len_full = max_len when max_new_tokens == -1."""
+        c = self.cfg
+        prefix = list(prefix) if prefix is not None else []
+        start = len(prefix)
+        max_len = max_len_full if max_new_tokens == -1 else start + max_new_tokens
+        assert min_len <= max_len
+        tokens = [c.eos] + prefix
+        for step in range(start, max_len + 1):
+            logits = self._mt_step_incremental(state, tokens[step], step, enc_out)
+            lprobs = F.log_softmax(logits.float(), dim=-1)
+            lprobs[lprobs != lprobs] = NEG_INF
+            lprobs[c.pad] = NEG_INF
+            if step >= max_len:
+                lprobs[: c.eos] = NEG_INF
+                lprobs[c.eos + 1:] = NEG_INF
+            elif step < min_len:
+                lprobs[c.eos] = NEG_INF
+            best = int(torch.topk(lprobs, 2)[1][0])
+            if best == c.eos:
+                return tokens[1:] + [c.eos]
+            tokens.append(best)
+        raise AssertionError("unreachable: eos is forced at step == max_len")
+
     # ---- T1 UniTransformerEncoderNoEmb.forward (ctc_unity/modules/transformer_encoder.py:32-77)
     def t2u_encoder(self, x: torch.Tensor, pad_mask: Optional[torch.Tensor]) -> torch.Tensor:
         """x [S,B,512] -> [S,B,512]."""

@@ -3,7 +3,9 @@
   agent/speech_to_speech.streamspeech.agent.py   (StreamSpeechS2STAgent, :101-770)
   agent/speech_to_text.asr.streamspeech.agent.py (StreamSpeechASRAgent,  :100-433)
 
-but every tensor op of policy() runs in libstreamspeech_b200.so.  Host code keeps exactly the
+but every tensor op of policy() runs in libstreamspeech_b200.so.  The classes here carry no @entrypoint: SimulEval
+accepts exactly one registered system per `--agent` file (utils/agent.py:51-56), so each agent has its own thin file under
+streamspeech_b200/agents/ named like the reference's (`speech_to_speech.streamspeech.agent.py`, ...).  Host code keeps exactly the
 reference's control flow (READ/WRITE gate, prefix bookkeeping, wav tail slicing, the reset quirk).
 What differs on purpose, without changing results:
   * new source samples are appended to a device buffer instead of re-converting the whole python list;
@@ -15,16 +17,23 @@ from __future__ import annotations
 
 import json
 import os
+import sys
 from typing import List, Optional
 
 import numpy as np
 import torch
 
-from .config import ModelConfig, VocoderConfig
-from .dictionary import Dictionary
-from .engine import Engine, EngineError
-from .simuleval_compat import (ReadAction, SpeechSegment, SpeechToSpeechAgent, SpeechToTextAgent, WriteAction, entrypoint)
-from . import synth
+# Absolute imports with a path bootstrap: SimulEval loads `--agent FILE` as a top-level module named "agents"
+# (SimulEval/simuleval/utils/agent.py:25-28), where relative imports do not resolve.
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _REPO not in sys.path:
+    sys.path.insert(0, _REPO)
+
+from streamspeech_b200.config import ModelConfig, VocoderConfig  # noqa: E402
+from streamspeech_b200.dictionary import Dictionary  # noqa: E402
+from streamspeech_b200.engine import Engine, EngineError  # noqa: E402
+from streamspeech_b200.simuleval_compat import (ReadAction, SpeechSegment, SpeechToSpeechAgent, SpeechToTextAgent, WriteAction)  # noqa: E402
+from streamspeech_b200 import synth  # noqa: E402
 
 SHIFT_SIZE = 10
 WINDOW_SIZE = 25
@@ -104,10 +113,20 @@ class _EngineAgentMixin:
     def _init_engine(self, args, need_vocoder: bool):
         if args.sample_rate != SAMPLE_RATE:
             raise NotImplementedError("the B200 front-end takes 16 kHz input; resample upstream (SURVEY.md §8f.3)")
-        cfg, sd, gcmvn, dicts = load_streamspeech_checkpoint(args)
+        override = getattr(args, "checkpoint_override", None)  # (cfg, model state dict, vocoder state dict, gcmvn) already in memory
+        if override is not None:                                # (bench.py: the NCCL-broadcast copy of rank 0's checkpoint)
+            cfg, sd, vsd_o, gcmvn = override
+            dicts = {k: Dictionary.synthetic(n) for k, n in (("source_unigram", cfg.src_vocab), ("ctc_target_unigram", cfg.tgt_vocab),
+                                                             ("target_unigram", cfg.tgt_vocab))}
+            dicts["tgt"] = Dictionary.units(cfg.unit_vocab - 5)
+        else:
+            cfg, sd, gcmvn, dicts = load_streamspeech_checkpoint(args)
         vsd = None
         if need_vocoder:
-            cfg.vocoder, vsd = load_vocoder(args, cfg)
+            if override is not None:
+                vsd = vsd_o
+            else:
+                cfg.vocoder, vsd = load_vocoder(args, cfg)
         self.cfg = cfg
         self.dict = dicts
         dev = getattr(args, "device_index", 0)
@@ -189,7 +208,6 @@ class _EngineAgentMixin:
         return a, b
 
 
-@entrypoint
 class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
     """Drop-in for the reference class of the same name (agent:101-770)."""
 
@@ -325,7 +343,10 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
                 tokens = tokens[:j]
                 if j == 0:
                     return READ
-            n_pad_tail = 1
+            else:
+                # source finished: the hypothesis keeps its eos, max_tgt_len = len + 1 -> ONE trailing <pad> (agent:576-591).
+                # While reading, the hypothesis was cut to [:j] (no eos) and max_tgt_len = j + 1: no pad position.
+                n_pad_tail = 1
         prev_output_tokens_mt = [c.eos] + list(tokens) + [c.pad] * n_pad_tail  # agent:576-591
         tr["mt_tokens"] = list(tokens)
 
@@ -340,9 +361,9 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
         self.prev_output_tokens_mt = prev_output_tokens_mt
         # mt_decoder(prev_output_tokens_mt, features_only=True) (agent:638-642): already produced by the greedy pass
         # unless whole-word trimming changed the sequence
-        if self.whole_word:
+        if n_pad_tail:
             feats = eng.mt_features(enc, prev_output_tokens_mt, stable_rows=stable)
-        else:
+        else:  # causal decoder: the features of [eos, t1..tj] are the first j + 1 rows of the greedy pass
             feats = feats[: len(prev_output_tokens_mt)]
         # 2./3. T2U encoder + CTC unit decoder (agent:662-689)
         r = eng.t2u_unit_decode(feats.contiguous(), n_pad_tail=n_pad_tail)
@@ -386,7 +407,6 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
         return ("write", new_wav, self.states.source_finished, self.states.target_finished)
 
 
-@entrypoint
 class StreamSpeechASRAgent(_EngineAgentMixin, SpeechToTextAgent):
     """Drop-in for agent/speech_to_text.asr.streamspeech.agent.py: fbank -> encoder -> ASR CTC -> text delta."""
 
@@ -418,6 +438,87 @@ class StreamSpeechASRAgent(_EngineAgentMixin, SpeechToTextAgent):
         new_text = text[len(self.asr_text):]
         self.asr_text = text
         if self.states.source_finished:
+            self.states.target_finished = True
+            self.reset()
+        return WriteAction(new_text, finished=self.states.target_finished)
+
+
+class StreamSpeechS2TTAgent(_EngineAgentMixin, SpeechToTextAgent):
+    """Drop-in for agent/speech_to_text.s2tt.streamspeech.agent.py (StreamSpeechS2TTAgent, :101-545): fbank -> encoder ->
+    ASR / ST CTC -> policy gate -> MT decoder -> text delta.  The reference runs this agent's MT generator with incremental
+    states that live across policy() calls (:161-179); the engine keeps the same state in the handle
+    (ss_mt_greedy_incremental) and reproduces its two quirks (duplicate self-attention entry per call, cross-attention K / V of
+    early encoder rows never refreshed)."""
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.args = args
+        self._init_engine(args, need_vocoder=False)
+        self.lagging_k1 = args.lagging_k1
+        self.lagging_k2 = args.lagging_k2
+        self.segment_size = args.segment_size
+        self.stride_n = args.stride_n
+        self.unit_per_subword = args.unit_per_subword
+        self.stride_n2 = args.stride_n2
+        chunk_size = args.source_segment_size // 40
+        self.engine.set_chunk(chunk_size, min(chunk_size, 16))  # :359-366
+        self.max_decoder_positions = getattr(args, "max_decoder_positions", 1200)  # model.max_decoder_positions() (unit decoder)
+        self.trace = {}
+        self.reset()
+
+    add_args = StreamSpeechS2STAgent.add_args
+
+    def reset(self):  # :300-309
+        self.src_seg_num = 0
+        self.tgt_subwords_indices = None
+        self.src_ctc_indices = None
+        self.src_ctc_prefix_length = 0
+        self.tgt_ctc_prefix_length = 0
+        self.tgt_text = ""
+        self.states.reset()
+        self._reset_caches()
+        if hasattr(self, "engine"):
+            self.engine.mt_incremental_reset()
+
+    @torch.inference_mode()
+    def policy(self):
+        tr = self.trace = {}
+        feature = self._features()
+        if feature.size(0) == 0 and not self.states.source_finished:
+            return ReadAction()
+        enc = self._encode(feature)
+        (src_ctc_indices, _), (tgt_ctc_indices, _) = self._ctc_pair(enc)
+        tr["asr_tokens"], tr["st_tokens"] = src_ctc_indices, tgt_ctc_indices
+        if not self.states.source_finished:  # :437-465
+            src_ctc_prefix_length, tgt_ctc_prefix_length = len(src_ctc_indices), len(tgt_ctc_indices)
+            self.src_ctc_indices = src_ctc_indices
+            if (src_ctc_prefix_length < self.src_ctc_prefix_length + self.stride_n
+                    or tgt_ctc_prefix_length < self.tgt_ctc_prefix_length + self.stride_n):
+                return ReadAction()
+            self.src_ctc_prefix_length = max(src_ctc_prefix_length, self.src_ctc_prefix_length)
+            self.tgt_ctc_prefix_length = max(tgt_ctc_prefix_length, self.tgt_ctc_prefix_length)
+            subword_tokens = ((tgt_ctc_prefix_length - self.lagging_k1) // self.stride_n) * self.stride_n
+            new_subword_tokens = (subword_tokens - len(self.tgt_subwords_indices)) if self.tgt_subwords_indices is not None else subword_tokens
+            if new_subword_tokens < 1:
+                return ReadAction()
+        else:
+            self.src_ctc_indices = src_ctc_indices
+            new_subword_tokens = -1
+        new_subword_tokens = int(new_subword_tokens)
+        tr["new_subword_tokens"] = new_subword_tokens
+        # generator_mt: max_len_a = 1, max_len_b = 200 (:161-179); src_len = src_tokens.size(1) = fbank frames
+        max_len_full = min(int(feature.size(0) + 200), self.max_decoder_positions - 1)
+        tokens = self.engine.mt_greedy_incremental(enc, self.tgt_subwords_indices, new_subword_tokens, max_len_full)
+        tr["mt_tokens"] = list(tokens)
+        if self.tgt_subwords_indices is not None and self.tgt_subwords_indices == tokens:  # :519-529
+            if not self.states.source_finished:
+                return ReadAction()
+            return WriteAction("", finished=True)
+        self.tgt_subwords_indices = tokens
+        text = " ".join(self.dict["target_unigram"][t] for t in tokens)  # :532-535
+        new_text = text[len(self.tgt_text):]
+        self.tgt_text = text
+        if self.states.source_finished and new_subword_tokens == -1:
             self.states.target_finished = True
             self.reset()
         return WriteAction(new_text, finished=self.states.target_finished)

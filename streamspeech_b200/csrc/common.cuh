@@ -4,7 +4,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <set>
 #include <unordered_set>
+#include <utility>
 
 namespace ss {
 
@@ -23,10 +26,33 @@ extern thread_local int g_pdl_off;
 // -- which is what the vocoder's three concurrent streams of alternating conv / reduce kernels would do.  With the option on
 // (default) every kernel of the library asks for the maximum shared-memory carve-out, once per kernel function.
 extern int g_prefer_shared;
+
+// Function attributes (cudaFuncSetAttribute) belong to the CURRENT DEVICE: a process that holds handles on several devices
+// must configure every kernel once per device, not once per process.  true the first time (device, key) is seen.
+inline bool first_time_on_device(const void* key) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  return seen.insert({dev, key}).second;
+}
+// SM count of the current device (cached per device)
+inline int current_device_sms() {
+  static std::mutex mu;
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  if (dev < 0 || dev >= 64) return 0;
+  if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
 inline void prefer_shared_once(const void* fn) {
   if (!g_prefer_shared) return;
-  static thread_local std::unordered_set<const void*> done;
-  if (done.insert(fn).second) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  // (key fn + 1: a key space distinct from the max-shared-memory configuration of the same function)
+  if (first_time_on_device((const char*)fn + 1)) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
 // launch with programmatic stream serialization: the grid may be scheduled while its predecessor is still running; every

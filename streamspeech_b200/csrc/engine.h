@@ -153,6 +153,10 @@ struct ss_engine {
   int mt_cross_final = 0;            // rows of mt_cross_kv that were projected from final encoder rows (ss_mt_stable_rows)
   int mt_stable_hint = 0;            // hint for the next MT call, consumed by it
   const float* mt_cross_enc = nullptr;  // encoder buffer those rows came from
+  // incremental-state decoding across calls (ss_mt_greedy_incremental: the S2TT / ASR agents' use_incremental_states=True)
+  int mt_inc_self_len = 0;           // entries in the self-attention cache (can exceed the hypothesis length: call boundaries
+                                     // feed the last prefix token again, speech_to_text.s2tt agent + sequence_generator.py:338-346)
+  int mt_inc_cross_rows = 0;         // encoder rows whose cross K / V were appended (never refreshed, transformer_layer.py:492-505)
   int64_t* mt_tok_dev = nullptr;  // [max_pos]
   int64_t* mt_next_dev = nullptr;
   int64_t* mt_next_pinned = nullptr;
@@ -175,6 +179,7 @@ struct ss_engine {
   int persistent_alias = 0;
   unsigned* persist_bar = nullptr;   // arrival counter of the kernel's own grid barrier (option persistent_barrier)
   unsigned persist_bar_target = 0;
+  unsigned* async_err_pinned = nullptr;  // host copy of persist_bar[SS_BAR_ERR_WORD] (read back at synchronisation points)
   int persistent_barrier = 1;        // 0: cooperative-groups grid.sync(), 1: own counter barrier (1.6 us cheaper per barrier)
   ss::MtLayerP* mt_persist_layers = nullptr;   // [mt_layers] device pointer table for kernels_persist_mt.cu
   int persistent_mt = 1;                       // single-token MT decode steps as one cooperative kernel per burst

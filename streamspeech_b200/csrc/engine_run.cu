@@ -111,6 +111,17 @@ Epilogue ep_residual(float* inout, int ldo, float alpha = 1.0f) {  // inout = in
   return e;
 }
 
+// A persistent kernel whose grid barrier timed out raised persist_bar[SS_BAR_ERR_WORD].  `flag` = its host copy (taken after a
+// synchronisation).  Re-arms the barrier (counter and host target back in step) and reports the failure.
+int report_async_error(ss_engine* h, unsigned flag, const char* where) {
+  if (!flag) return SS_OK;
+  cudaDeviceSynchronize();
+  if (h->persist_bar) cudaMemset(h->persist_bar, 0, 64 * sizeof(unsigned));
+  h->persist_bar_target = 0;
+  return h->fail(SS_ERR_CUDA, std::string(where) + ": a grid barrier of a persistent kernel timed out; the results of the calls since the "
+                                                   "last check are invalid (barrier re-armed)");
+}
+
 void clear_graphs(ss_engine* h) {
   cudaDeviceSynchronize();
   for (auto& kv : h->voc_graphs) cudaGraphExecDestroy(kv.second.first);
@@ -219,6 +230,15 @@ extern "C" {
 
 int64_t ss_launch_count(const ss_engine*) { return (int64_t)ss::g_launches; }
 
+int ss_async_error(ss_engine* h) {
+  if (!h) return SS_ERR_INVALID;
+  if (!h->persist_bar) return SS_OK;
+  unsigned f = 0;
+  if (cudaMemcpy(&f, h->persist_bar + SS_BAR_ERR_WORD, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return h->fail(SS_ERR_CUDA, std::string("ss_async_error: ") + cudaGetErrorString(cudaGetLastError()));
+  return report_async_error(h, f, "ss_async_error");
+}
+
 int64_t ss_fbank_num_frames(int64_t n) {
   if (n < 240) return 0;
   int64_t f = (n - 240) / 160;
@@ -278,11 +298,14 @@ int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const
     if (!all_full) {
       if (B > h->lengths_cap) {
         if (h->lengths_dev) cudaFree(h->lengths_dev);
-        cudaMalloc((void**)&h->lengths_dev, (size_t)B * 2 * sizeof(int));
+        h->lengths_dev = nullptr;
+        h->lengths_cap = 0;
+        if (cudaMalloc((void**)&h->lengths_dev, (size_t)B * 2 * sizeof(int)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc(lengths) failed");
         h->lengths_cap = B * 2;
       }
-      cudaMemcpyAsync(h->lengths_dev, lens.data(), B * sizeof(int), cudaMemcpyHostToDevice, st);
-      cudaStreamSynchronize(st);  // `lens` is a stack vector
+      if (cudaMemcpyAsync(h->lengths_dev, lens.data(), B * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)  // `lens` is a stack vector
+        return h->fail(SS_ERR_CUDA, "copy of src_lengths failed");
       len_dev = h->lengths_dev;
     }
   }
@@ -361,7 +384,15 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
   }
   const int T1 = (F - 1) / 2 + 1, T = (T1 - 1) / 2 + 1;
   if (T > h->Tpos) return h->fail(SS_ERR_CAPACITY, "encoder sequence longer than max_enc_frames");
-  const int G = std::max(h->attn_chunk, h->conv_chunk);  // rows of a group are final once 4*G*(i+1) fbank frames exist
+  // Rows of a group [iG, (i+1)G) are final once 4*G*(i+1) fbank frames exist, where G must be a common multiple of the
+  // attention chunk and the conv chunk (every chunk grid has a boundary at the group's end): G = lcm.  For nested settings
+  // (4/8, 8/8, 16/16) that is the larger one; for 12/8, 24/16, 40/16 ... it is not.
+  int G;
+  {
+    int a = h->attn_chunk, b = h->conv_chunk;
+    while (b) { int t = a % b; a = b; b = t; }
+    G = h->attn_chunk / a * h->conv_chunk;
+  }
   const int a0 = std::min(h->st_T_final, T);
   const int nA = T - a0;
   if (T_out) *T_out = T;
@@ -585,8 +616,15 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
     int produced = step - burst_first - (done ? 1 : 0);
     if (produced > 0) {
       cudaMemcpyAsync(h->mt_next_pinned, h->mt_tok_dev + burst_first + 1, produced * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+      if (h->persist_bar && h->async_err_pinned)
+        cudaMemcpyAsync(h->async_err_pinned, h->persist_bar + SS_BAR_ERR_WORD, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
       if (cudaStreamSynchronize(st) != cudaSuccess)
         return h->fail(SS_ERR_CUDA, std::string("ss_mt_greedy: ") + cudaGetErrorString(cudaGetLastError()));
+      if (h->async_err_pinned && *h->async_err_pinned) {
+        const unsigned f = *h->async_err_pinned;
+        *h->async_err_pinned = 0;
+        return report_async_error(h, f, "ss_mt_greedy");
+      }
       for (int i = 0; i < produced; ++i) {
         int64_t next = h->mt_next_pinned[i];
         if (next == c.eos) {
@@ -600,6 +638,102 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
   }
   *n_out = n_tok;
   return check_launch(h, "ss_mt_greedy");
+}
+
+int ss_mt_incremental_reset(ss_engine* h) {
+  if (!h) return SS_ERR_INVALID;
+  h->mt_inc_self_len = 0;
+  h->mt_inc_cross_rows = 0;
+  return SS_OK;
+}
+
+int ss_mt_greedy_incremental(ss_engine* h, void* stream, const float* enc_dev, int T, const int64_t* prefix_host, int n_prefix,
+                             int max_new_tokens, int max_len_b, int64_t* tokens_out_host, int max_out, int* n_out) {
+  if (h) route_from(h);
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  const ss_config& c = h->cfg;
+  cudaStream_t st = S(stream);
+  if (T <= 0 || n_prefix < 0 || !n_out) return h->fail(SS_ERR_INVALID, "bad arguments to ss_mt_greedy_incremental");
+  const int start = n_prefix;
+  const int max_len = (max_new_tokens == -1) ? max_len_b : start + max_new_tokens;
+  if (max_len < 1) return h->fail(SS_ERR_INVALID, "min_len cannot be larger than max_len");
+  if (start > max_len) return h->fail(SS_ERR_INVALID, "prefix longer than max_len");
+  // slot of the token at position s = s + kv_off; the first call starts with an empty cache (kv_off = 0), every later call
+  // re-feeds the last prefix token on top of the entry the previous call's final step left (kv_off grows by one per call)
+  const int kv_off = h->mt_inc_self_len - start;
+  if (kv_off < 0) return h->fail(SS_ERR_STATE, "incremental MT state is shorter than the prefix (reset missing, or a prefix that this state did not produce)");
+  if (max_len + kv_off + 2 > c.max_mt_positions || max_len > max_out) return h->fail(SS_ERR_CAPACITY, "MT hypothesis longer than capacity");
+  if (!h->persistent_mt || !h->persist_bar || !mt_decode_persistent_supported(c.mt_dim, c.mt_ffn, c.mt_heads, c.tgt_vocab, c.max_mt_positions, std::max(T, h->mt_inc_cross_rows)))
+    return h->fail(SS_ERR_STATE, "incremental MT decoding runs on the persistent MT kernel, which is off or does not support this shape");
+  int rc = ensure_mt_cross(h, std::max(T, h->mt_inc_cross_rows));
+  if (rc) return rc;
+  if (h->mt_cross_cap < std::max(T, h->mt_inc_cross_rows)) return h->fail(SS_ERR_CAPACITY, "cross-attention cache too small");
+  const int dim = c.mt_dim;
+  if (!ws_begin(h, ((size_t)(dim * 8 + c.mt_ffn) + c.tgt_vocab + (size_t)c.max_mt_positions * dim + 4096) * sizeof(float))) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+  DecScratch s = dec_scratch(h, 1, dim, c.mt_ffn);
+  float* x = h->ws.f32(dim);
+  float* logits = h->ws.f32(c.tgt_vocab);
+  float* feats = h->ws.f32((size_t)c.max_mt_positions * dim);
+  if (!x || !logits || !feats) return h->fail(SS_ERR_CUDA, "workspace too small");
+  // cross K / V: only the encoder rows that were not there at the previous call are projected and appended; older rows keep
+  // the projections of the (then provisional) encoder output of the call that first saw them (N12)
+  if (h->mt_inc_cross_rows == 0) {  // a fresh state must not inherit rows of an earlier utterance
+    h->mt_cross_final = 0;
+    h->mt_cross_enc = nullptr;
+  }
+  if (T > h->mt_inc_cross_rows) {
+    const int from = h->mt_inc_cross_rows;
+    for (int l = 0; l < c.mt_layers; ++l) {
+      float* cross = h->mt_cross_kv + (size_t)l * h->mt_cross_cap * 2 * dim;
+      linear(enc_dev + (size_t)from * c.enc_dim, c.enc_dim, T - from, h->mt[l].ckv, ep_out(cross + (size_t)from * 2 * dim, 2 * dim), st);
+    }
+    h->mt_inc_cross_rows = T;
+  }
+  const int Tk = h->mt_inc_cross_rows;
+  std::vector<int64_t> toks(start + 1);
+  toks[0] = c.eos;
+  for (int i = 0; i < start; ++i) toks[i + 1] = prefix_host[i];
+  cudaMemcpyAsync(h->mt_tok_dev, toks.data(), toks.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  int n_tok = start;
+  for (int i = 0; i < start; ++i) tokens_out_host[i] = prefix_host[i];
+  const int burst = (max_new_tokens >= 0) ? std::max(1, max_new_tokens + 1) : 32;
+  int step = start;
+  bool done = false;
+  while (!done) {
+    const int cnt = std::min(max_len - step + 1, burst);
+    MtDecodeParams P;
+    P.n_layers = c.mt_layers; P.heads = c.mt_heads; P.vocab = c.tgt_vocab; P.pad = c.pad; P.eos = c.eos;
+    P.max_pos = c.max_mt_positions; P.cross_cap = h->mt_cross_cap; P.kv_off = kv_off;
+    P.emb = h->mt_emb; P.pos = h->mt_pos; P.out_g = h->mt_ln.g; P.out_b = h->mt_ln.b;
+    P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
+    P.tok = h->mt_tok_dev; P.feats = feats; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
+    if (mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, Tk, h->persist_bar, &h->persist_bar_target, st) != 0) {
+      cudaGetLastError();
+      return h->fail(SS_ERR_CUDA, "cooperative launch of the persistent MT kernel was refused");
+    }
+    const int readable = std::min(cnt, max_len - step);  // the forced-eos step writes no token
+    if (readable > 0) cudaMemcpyAsync(h->mt_next_pinned, h->mt_tok_dev + step + 1, readable * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (h->async_err_pinned) cudaMemcpyAsync(h->async_err_pinned, h->persist_bar + SS_BAR_ERR_WORD, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return h->fail(SS_ERR_CUDA, std::string("ss_mt_greedy_incremental: ") + cudaGetErrorString(cudaGetLastError()));
+    if (h->async_err_pinned && *h->async_err_pinned) {
+      const unsigned f = *h->async_err_pinned;
+      *h->async_err_pinned = 0;
+      return report_async_error(h, f, "ss_mt_greedy_incremental");
+    }
+    for (int i = 0; i < cnt && !done; ++i) {
+      const int sidx = step + i;            // this step fed the token at position sidx (one more cache entry)
+      h->mt_inc_self_len = sidx + kv_off + 1;
+      if (sidx >= max_len) { done = true; break; }   // eos forced (sequence_generator.py:362-364)
+      const int64_t next = h->mt_next_pinned[i];
+      if (next == c.eos) { done = true; break; }
+      tokens_out_host[n_tok++] = next;
+    }
+    step += cnt;
+    if (step > max_len) done = true;
+  }
+  *n_out = n_tok;
+  return check_launch(h, "ss_mt_greedy_incremental");
 }
 
 int ss_t2u_unit_decode(ss_engine* h, void* stream, const float* mt_feats_dev, int Slen, int n_pad_tail, int mask_eos, int64_t* argmax_dev,
@@ -671,9 +805,14 @@ int ss_vocoder_durations(ss_engine* h, void* stream, const int64_t* codes_dev, i
   if (U > h->voc_ucap) {
     if (h->voc_unit_emb) cudaFree(h->voc_unit_emb);
     if (h->voc_cumsum) cudaFree(h->voc_cumsum);
-    h->voc_ucap = std::max(2 * U, 1024);
-    cudaMalloc((void**)&h->voc_unit_emb, (size_t)h->voc_ucap * E * sizeof(float));
-    cudaMalloc((void**)&h->voc_cumsum, (size_t)(h->voc_ucap + 1) * sizeof(int));
+    h->voc_unit_emb = nullptr;
+    h->voc_cumsum = nullptr;
+    h->voc_ucap = 0;
+    const int cap = std::max(2 * U, 1024);
+    if (cudaMalloc((void**)&h->voc_unit_emb, (size_t)cap * E * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void**)&h->voc_cumsum, (size_t)(cap + 1) * sizeof(int)) != cudaSuccess)
+      return h->fail(SS_ERR_CUDA, "cudaMalloc(vocoder unit cache) failed");
+    h->voc_ucap = cap;
   }
   h->voc_U = U;
   if (!ws_begin(h, ((size_t)U * (2 * Hd + 2) + 4096) * sizeof(float))) return h->fail(SS_ERR_CUDA, "workspace allocation failed");

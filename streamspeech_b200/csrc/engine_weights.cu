@@ -275,6 +275,8 @@ void finalize_impl(ss_engine* h) {
     h->persist_bar = dev_alloc<unsigned>(h, 64);
     cudaMemset(h->persist_bar, 0, 64 * sizeof(unsigned));
     h->persist_bar_target = 0;
+    if (!h->async_err_pinned && cudaHostAlloc((void**)&h->async_err_pinned, sizeof(unsigned), cudaHostAllocDefault) == cudaSuccess)
+      *h->async_err_pinned = 0;
   }
   // ---- CTC heads
   h->ctc_head[0] = make_linear(h, "source_unigram_decoder.proj", c.src_vocab, D);
@@ -453,6 +455,7 @@ int ss_destroy(ss_engine* h) {
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->mt_cross_kv) cudaFree(h->mt_cross_kv);
   if (h->mt_next_pinned) cudaFreeHost(h->mt_next_pinned);
+  if (h->async_err_pinned) cudaFreeHost(h->async_err_pinned);
   if (h->voc_unit_emb) cudaFree(h->voc_unit_emb);
   if (h->voc_cumsum) cudaFree(h->voc_cumsum);
   if (h->lengths_dev) cudaFree(h->lengths_dev);

@@ -322,21 +322,15 @@ void launch_attn(const float* q, int ldq, const float* k, int ldk, const float* 
   const long tiles = (long)((nQ + QT - 1) / QT) * H * B;
   if (tiles < 96 && (size_t)T * sizeof(float) <= 160 * 1024) {
     size_t smem_row = (size_t)((T + 3) & ~3) * sizeof(float);
-    static size_t configured_row = 0;
-    if (smem_row > 40 * 1024 && smem_row > configured_row) {
+    if (smem_row > 40 * 1024 && first_time_on_device((const void*)attn_row_kernel<RELPOS>))
       cudaFuncSetAttribute(attn_row_kernel<RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      configured_row = 160 * 1024;
-    }
     launch_pdl(attn_row_kernel<RELPOS>, dim3(dim3(nQ, H, B)), dim3(ATT_NT), smem_row, st, q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo, nQ,
                                                                       q_offset, T, scale, chunk, causal, causal_offset, lengths);
     return;
   }
   size_t smem = (size_t)((RELPOS ? 2 : 1) * QT * LDK + 2 * KT * LDK + (RELPOS ? (KT + QT - 1) * LDK : 0) + QT * (KT + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  if (first_time_on_device((const void*)attn_tile_kernel<RELPOS>))
     cudaFuncSetAttribute(attn_tile_kernel<RELPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
   launch_pdl(attn_tile_kernel<RELPOS>, dim3(dim3((nQ + QT - 1) / QT, H, B)), dim3(ATT_NT), smem, st, q, ldq, k, ldk, v, ldv, pos, Tpos, ldp, bias_u, bias_v, out, ldo,
                                                                                  nQ, q_offset, T, scale, chunk, causal, causal_offset, lengths);
 }

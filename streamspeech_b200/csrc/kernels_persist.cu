@@ -52,7 +52,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     unsigned v, spins = 0;
     do {  // (bounded: a counter out of step with the host's target must not hang the device)
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while ((int)(v - target) < 0 && ++spins < (1u << 18));
+    } while ((int)(v - target) < 0 && ++spins < (1u << 20));
+    // A counter that never reaches the target (lost arrival, counter out of step with the host's target) must neither hang
+    // the device nor pass silently: the word ctr[SS_BAR_ERR_WORD] is raised and the host reports it at its next
+    // synchronisation point (ss_async_error / ss_mt_greedy), after which results of this launch are invalid.
+    if ((int)(v - target) < 0) atomicExch(ctr + SS_BAR_ERR_WORD, 1u);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
@@ -612,15 +616,13 @@ int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, floa
   (void)D;
   (void)FFN;
   auto kernel = encoder_layers_persistent_kernel<2048>;
-  static int grid = 0;
-  if (grid == 0) {
-    int dev = 0, sms = 0, occ = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int occ = 0;
+  if (first_time_on_device((const void*)kernel)) {  // cooperative launch needs one resident CTA per SM on this device
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PT, 0);
     if (occ < 1) return -1;
-    grid = sms;
   }
+  const int grid = current_device_sms();
+  if (grid <= 0) return -1;
   unsigned bar_target = bar_target_host ? *bar_target_host : 0u;
   void* args[] = {(void*)&layers_dev, (void*)&n_layers, (void*)&x, (void*)&hid, (void*)&qb, (void*)&att, (void*)&dw, (void*)&kc, (void*)&vc,
                   (void*)&gc, (void*)&nA, (void*)&a0, (void*)&T, (void*)&H, (void*)&Tpos, (void*)&chunk, (void*)&conv_chunk, (void*)&dw_k,

@@ -5,6 +5,9 @@
 
 namespace ss {
 
+// word of the barrier buffer (unsigned[64]: [0] = arrival counter) that a timed-out grid barrier raises
+#define SS_BAR_ERR_WORD 32
+
 struct PersistLayer {  // device pointers of one Conformer layer (fp32, layouts as in engine.h ConformerLayerW)
   const float *ffn1_g, *ffn1_b, *ffn1_w1, *ffn1_b1, *ffn1_w2, *ffn1_b2;
   const float *attn_g, *attn_b, *wqkv, *bqkv, *wo, *bo, *pos_u, *pos_v, *pos_proj;
@@ -28,6 +31,8 @@ struct MtLayerP {  // device pointers of one pre-LN decoder layer (fp32, [N][K] 
 };
 struct MtDecodeParams {
   int n_layers, heads, vocab, pad, eos, max_pos, cross_cap;
+  int kv_off = 0;                           // self-attention cache slot of the token at position s is s + kv_off (> 0 only in the
+                                            // reference's incremental-state mode, where call boundaries duplicate an entry)
   const float *emb, *pos, *out_g, *out_b;   // tied embedding / output projection [vocab][dim], sinusoidal table, final LN
   float *self_k, *self_v;                   // [layers][max_pos][dim]
   const float* cross_kv;                    // [layers][cross_cap][2 * dim] (K | V per row)

@@ -36,7 +36,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     unsigned v, spins = 0;
     do {
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while ((int)(v - target) < 0 && ++spins < (1u << 18));
+    } while ((int)(v - target) < 0 && ++spins < (1u << 20));
+    // A counter that never reaches the target (lost arrival, counter out of step with the host's target) must neither hang
+    // the device nor pass silently: the word ctr[SS_BAR_ERR_WORD] is raised and the host reports it at its next
+    // synchronisation point (ss_async_error / ss_mt_greedy), after which results of this launch are invalid.
+    if ((int)(v - target) < 0) atomicExch(ctr + SS_BAR_ERR_WORD, 1u);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
@@ -203,8 +207,8 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel(MtDecodePa
     }
     for (int l = 0; l < P.n_layers; ++l) {
       const MtLayerP L = layers[l];
-      float* kc = P.self_k + ((size_t)l * P.max_pos + s) * DIM;
-      float* vc = P.self_v + ((size_t)l * P.max_pos + s) * DIM;
+      float* kc = P.self_k + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
+      float* vc = P.self_v + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
       // (1) q | k | v = LN(x) Wqkv^T
       GemvW<DIM, 2> w_qkv;
       gemv_issue(w_qkv, L.wqkv, 3 * DIM);
@@ -217,11 +221,11 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel(MtDecodePa
         else vc[col - 2 * DIM] = y;
       });
       BAR();
-      // (2) causal self-attention over rows 0..s of the cache
+      // (2) causal self-attention over rows 0..s (+ kv_off) of the cache
       if (blockIdx.x < P.heads) {
         const int h = blockIdx.x;
         attend_head(sm, P.q + h * MHD, P.self_k + (size_t)l * P.max_pos * DIM + h * MHD, P.self_v + (size_t)l * P.max_pos * DIM + h * MHD, DIM,
-                    s + 1, P.attn + h * MHD);
+                    s + P.kv_off + 1, P.attn + h * MHD);
       }
       BAR();
       // (3) x += attn Wo^T
@@ -342,15 +346,13 @@ bool mt_decode_persistent_supported(int dim, int ffn, int heads, int vocab, int 
 int mt_decode_persistent(const MtDecodeParams& P, const MtLayerP* layers_dev, int step0, int nsteps, int max_len, int T, unsigned* bar_ctr,
                          unsigned* bar_target_host, cudaStream_t st) {
   ++g_launches;
-  static int grid = 0;
-  if (grid == 0) {
-    int dev = 0, sms = 0, occ = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int occ = 0;
+  if (first_time_on_device((const void*)mt_decode_persistent_kernel)) {  // cooperative launch needs one resident CTA per SM on this device
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mt_decode_persistent_kernel, MTT, 0);
     if (occ < 1) return -1;
-    grid = sms;
   }
+  const int grid = current_device_sms();
+  if (grid <= 0) return -1;
   if (grid < 128 || P.vocab > 6 * MW * grid) return -1;  // one round of columns per GEMV phase (see gemv_issue)
   MtDecodeParams p = P;
   unsigned bar_target = *bar_target_host;

@@ -325,11 +325,8 @@ template <int BN, int NP>
 void launch_umma(const ConvA& a, const float* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
   constexpr int STAGE = NP * (UM_BM * UM_BK * 2 + BN * UM_BK * 2);
   const size_t smem = 2 * STAGE + 1024;
-  static bool configured = false;
-  if (!configured) {
+  if (first_time_on_device((const void*)umma_gemm_kernel<BN, NP>))
     cudaFuncSetAttribute(umma_gemm_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
   dim3 grid((N + BN - 1) / BN, (M + UM_BM - 1) / UM_BM);
   const long ctas = (long)grid.x * grid.y;
   const int nk = (K + UM_BK - 1) / UM_BK;

@@ -493,12 +493,9 @@ int u2_bn(int N) { return N >= 128 ? 128 : N > 32 ? 64 : N > 16 ? 32 : 16; }
 
 template <int BN, int NP, int UPT, int SETS>
 void u2_launch_v(const U2Params& p, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  if (first_time_on_device((const void*)umma2_kernel<BN, NP, UPT, SETS>))
     cudaFuncSetAttribute(umma2_kernel<BN, NP, UPT, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    prefer_shared_once((const void*)umma2_kernel<BN, NP, UPT, SETS>);
-    configured = true;
-  }
+  prefer_shared_once((const void*)umma2_kernel<BN, NP, UPT, SETS>);
   umma2_kernel<BN, NP, UPT, SETS><<<grid, U2_THREADS, smem, st>>>(p);
 }
 

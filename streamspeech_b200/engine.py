@@ -72,6 +72,8 @@ def load_library() -> ctypes.CDLL:
     lib.ss_ctc_greedy_rows.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
     lib.ss_mt_greedy.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, i32, ctypes.POINTER(i32), vp]
     lib.ss_mt_stable_rows.argtypes = [vp, i32]
+    lib.ss_mt_incremental_reset.argtypes = [vp]
+    lib.ss_mt_greedy_incremental.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, i32, ctypes.POINTER(i32)]
     lib.ss_mt_features.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp]
     lib.ss_t2u_unit_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.ss_unit_position_row.argtypes = [vp, vp]
@@ -87,6 +89,7 @@ def load_library() -> ctypes.CDLL:
     lib.ss_debug_copy.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t]
     lib.ss_launch_count.argtypes = [vp]
     lib.ss_launch_count.restype = i64
+    lib.ss_async_error.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -95,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_ctc_greedy_rows", "ss_mt_greedy",
     "ss_mt_features", "ss_mt_stable_rows", "ss_t2u_unit_decode", "ss_unit_position_row", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
-    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count",
+    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count", "ss_async_error", "ss_mt_incremental_reset", "ss_mt_greedy_incremental",
 ]
 
 
@@ -233,6 +236,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.ss_launch_count(self._h))
 
+    def check_async_error(self):
+        """raise if a persistent kernel's grid barrier timed out since the last check (synchronises the device)"""
+        self._check(self.lib.ss_async_error(self._h))
+
     def set_chunk(self, attn_chunk: Optional[int], conv_chunk: Optional[int] = None):
         """encoder.chunk_size and the conv chunk sizes the agents poke (agent:395-413).  None = offline model."""
         a = 0 if attn_chunk is None else int(attn_chunk)
@@ -346,6 +353,22 @@ class Engine:
                                           int(max_len_b), out, cap, ctypes.byref(n_out), feats.data_ptr()))
         n = n_out.value
         return [int(out[i]) for i in range(n)], feats[: n + 1]
+
+    def mt_incremental_reset(self):
+        self._check(self.lib.ss_mt_incremental_reset(self._h))
+
+    def mt_greedy_incremental(self, enc: torch.Tensor, prefix: Optional[Sequence[int]], max_new_tokens: int, max_len: int) -> List[int]:
+        """generate_decoder with use_incremental_states=True (S2TT agent): decoder state persists in the handle across calls
+        (ss_mt_greedy_incremental).  `max_len` = the generator's max_len for max_new_tokens == -1.  Returns tokens without eos."""
+        assert enc.is_cuda and enc.is_contiguous() and enc.dim() == 2
+        prefix = list(prefix) if prefix is not None else []
+        cap = self.max_mt_positions
+        pfx = (ctypes.c_int64 * max(len(prefix), 1))(*prefix)
+        out = (ctypes.c_int64 * cap)()
+        n_out = ctypes.c_int32(0)
+        self._check(self.lib.ss_mt_greedy_incremental(self._h, self._stream(), enc.data_ptr(), enc.shape[0], pfx, len(prefix), int(max_new_tokens),
+                                                      int(max_len), out, cap, ctypes.byref(n_out)))
+        return [int(out[i]) for i in range(n_out.value)]
 
     def mt_features(self, enc: torch.Tensor, tokens: Sequence[int], want_logits: bool = False, stable_rows: int = 0):
         if stable_rows > 0:

@@ -13,6 +13,7 @@ try:  # pragma: no cover - not installable in the build image
     from simuleval.agents.states import AgentStates  # type: ignore
     from simuleval.data.segments import EmptySegment, Segment, SpeechSegment, TextSegment  # type: ignore
     from simuleval.utils import entrypoint  # type: ignore
+    from simuleval.utils.agent import EVALUATION_SYSTEM_LIST  # type: ignore
 
     HAVE_SIMULEVAL = True
 except Exception:  # noqa: BLE001
@@ -182,6 +183,8 @@ except Exception:  # noqa: BLE001
         source_type: str = "speech"
         target_type: str = "speech"
 
-    def entrypoint(klass):  # simuleval/utils/agent.py
-        klass._is_entrypoint = True
+    EVALUATION_SYSTEM_LIST = []  # simuleval/utils/agent.py:20
+
+    def entrypoint(klass):  # simuleval/utils/__init__.py:10-12
+        EVALUATION_SYSTEM_LIST.append(klass)
         return klass

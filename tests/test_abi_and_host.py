@@ -123,3 +123,35 @@ def _shard_worker(rank, world):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert t.item() == 4.0
     dist.destroy_process_group()
+
+
+def test_agent_files_load_the_way_simuleval_loads_them():
+    """`simuleval --agent FILE` imports the file as a top-level module named "agents" and then requires exactly ONE class
+    registered by @entrypoint (SimulEval/simuleval/utils/agent.py:25-28,46-56).  Each file under streamspeech_b200/agents/ must
+    survive that (no relative imports) and register exactly its own agent, with the reference's class name and flags."""
+    import argparse
+    import importlib.util
+
+    from streamspeech_b200 import simuleval_compat as sc
+
+    expected = {"speech_to_speech.streamspeech.agent.py": ("StreamSpeechS2STAgent", "speech"),
+                "speech_to_text.asr.streamspeech.agent.py": ("StreamSpeechASRAgent", "text"),
+                "speech_to_text.s2tt.streamspeech.agent.py": ("StreamSpeechS2TTAgent", "text")}
+    d = os.path.join(ROOT, "streamspeech_b200", "agents")
+    assert sorted(os.listdir(d)) == sorted(expected) or sorted(f for f in os.listdir(d) if f.endswith(".py")) == sorted(expected)
+    for fname, (cls_name, target) in expected.items():
+        before = len(sc.EVALUATION_SYSTEM_LIST)
+        spec = importlib.util.spec_from_file_location("agents", os.path.join(d, fname))  # import_file()
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        new = sc.EVALUATION_SYSTEM_LIST[before:]
+        assert len(new) == 1 and new[0].__name__ == cls_name, (fname, new)
+        klass = new[0]
+        assert klass.source_type == "speech" and klass.target_type == target
+        p = argparse.ArgumentParser()
+        klass.add_args(p)
+        a = p.parse_args(["--model-path", "m", "--data-bin", "d", "--vocoder", "v", "--vocoder-cfg", "c"])
+        for flag in ("config_yaml", "multitask_config_yaml", "lagging_k1", "stride_n", "segment_size", "sample_rate", "dur_prediction",
+                     "extra_output_dir", "max_len", "force_finish"):
+            assert hasattr(a, flag), (fname, flag)
+        assert a.sample_rate == 48000  # the reference's default (agent:32-35)

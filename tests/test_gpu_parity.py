@@ -166,10 +166,12 @@ def test_encoder_streaming_prefix_invariance(full):
     assert d < 1e-4, d
 
 
-@pytest.mark.parametrize("seg_ms,attn,conv", [(160, 4, 8), (320, 8, 8), (640, 16, 16), (160, 4, 4)])
+@pytest.mark.parametrize("seg_ms,attn,conv", [(160, 4, 8), (320, 8, 8), (640, 16, 16), (160, 4, 4), (480, 12, 8), (960, 24, 16), (1600, 40, 16)])
 def test_encoder_streaming_cache_equals_recompute(full, seg_ms, attn, conv):
     """ss_encoder_stream_step (K/V + conv-input caches, only the open chunk group recomputed) must reproduce the
-    full-prefix recompute that the reference performs on every policy() call, at every call."""
+    full-prefix recompute that the reference performs on every policy() call, at every call.  (12, 8), (24, 16), (40, 16):
+    chunk sizes that do not nest (--source-segment-size 480 / 960 / 1600): rows are final only at common multiples of the
+    attention chunk and the conv chunk."""
     cfg, e, o = full
     e.set_chunk(attn, conv)
     feats = e.fbank(cuda(synth.make_audio(5.0, seed=31)))
@@ -372,21 +374,27 @@ def agent_args(**kw):
     return argparse.Namespace(**d)
 
 
-@pytest.mark.parametrize("seconds,seed,mode", [(4.0, 1234, "cached"), (6.4, 77, "cached"), (3.0, 1234, "recompute")])
-def test_streaming_s2st_agent_vs_oracle(seconds, seed, mode):
-    """Config 2 shape (chunk 320 ms, batch 1): every policy() call must reproduce the oracle agent's action,
-    token sequences bit-exactly and the emitted waveform within 1e-3."""
+@pytest.mark.parametrize("seconds,seed,mode,seg_ms", [(4.0, 1234, "cached", 320), (6.4, 77, "cached", 320), (3.0, 1234, "recompute", 320),
+                                                     (10.0, 1234, "cached", 320),   # the utterance bench.py times (configs[1])
+                                                     (5.12, 1234, "cached", 640),   # whole-word path (agent:540-574), configs[4] chunk
+                                                     (4.8, 5, "cached", 480)])      # attention chunk 12 / conv chunk 8 (not nested)
+def test_streaming_s2st_agent_vs_oracle(seconds, seed, mode, seg_ms):
+    """Config 2 shape (chunk 320 ms, batch 1) and the 640 / 480 ms variants: every policy() call must reproduce the oracle
+    agent's action, token sequences bit-exactly and the emitted waveform within 1e-3."""
     from oracle.agent_oracle import OracleS2STAgent
     from oracle.streamspeech_oracle import StreamSpeechOracle
     from streamspeech_b200.agent import StreamSpeechS2STAgent
+    from streamspeech_b200.dictionary import Dictionary
     from streamspeech_b200.simuleval_compat import SpeechSegment
 
     cfg = ModelConfig()
     o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), synth.make_vocoder_state_dict(cfg.vocoder, 1), synth.make_gcmvn(cfg))
-    ref = OracleS2STAgent(o, 320)
-    agent = StreamSpeechS2STAgent(agent_args(encoder_mode=mode, vocoder_context="full" if mode == "recompute" else "receptive-field"))
+    d = Dictionary.synthetic(cfg.tgt_vocab)
+    ref = OracleS2STAgent(o, seg_ms, is_word_start=lambda t: d[t].startswith("\u2581"))
+    agent = StreamSpeechS2STAgent(agent_args(encoder_mode=mode, vocoder_context="full" if mode == "recompute" else "receptive-field",
+                                             source_segment_size=seg_ms))
     wav = synth.make_audio(seconds, seed=seed)
-    n = 5120
+    n = 16 * seg_ms
     worst, writes = 0.0, 0
     for i in range(0, len(wav), n):
         fin = i + n >= len(wav)
@@ -404,7 +412,7 @@ def test_streaming_s2st_agent_vs_oracle(seconds, seed, mode):
             if len(a_ref.wav):
                 worst = max(worst, float(np.abs(np.array(seg.content) - np.array(a_ref.wav)).max()))
                 writes += 1
-    report("s2st_streaming_" + mode, seconds=seconds, wav_maxdiff=worst, writes=writes)
+    report(f"s2st_streaming_{mode}_{seg_ms}ms", seconds=seconds, wav_maxdiff=worst, writes=writes)
     assert writes >= 1 and worst < WAV_TOL, (writes, worst)
     agent.engine.close()
 
@@ -449,6 +457,7 @@ def test_unit_decoder_grouped_first_layer(eng3, gold):
     g = gold["decoders"]
     feats = cuda(g["mt_feats"])
     big = feats.repeat(7, 1).contiguous() * torch.linspace(0.8, 1.2, 7 * feats.shape[0], device="cuda").unsqueeze(1)  # 49 tokens -> 1225 positions
+    eng3.set_option("unit_grouped", 0)  # the reference of this test is the FULL 25*S-row first layer
     ref_small = eng3.t2u_unit_decode(feats, debug=True)
     ref_big = eng3.t2u_unit_decode(big, debug=True)
     ref_pad = eng3.t2u_unit_decode(cuda(g["mt_feats_pad"]), n_pad_tail=1, debug=True)
@@ -468,6 +477,107 @@ def test_unit_decoder_grouped_first_layer(eng3, gold):
         d3 = maxdiff(rp["logits"], ref_pad["logits"])
         assert rp["argmax"].tolist() == g["unit_argmax_pad"].tolist()
     finally:
-        eng3.set_option("unit_grouped", 0)
+        eng3.set_option("unit_grouped", 1)  # the engine default
     report("unit_grouped", vs_full=d1, vs_fixture=d0, long_vs_full=d2, pad_vs_full=d3)
+    assert d1 > 0.0, "the full-attention reference was not computed with unit_grouped = 0"
     assert d1 < 5e-5 and d0 < 5e-4 and d2 < 1e-4 and d3 < 5e-5, (d1, d0, d2, d3)
+
+
+# --------------------------------------------------------------------------------------------- fixtures from the reference's own generator / policy
+def test_mt_greedy_reference_generate_decoder_fixture(full, gold):
+    """M1 against the REAL reference: tests/golden/mt_greedy.npz holds the tokens `SequenceGenerator.generate_decoder`
+    (agent/sequence_generator.py:165-582, imported unchanged) finalized on the reference MT decoder."""
+    cfg, e, o = full
+    g = gold["mt_greedy"]
+    e.set_chunk(8)
+    enc = cuda(g["enc_out"])
+    for i in range(int(g["n_cases"])):
+        prefix = g[f"case{i}_prefix"].tolist() if bool(g[f"case{i}_has_prefix"]) else None
+        toks, _ = e.mt_greedy(enc, prefix, int(g[f"case{i}_max_new"]), max_len_b=100)
+        ref = g[f"case{i}_tokens"].tolist()
+        assert ref[-1] == cfg.eos and toks == ref[:-1], (i, toks, ref)
+
+
+@pytest.mark.parametrize("tag", ["c320", "c640"])
+def test_s2st_agent_vs_reference_policy_fixture(gold, tag):
+    """A1 / P1 against the REAL reference: tests/golden/agent_policy.npz is the action sequence of the reference's own policy()
+    (agent:422-770, executed from its source on reference generator / module objects, oracle/gen_golden_agent.py).  The engine
+    agent must take the same READ / WRITE decisions, emit the same units and the same waveform (1e-3)."""
+    from streamspeech_b200.agent import StreamSpeechS2STAgent
+    from streamspeech_b200.simuleval_compat import SpeechSegment
+
+    g = gold["agent_policy"]
+    seg_ms, seconds, seed = int(g[f"{tag}_segment_ms"]), float(g[f"{tag}_seconds"]), int(g[f"{tag}_seed"])
+    agent = StreamSpeechS2STAgent(agent_args(source_segment_size=seg_ms))
+    wav = synth.make_audio(seconds, seed=seed)
+    n = 16 * seg_ms
+    kinds = g[f"{tag}_kinds"].tolist()
+    worst, writes = 0.0, 0
+    for ci, i in enumerate(range(0, len(wav), n)):
+        fin = i + n >= len(wav)
+        seg = agent.pushpop(SpeechSegment(content=wav[i:i + n].tolist(), sample_rate=16000, finished=fin))
+        assert (not seg.is_empty) == bool(kinds[ci]), (tag, ci)
+        if kinds[ci]:
+            ref = g[f"{tag}_call{ci}_wav"]
+            assert len(seg.content) == len(ref), (tag, ci, len(seg.content), len(ref))
+            assert bool(seg.finished) == bool(g[f"{tag}_call{ci}_flags"][1]), (tag, ci)
+            if len(ref):
+                assert agent.trace.get("units") == g[f"{tag}_call{ci}_units"].tolist(), (tag, ci)
+                assert agent.trace.get("dur") == g[f"{tag}_call{ci}_dur"].tolist(), (tag, ci)
+                worst = max(worst, float(np.abs(np.array(seg.content, dtype=np.float32) - ref).max()))
+                writes += 1
+    report("s2st_reference_policy_" + tag, wav_maxdiff=worst, writes=writes)
+    assert writes >= 1 and worst < WAV_TOL, (writes, worst)
+    agent.engine.close()
+
+
+def test_s2tt_agent_vs_reference_policy_fixture_and_oracle(gold):
+    """Row f1: StreamSpeechS2TTAgent (incremental MT decoder states across policy() calls) against (a) the action
+    sequence of the reference's own S2TT policy() (tests/golden/agent_policy.npz, oracle/gen_golden_agent.py) and (b) the oracle
+    agent on a second utterance: every text delta and every hypothesis bit-exact."""
+    from oracle.agent_oracle import OracleS2TTAgent
+    from oracle.streamspeech_oracle import StreamSpeechOracle
+    from streamspeech_b200.agent import StreamSpeechS2TTAgent
+    from streamspeech_b200.dictionary import Dictionary
+    from streamspeech_b200.simuleval_compat import SpeechSegment
+
+    g = gold["agent_policy"]
+    tag = "s2tt320"
+    seg_ms, seconds, seed = int(g[f"{tag}_segment_ms"]), float(g[f"{tag}_seconds"]), int(g[f"{tag}_seed"])
+    agent = StreamSpeechS2TTAgent(agent_args(source_segment_size=seg_ms))
+    wav = synth.make_audio(seconds, seed=seed)
+    n = 16 * seg_ms
+    kinds, texts = g[f"{tag}_kinds"].tolist(), g[f"{tag}_texts"].tolist()
+    for ci, i in enumerate(range(0, len(wav), n)):
+        fin = i + n >= len(wav)
+        seg = agent.pushpop(SpeechSegment(content=wav[i:i + n].tolist(), sample_rate=16000, finished=fin))
+        assert (not seg.is_empty) == bool(kinds[ci]), ci
+        if kinds[ci]:
+            assert seg.content == texts[ci], (ci, seg.content, texts[ci])
+            assert agent.trace["mt_tokens"] == g[f"{tag}_call{ci}_mt_tokens"].tolist(), ci
+    # (b) a second utterance through the same agent object (reset() must clear the incremental state), vs the oracle
+    cfg = ModelConfig()
+    o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), None, synth.make_gcmvn(cfg))
+    d = Dictionary.synthetic(cfg.tgt_vocab)
+    ref = OracleS2TTAgent(o, seg_ms, symbols=lambda t: d[t])
+    wav = synth.make_audio(3.2, seed=99)
+    writes = 0
+    for ci, i in enumerate(range(0, len(wav), n)):
+        fin = i + n >= len(wav)
+        chunk = wav[i:i + n].tolist()
+        ref.push(chunk, finished=fin)
+        a = ref.policy()
+        seg = agent.pushpop(SpeechSegment(content=chunk, sample_rate=16000, finished=fin))
+        assert seg.is_empty == (a.kind == "read"), ci
+        if a.kind == "write":
+            assert seg.content == a.wav and agent.trace["mt_tokens"] == a.trace["mt_tokens"], ci
+            writes += 1
+    report("s2tt_agent", writes=writes)
+    assert writes >= 2
+    agent.engine.close()
+
+
+def test_grid_barrier_error_flag_is_clear_after_the_suite(full):
+    """ss_async_error: no persistent-kernel grid barrier timed out during the tests above on this handle."""
+    cfg, e, o = full
+    e.check_async_error()

@@ -54,7 +54,7 @@ def test_unit_positions_depend_on_batch_index(gold):
     assert float((both[1] - single[0]).abs().max()) > 1e-3
 
 
-@pytest.mark.gpu_staged
+@pytest.mark.gpu
 @pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
 def test_offline_generator_engine_vs_fixture(gold):
     from streamspeech_b200.engine import Engine

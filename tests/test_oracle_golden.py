@@ -1,6 +1,7 @@
 """CPU: the oracle restatement reproduces the fixtures dumped from the REAL reference modules
 (oracle/gen_golden.py) and the reference's own known-answer tests for this path."""
 import numpy as np
+import pytest
 import torch
 
 from oracle.streamspeech_oracle import (StreamSpeechOracle, kaldi_fbank, online_features, rel_positional_encoding,
@@ -172,3 +173,79 @@ def test_unit_decoder_first_layer_grouped_attention_identity(gold):
                     out[g, r, h] = (R * A + c * e_own * (v[g, h] if own else 0)) / (R * a + c * e_own)
         grouped = _lin(out.view(L, 1, E), o.sd, p + ".self_attn.out_proj")
         assert float((grouped - full).abs().max()) < 2e-5, n_valid
+
+
+def test_mt_greedy_matches_reference_generate_decoder(gold):
+    """M1 pin: tests/golden/mt_greedy.npz holds the finalized tokens of the reference's own
+    `agent/sequence_generator.py:SequenceGenerator.generate_decoder` (beam 1, the agent's constructor arguments) on the
+    reference MT decoder (oracle/gen_golden_agent.py); the restatement must return the same tokens for every
+    (prefix, max_new_tokens) case, including the forced-eos and max_new_tokens = -1 cases."""
+    g = gold["mt_greedy"]
+    cfg = ModelConfig()
+    o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), None, synth.make_gcmvn(cfg), chunk_size=8)
+    eo = torch.from_numpy(g["enc_out"]).unsqueeze(1)
+    for i in range(int(g["n_cases"])):
+        prefix = g[f"case{i}_prefix"].tolist() if bool(g[f"case{i}_has_prefix"]) else None
+        k = int(g[f"case{i}_max_new"])
+        if k == -1 and i not in (2,):  # the 99-step cases cost ~10 s each on the CPU: one of them is enough here
+            continue
+        assert o.mt_greedy(eo, prefix, k, max_len_b=100, max_decoder_positions=1200) == g[f"case{i}_tokens"].tolist(), i
+
+
+@pytest.mark.parametrize("tag", ["c320", "c640"])
+def test_agent_oracle_matches_reference_policy_fixture(gold, tag):
+    """A1 / P1 pin: tests/golden/agent_policy.npz is the action sequence of the reference's own `policy()` (executed from its
+    source on reference generator / module objects, oracle/gen_golden_agent.py) for a 320 ms utterance and a 640 ms
+    (whole-word, agent:540-574) utterance.  OracleS2STAgent must reproduce every READ / WRITE, the flags, and the waveform."""
+    from oracle.agent_oracle import OracleS2STAgent
+    from streamspeech_b200.dictionary import Dictionary
+
+    g = gold["agent_policy"]
+    cfg = ModelConfig()
+    o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), synth.make_vocoder_state_dict(cfg.vocoder, 1, weight_norm=True),
+                           synth.make_gcmvn(cfg))
+    d = Dictionary.synthetic(cfg.tgt_vocab)
+    seg_ms, seconds, seed = int(g[f"{tag}_segment_ms"]), float(g[f"{tag}_seconds"]), int(g[f"{tag}_seed"])
+    ag = OracleS2STAgent(o, seg_ms, is_word_start=lambda t: d[t].startswith("▁"))
+    wav = synth.make_audio(seconds, seed=seed)
+    n = 16 * seg_ms
+    kinds = g[f"{tag}_kinds"].tolist()
+    for ci, i in enumerate(range(0, len(wav), n)):
+        fin = i + n >= len(wav)
+        ag.push(wav[i:i + n].tolist(), finished=fin)
+        a = ag.policy()
+        assert (a.kind == "write") == bool(kinds[ci]), (tag, ci)
+        if a.kind == "write":
+            ref = g[f"{tag}_call{ci}_wav"]
+            assert len(a.wav) == len(ref), (tag, ci)
+            assert [a.finished, a.seg_finished] == g[f"{tag}_call{ci}_flags"].tolist()
+            if len(ref):
+                assert float(np.abs(np.array(a.wav, dtype=np.float32) - ref).max()) < 1e-5, (tag, ci)
+            assert a.trace.get("units", []) == g[f"{tag}_call{ci}_units"].tolist()
+
+
+def test_s2tt_oracle_matches_reference_policy_fixture(gold):
+    """f1 pin: the S2TT agent's policy() (agent/speech_to_text.s2tt.streamspeech.agent.py:381-545) executed from its own source
+    with the reference SequenceGenerator in incremental-state mode (N12: duplicate self-attention entry per call, stale
+    cross-attention K / V).  OracleS2TTAgent must emit the same text deltas."""
+    from oracle.agent_oracle import OracleS2TTAgent
+    from streamspeech_b200.dictionary import Dictionary
+
+    g = gold["agent_policy"]
+    cfg = ModelConfig()
+    o = StreamSpeechOracle(cfg, synth.make_model_state_dict(cfg, 0), None, synth.make_gcmvn(cfg))
+    d = Dictionary.synthetic(cfg.tgt_vocab)
+    tag = "s2tt320"
+    seg_ms, seconds, seed = int(g[f"{tag}_segment_ms"]), float(g[f"{tag}_seconds"]), int(g[f"{tag}_seed"])
+    ag = OracleS2TTAgent(o, seg_ms, symbols=lambda t: d[t])
+    wav = synth.make_audio(seconds, seed=seed)
+    n = 16 * seg_ms
+    kinds, texts = g[f"{tag}_kinds"].tolist(), g[f"{tag}_texts"].tolist()
+    for ci, i in enumerate(range(0, len(wav), n)):
+        fin = i + n >= len(wav)
+        ag.push(wav[i:i + n].tolist(), finished=fin)
+        a = ag.policy()
+        assert (a.kind == "write") == bool(kinds[ci]), ci
+        if a.kind == "write":
+            assert a.wav == texts[ci], (ci, a.wav, texts[ci])
+            assert a.trace["mt_tokens"] == g[f"{tag}_call{ci}_mt_tokens"].tolist()
