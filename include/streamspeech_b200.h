@@ -111,6 +111,14 @@ int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, in
 int ss_ctc_greedy_rows(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int row0, int64_t* argmax_dev,
                        int64_t* tokens_dev, int32_t* index_dev, int32_t* count_dev);
 
+/* Both heads of one policy() call (agent:437 and :461) in two launches: one [rows - row0][2V] projection over the concatenated
+ * head weights and one kernel that takes the arg-max of every new row and then (last block) collapses both sequences.
+ * argmax{0,1}_dev as in ss_ctc_greedy_rows (caller-kept, rows below row0 valid).  packed_out_dev holds, per head h, at int64
+ * offset h * (2 * rows + 2): [count (int32) | tokens[rows] int64 | index[rows] int32] -- one device->host copy reads everything.
+ * Heads with different vocabularies fall back to two ss_ctc_greedy_rows calls with the same packing.  enqueue only */
+int ss_ctc_greedy_pair(ss_engine* h, void* stream, const float* enc_dev, int rows, int row0, int64_t* argmax0_dev, int64_t* argmax1_dev,
+                       int64_t* packed_out_dev);
+
 /* ---- M1/M2: SequenceGenerator.generate_decoder, beam 1 (agent/sequence_generator.py:165-582) + the extra
  * mt_decoder(prev_output_tokens, features_only=True) forward (agent:638-642).
  * prefix_host[n_prefix] = tgt_subwords_indices; max_new_tokens as in the agent (-1 = source finished:
@@ -172,6 +180,25 @@ int ss_vocoder_generate(ss_engine* h, void* stream, int total_frames, int frame0
                         float* wav_out_dev);
 int ss_vocoder_hop(const ss_engine* h);
 int ss_vocoder_receptive_field(const ss_engine* h);
+
+/* ---- multi-stream pool: n concurrent utterances per handle, ONE batched streaming step (BASELINE configs[3] = 256
+ * concurrent ASR streams, 32 per GPU).  The reference is one utterance per agent process (agent/speech_to_text.asr.streamspeech.
+ * agent.py:385-433).  Each stream owns a slot: device audio, fbank frames, per-layer K / V / conv-input caches, encoder rows and CTC
+ * arg-max rows.  Results of every stream equal the single-stream entry points' (same arithmetic per stream; GEMMs see n x rows). */
+int ss_pool_create(ss_engine* h, int n_slots, int max_seconds);
+int ss_pool_reset(ss_engine* h, int slot);                       /* new utterance on this slot */
+/* append n 16 kHz samples (host memory) to the slot's device audio: enqueue of one host->device copy */
+int ss_pool_push_audio(ss_engine* h, void* stream, int slot, const float* samples_host, int n);
+/* state of a slot: samples / fbank frames held, final encoder rows, device pointers of its encoder rows [Tcap][enc_dim] and fbank
+ * frames [Fcap][feat_dim] (any out pointer may be NULL) */
+int ss_pool_info(ss_engine* h, int slot, int64_t* n_audio, int32_t* n_feat, int32_t* T_final, float** enc_out_dev, float** feats_dev);
+/* One streaming step of the n listed slots over all the audio pushed so far: OnlineFeatureExtractor (new frames only) ->
+ * forward_encoder (rows not yet final, ss_encoder_stream_step semantics) -> CTCDecoder.generate for ctc_heads heads (0: none, 1: ASR,
+ * 2: ASR + ST).  Per stream i, packed_out_dev + out_off_host[i] holds per head [count (int32) | tokens[T_i] int64 | index[T_i] int32]
+ * (head h at + h * (2 T_i + 2) int64 words).  T_out_host / T_final_out_host / out_off_host: n entries each (host, written before
+ * return).  Synchronises `stream` once at entry (descriptor staging); everything else is enqueue only. */
+int ss_pool_step(ss_engine* h, void* stream, int n, const int32_t* slots_host, int ctc_heads, int64_t* packed_out_dev, int64_t packed_capacity,
+                 int32_t* T_out_host, int32_t* T_final_out_host, int64_t* out_off_host);
 
 /* ---- single ops exported for the parity tests (same kernels the entry points above launch) ------------- */
 int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N,

@@ -12,6 +12,7 @@
 #include "../../include/streamspeech_b200.h"
 #include "kernels.h"
 #include "kernels_persist.h"
+#include "kernels_multistream.h"
 
 namespace ss {
 
@@ -102,6 +103,8 @@ struct ss_engine {
   int graph_pdl = 0;
   cudaStream_t capture_stream = nullptr;
   std::map<std::tuple<int, uintptr_t, int, int, int>, std::pair<cudaGraphExec_t, int>> voc_graphs;
+  float* persist_ffn_scratch = nullptr;  // [enc_ffn / 16][16][enc_dim] partial sums of the fused FFN phases
+  int persistent_ffn_fused = 1;          // fused FFN phases in the persistent encoder kernel (0: separate W1 / W2 phases)
   int persistent_encoder = 1;  // streaming encoder step as ONE cooperative kernel (kernels_persist.cu) when the shape fits
   std::map<std::string, ss::HostTensor> host;  // loaded tensors by key
   std::vector<void*> dev_allocs;
@@ -112,6 +115,8 @@ struct ss_engine {
   std::vector<ss::ConformerLayerW> enc;
   int Tpos = 0;
   ss::Linear ctc_head[2];
+  ss::Linear ctc_pair;              // both heads as one [2V][D] linear (N == 0 when the vocabularies differ)
+  unsigned* ctc_ticket = nullptr;   // "last block done" ticket of ctc_argmax_collapse_pair_kernel
   float* mt_emb = nullptr;
   float* mt_pos = nullptr;  // sinusoid table [max_mt_positions + pad + 2][mt_dim]
   int mt_pos_rows = 0;
@@ -183,9 +188,21 @@ struct ss_engine {
   int persistent_barrier = 1;        // 0: cooperative-groups grid.sync(), 1: own counter barrier (1.6 us cheaper per barrier)
   ss::MtLayerP* mt_persist_layers = nullptr;   // [mt_layers] device pointer table for kernels_persist_mt.cu
   int persistent_mt = 1;                       // single-token MT decode steps as one cooperative kernel per burst
+  int persistent_mt_prefix = 1;                // ... and the forced-prefix pass (M <= 64 rows) as one cooperative kernel
   ss::PersistLayer* persist_layers = nullptr;  // [enc_layers] device copy of the per-layer pointer table
   int* lengths_dev = nullptr;     // [Bcap]
   int lengths_cap = 0;
+
+  // ---- multi-stream pool (engine_pool.inc): per-slot streaming state at fixed strides
+  struct StreamPool {
+    int n_slots = 0, Tcap = 0, Fcap = 0;
+    int64_t audio_cap = 0;
+    float *audio = nullptr, *feats = nullptr, *k = nullptr, *v = nullptr, *glu = nullptr, *enc_out = nullptr, *melT = nullptr;
+    int64_t* ctc_am = nullptr;                         // [slot][2][Tcap]
+    ss::MsStream *desc_dev = nullptr, *desc_pinned = nullptr, *desc_dev2 = nullptr, *desc_pinned2 = nullptr;
+    std::vector<int> T_final, n_feat;
+    std::vector<int64_t> n_audio;
+  } pool;
 
   int fail(int code, const std::string& msg) {
     err = msg;

@@ -441,7 +441,7 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
                                              c.enc_ffn, c.enc_heads, h->Tpos, h->attn_chunk, cc, c.dw_kernel,
                                              h->persistent_profile ? h->persist_ts : nullptr,
                                              h->persistent_barrier ? h->persist_bar : nullptr, &h->persist_bar_target,
-                                             h->persistent_prefetch, st) == 0;
+                                             h->persistent_prefetch, h->persistent_ffn_fused ? h->persist_ffn_scratch : nullptr, st) == 0;
     if (ev0 && ev1) {
       cudaEventRecord(ev1, st);
       // algorithmic bytes of this launch: every GEMM weight once + the K / V caches and relative-position rows the attention reads
@@ -494,6 +494,35 @@ int ss_ctc_greedy_rows(ss_engine* h, void* stream, int head, const float* enc_de
   }
   ctc_collapse(argmax_dev, rows, 0 /* <s> is the CTC blank (agent/ctc_decoder.py:72-76) */, h->cfg.pad, tokens_dev, index_dev, count_dev, st);
   return check_launch(h, "ss_ctc_greedy");
+}
+
+int ss_ctc_greedy_pair(ss_engine* h, void* stream, const float* enc_dev, int rows, int row0, int64_t* argmax0_dev, int64_t* argmax1_dev,
+                       int64_t* packed_out_dev) {
+  if (h) route_from(h);
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (rows <= 0 || row0 < 0 || row0 > rows) return h->fail(SS_ERR_INVALID, "bad ctc rows");
+  cudaStream_t st = S(stream);
+  const int V = h->cfg.src_vocab;
+  const int nr = rows - row0;
+  const int W = 2 * rows + 2;
+  if (h->ctc_pair.N != 2 * V || h->cfg.tgt_vocab != V) {  // different vocabularies: two single-head calls into the same packing
+    for (int hd = 0; hd < 2; ++hd) {
+      int64_t* o = packed_out_dev + (size_t)hd * W;
+      int rc = ss_ctc_greedy_rows(h, stream, hd, enc_dev, rows, row0, hd ? argmax1_dev : argmax0_dev, o + 1, reinterpret_cast<int32_t*>(o + 1 + rows),
+                                  reinterpret_cast<int32_t*>(o));
+      if (rc) return rc;
+    }
+    return SS_OK;
+  }
+  float* logits = nullptr;
+  if (nr > 0) {
+    if (!ws_begin(h, (size_t)nr * 2 * V * sizeof(float) + 4096)) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
+    logits = h->ws.f32((size_t)nr * 2 * V);
+    linear(enc_dev + (size_t)row0 * h->cfg.enc_dim, h->cfg.enc_dim, nr, h->ctc_pair, ep_out(logits, 2 * V), st);
+  }
+  ctc_argmax_collapse_pair(logits, 2 * V, V, nr, row0, rows, h->mask_pad_unk, 2, 0 /* <s> = CTC blank */, h->cfg.pad, argmax0_dev, argmax1_dev,
+                           packed_out_dev, W, h->ctc_ticket, st);
+  return check_launch(h, "ss_ctc_greedy_pair");
 }
 
 int ss_ctc_greedy(ss_engine* h, void* stream, int head, const float* enc_dev, int rows, int64_t* argmax_dev, int64_t* tokens_dev,
@@ -574,6 +603,19 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
   const bool persistent_mt = h->persistent_mt && mt_decode_persistent_supported(dim, c.mt_ffn, c.mt_heads, c.tgt_vocab, c.max_mt_positions, T);
   int step = start;
   bool done = false;
+  if (persistent_mt && h->persistent_mt_prefix && h->persist_bar && start >= 1 && mt_prefix_persistent_supported(dim, c.mt_ffn, c.mt_heads, start, T)) {
+    // rows 0 .. start-1 ([eos, p1 .. p_{start-1}]) in one cooperative launch; the single-token kernel continues at position `start`
+    MtDecodeParams P;
+    P.n_layers = c.mt_layers; P.heads = c.mt_heads; P.vocab = c.tgt_vocab; P.pad = c.pad; P.eos = c.eos;
+    P.max_pos = c.max_mt_positions; P.cross_cap = h->mt_cross_cap;
+    P.emb = h->mt_emb; P.pos = h->mt_pos; P.out_g = h->mt_ln.g; P.out_b = h->mt_ln.b;
+    P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
+    P.tok = h->mt_tok_dev; P.feats = feats_out_dev; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
+    if (mt_prefix_persistent(P, h->mt_persist_layers, start, T, h->persist_bar, &h->persist_bar_target, st) == 0)
+      fed = start;
+    else
+      cudaGetLastError();  // refused launch: per-kernel path
+  }
   while (!done) {
     const int burst_first = step;
     int enq = 0;
@@ -1071,8 +1113,10 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "vocoder_graph") h->vocoder_graph = value;
   else if (n == "graph_pdl") h->graph_pdl = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
+  else if (n == "persistent_ffn_fused") h->persistent_ffn_fused = value;
   else if (n == "vocoder_streams") h->vocoder_streams = value;
   else if (n == "persistent_mt") h->persistent_mt = value;
+  else if (n == "persistent_mt_prefix") h->persistent_mt_prefix = value;
   else if (n == "persistent_prefetch") h->persistent_prefetch = value;
   else if (n == "persistent_time") h->persistent_time = value;
   else if (n == "persistent_barrier") {
@@ -1188,3 +1232,5 @@ int ss_op_layer_norm(ss_engine* h, void* stream, const float* x_dev, int rows, i
 }
 
 }  // extern "C"
+
+#include "engine_pool.inc"

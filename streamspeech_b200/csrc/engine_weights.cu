@@ -269,7 +269,16 @@ void finalize_impl(ss_engine* h) {
       q.bn_shift = L.bn_shift; q.pw2 = L.pw2.w; q.pw2_b = L.pw2.b;
       q.ffn2_g = L.ffn2_ln.g; q.ffn2_b = L.ffn2_ln.b; q.ffn2_w1 = L.ffn2_w1.w; q.ffn2_b1 = L.ffn2_w1.b; q.ffn2_w2 = L.ffn2_w2.w; q.ffn2_b2 = L.ffn2_w2.b;
       q.fin_g = L.final_ln.g; q.fin_b = L.final_ln.b;
+      // W2 transposed [FFN][D]: the fused FFN phases read one coalesced 1 KB row per hidden unit
+      for (int which = 0; which < 2; ++which) {
+        const HostTensor& w2 = get(h, "encoder.conformer_layers." + std::to_string(&q - pl.data()) + (which ? ".ffn2.w_2.weight" : ".ffn1.w_2.weight"));
+        std::vector<float> t((size_t)c.enc_ffn * D);
+        for (int n = 0; n < D; ++n)
+          for (int u = 0; u < c.enc_ffn; ++u) t[(size_t)u * D + n] = w2.data[(size_t)n * c.enc_ffn + u];
+        (which ? q.ffn2_w2t : q.ffn1_w2t) = upload(h, t);
+      }
     }
+    h->persist_ffn_scratch = dev_alloc<float>(h, (size_t)(c.enc_ffn / 16) * 16 * D);
     h->persist_layers = dev_alloc<PersistLayer>(h, pl.size());
     cudaMemcpy(h->persist_layers, pl.data(), pl.size() * sizeof(PersistLayer), cudaMemcpyHostToDevice);
     h->persist_bar = dev_alloc<unsigned>(h, 64);
@@ -279,8 +288,21 @@ void finalize_impl(ss_engine* h) {
       *h->async_err_pinned = 0;
   }
   // ---- CTC heads
-  h->ctc_head[0] = make_linear(h, "source_unigram_decoder.proj", c.src_vocab, D);
-  h->ctc_head[1] = make_linear(h, "ctc_target_unigram_decoder.proj", c.tgt_vocab, D);
+  if (c.src_vocab == c.tgt_vocab) {
+    // one [2V][D] matrix: both heads of a policy() call are ONE GEMM (ss_ctc_greedy_pair); the single heads are views of it
+    h->ctc_pair = make_fused(h, {"source_unigram_decoder.proj", "ctc_target_unigram_decoder.proj"}, c.src_vocab, D);
+    h->ctc_head[0] = h->ctc_pair;
+    h->ctc_head[0].N = c.src_vocab;
+    h->ctc_head[1] = h->ctc_pair;
+    h->ctc_head[1].N = c.tgt_vocab;
+    h->ctc_head[1].w = h->ctc_pair.w + (size_t)c.src_vocab * D;
+    h->ctc_head[1].b = h->ctc_pair.b + c.src_vocab;
+  } else {
+    h->ctc_head[0] = make_linear(h, "source_unigram_decoder.proj", c.src_vocab, D);
+    h->ctc_head[1] = make_linear(h, "ctc_target_unigram_decoder.proj", c.tgt_vocab, D);
+  }
+  h->ctc_ticket = dev_alloc<unsigned>(h, 8);
+  cudaMemset(h->ctc_ticket, 0, 8 * sizeof(unsigned));
   // ---- MT decoder
   {
     const HostTensor& e = get(h, "target_unigram_decoder.embed_tokens.weight");
@@ -456,6 +478,8 @@ int ss_destroy(ss_engine* h) {
   if (h->mt_cross_kv) cudaFree(h->mt_cross_kv);
   if (h->mt_next_pinned) cudaFreeHost(h->mt_next_pinned);
   if (h->async_err_pinned) cudaFreeHost(h->async_err_pinned);
+  if (h->pool.desc_pinned) cudaFreeHost(h->pool.desc_pinned);
+  if (h->pool.desc_pinned2) cudaFreeHost(h->pool.desc_pinned2);
   if (h->voc_unit_emb) cudaFree(h->voc_unit_emb);
   if (h->voc_cumsum) cudaFree(h->voc_cumsum);
   if (h->lengths_dev) cudaFree(h->lengths_dev);

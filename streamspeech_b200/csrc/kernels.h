@@ -136,6 +136,10 @@ void argmax_rows(const float* logits, int ld, int rows, int V, const int* masked
 // CTC collapse on one sequence: dedup consecutive, drop blank/pad.  Single CTA.
 void ctc_collapse(const int64_t* argmax, int n, int blank, int pad, int64_t* out_tokens, int* out_index, int* out_count,
                   cudaStream_t st);
+// both CTC heads: arg-max of the new rows [row0, row0 + n_new) from logits [n_new][ld] (head h at columns h*V..), then collapse
+// of all n_rows rows of both arg-max arrays into out[head] = [count | tokens[n_rows] | index[n_rows] (int32)]
+void ctc_argmax_collapse_pair(const float* logits, int ld, int V, int n_new, int row0, int n_rows, const int* masked, int n_masked, int blank,
+                              int pad, int64_t* am0, int64_t* am1, int64_t* out, int out_stride, unsigned* ticket, cudaStream_t st);
 void gather_rows(const int64_t* idx, int n, int idx_offset, const float* table, int C, float* out, cudaStream_t st);
 // dur = clamp(round(exp(x) - 1), min 1) (round half to even like torch.round); also inclusive prefix sum (single CTA)
 void duration_from_log(const float* logdur, int n, int64_t* dur, int* cumsum /*[n+1]*/, cudaStream_t st);

@@ -1,6 +1,8 @@
 // Streaming / scan kernels of the path: LayerNorm, depthwise chunk-causal conv + BN + SiLU, embedding
 // gathers, arg-max over the vocabulary, CTC collapse, duration rounding, frame expansion, conv_post.
 // All HBM-bound: coalesced row-major accesses, warp-shuffle reductions, no re-reads.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -235,6 +237,121 @@ __global__ void ctc_collapse_kernel(const int64_t* __restrict__ am, int n, int b
   if (t == 1023) *count = wsum[31];
 }
 
+// Both CTC heads of one policy() call after the fused [rows][2V] projection: block b = (head, new row) computes the arg-max of
+// log_softmax with masks exactly like argmax_rows_kernel; the LAST block to finish (ticket) then collapses both arg-max
+// sequences (CTCDecoder.generate, agent/ctc_decoder.py:64-111) into the packed outputs
+//   out[head] = [count (int32 in the first int64) | tokens[n_rows] int64 | index[n_rows] int32], stride out_stride int64 words.
+__global__ void __launch_bounds__(256) ctc_argmax_collapse_pair_kernel(const float* __restrict__ logits, int ld, int V, int n_new, int row0,
+                                                                      int n_rows, const int* __restrict__ masked, int n_masked, int blank,
+                                                                      int pad, int64_t* am0, int64_t* am1, int64_t* out, int out_stride,
+                                                                      unsigned* ticket) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[32];
+  __shared__ float sval[8];
+  __shared__ int sidx[8];
+  __shared__ int scount[256];
+  __shared__ unsigned s_last;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if ((int)blockIdx.x < 2 * n_new) {
+    const int head = blockIdx.x / n_new, r = blockIdx.x - head * n_new;
+    const float* x = logits + (int64_t)r * ld + head * V;
+    float mx = -INFINITY;
+    for (int c = tid; c < V; c += 256) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    if (lane == 0) red[w] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int c = tid; c < V; c += 256) s += expf(x[c] - mx);
+    s = block_sum(s, red);
+    const float lse = logf(s);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = tid; c < V; c += 256) {
+      bool m = false;
+      for (int q = 0; q < n_masked; ++q) m |= (masked[q] == c);
+      float lp = m ? -INFINITY : (x[c] - mx) - lse;
+      if (lp > best || (lp == best && c < bi)) {
+        best = lp;
+        bi = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    __syncthreads();
+    if (lane == 0) {
+      sval[w] = best;
+      sidx[w] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < 8; ++i)
+        if (sval[i] > best || (sval[i] == best && sidx[i] < bi)) {
+          best = sval[i];
+          bi = sidx[i];
+        }
+      (head ? am1 : am0)[row0 + r] = bi;
+    }
+  }
+  // ---- ticket: the last block collapses both sequences
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) *ticket = 0u;
+  __threadfence();
+  const int per = (n_rows + 255) / 256;
+  for (int head = 0; head < 2; ++head) {
+    const int64_t* am = head ? am1 : am0;
+    int64_t* o = out + (int64_t)head * out_stride;
+    int64_t* toks = o + 1;
+    int* index = reinterpret_cast<int*>(o + 1 + n_rows);
+    const int lo = min(tid * per, n_rows), hi = min(lo + per, n_rows);
+    int c = 0;
+    int64_t prev = lo > 0 ? __ldcg(am + lo - 1) : -1;
+    for (int i = lo; i < hi; ++i) {
+      int64_t v = __ldcg(am + i);
+      if ((i == 0 || v != prev) && v != blank && v != pad) ++c;
+      prev = v;
+    }
+    scount[tid] = c;
+    __syncthreads();
+    // inclusive scan over 256 counts (Hillis-Steele)
+    for (int off = 1; off < 256; off <<= 1) {
+      int add = tid >= off ? scount[tid - off] : 0;
+      __syncthreads();
+      scount[tid] += add;
+      __syncthreads();
+    }
+    int base = scount[tid] - c;
+    prev = lo > 0 ? __ldcg(am + lo - 1) : -1;
+    for (int i = lo; i < hi; ++i) {
+      int64_t v = __ldcg(am + i);
+      if ((i == 0 || v != prev) && v != blank && v != pad) {
+        toks[base] = v;
+        index[base] = i;
+        ++base;
+      }
+      prev = v;
+    }
+    if (tid == 255) *reinterpret_cast<int*>(o) = scount[255];
+    __syncthreads();
+  }
+}
+
 __global__ void gather_rows_kernel(const int64_t* __restrict__ idx, int idx_offset, const float* __restrict__ table, int C,
                                    float* __restrict__ out) {
   pdl_trigger();
@@ -363,6 +480,13 @@ void ctc_collapse(const int64_t* argmax, int n, int blank, int pad, int64_t* out
                   cudaStream_t st) {
   ++g_launches;
   launch_pdl(ctc_collapse_kernel, dim3(1), dim3(1024), 0, st, argmax, n, blank, pad, out_tokens, out_index, out_count);
+}
+
+void ctc_argmax_collapse_pair(const float* logits, int ld, int V, int n_new, int row0, int n_rows, const int* masked, int n_masked, int blank,
+                              int pad, int64_t* am0, int64_t* am1, int64_t* out, int out_stride, unsigned* ticket, cudaStream_t st) {
+  ++g_launches;
+  launch_pdl(ctc_argmax_collapse_pair_kernel, dim3(std::max(1, 2 * n_new)), dim3(256), 0, st, logits, ld, V, n_new, row0, n_rows, masked, n_masked,
+             blank, pad, am0, am1, out, out_stride, ticket);
 }
 
 void gather_rows(const int64_t* idx, int n, int idx_offset, const float* table, int C, float* out, cudaStream_t st) {

@@ -116,6 +116,8 @@ struct Smem {
   float strip[PW][48];
   float wstrip[PW][32];
   float red[PW];
+  float hs[PMR][16];          // fused FFN: this CTA's 16 hidden units for the 16 rows
+  float rsum[PW][32];         // fused FFN reduce: per-warp partial sums of 32 outputs
   unsigned long long* fine;  // profile mode, CTA 0, layer 1: (tag, clock64) stamps inside the phases
   int nfine;
 };
@@ -403,6 +405,140 @@ __device__ void phase_gemm(Smem& sm, const float* A, const float* __restrict__ p
   }
 }
 
+// ---- fused FFN (x += alpha * W2 act(W1 LN(x))) in TWO light phases instead of a W1 phase and a W2 phase that makes every CTA
+// read the whole 16 x 2048 hidden from L2 (16 MB per phase, measured 8 us):
+//   phase A : CTA j < FFN/16 owns hidden units [16j, 16j+16): hid = SiLU(LN(x) W1[16 rows]^T + b1) stays in shared memory, then the
+//             rank-16 update  P[j][m][n] = sum_u hid[m][u] * W2T[16j+u][n]  (W2T = W2 transposed, one coalesced 1 KB row per unit)
+//             goes to a global scratch (16 KB per CTA);
+//   phase A': CTA c owns 32 consecutive outputs (m, n): sums the FFN/16 partials in a fixed order (deterministic), adds bias,
+//             alpha and the residual.
+constexpr int FFN_UNITS = 16;   // hidden units per CTA
+
+template <int FFN>
+__device__ void phase_ffn_partial(Smem& sm, const float* x, const float* __restrict__ pre_g, const float* __restrict__ pre_b,
+                                  const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ W1,
+                                  const float* __restrict__ b1, const float* __restrict__ W2T, float* P, int M, int tag) {
+  constexpr int NJ = FFN / FFN_UNITS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x;
+  fine_stamp(sm, tag);
+  if (j >= NJ) return;  // (the reduce phase reads sm.fin_* only in CTAs < 8 M <= NJ, which all stage below)
+  // weight loads first: 2 hidden units per warp (2 x 2 float4 per lane), 16 W2T values per thread
+  const int u0 = warp * 2;
+  float4 wv[2][2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int it = 0; it < 2; ++it) wv[c][it] = ldw(W1 + (int64_t)(j * FFN_UNITS + u0 + c) * PD + it * 128 + lane * 4);
+  float w2[FFN_UNITS];
+#pragma unroll
+  for (int u = 0; u < FFN_UNITS; ++u) w2[u] = __ldg(W2T + (int64_t)(j * FFN_UNITS + u) * PD + threadIdx.x);
+  const float bias0 = b1[j * FFN_UNITS + u0], bias1 = b1[j * FFN_UNITS + u0 + 1];
+  stage_ln(sm, x, M, pre_g, pre_b, ln_g, ln_b);
+  __syncthreads();
+  fine_stamp(sm, tag + 1);
+  float acc[2][PMR];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int r = 0; r < PMR; ++r) acc[c][r] = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k = it * 128 + lane * 4;
+#pragma unroll
+    for (int r = 0; r < PMR; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(sm.As + r * PD + k);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        acc[c][r] = fmaf(xv.x, wv[c][it].x, acc[c][r]);
+        acc[c][r] = fmaf(xv.y, wv[c][it].y, acc[c][r]);
+        acc[c][r] = fmaf(xv.z, wv[c][it].z, acc[c][r]);
+        acc[c][r] = fmaf(xv.w, wv[c][it].w, acc[c][r]);
+      }
+    }
+  }
+  // 16 row sums per unit across the warp (same halving tree as phase_gemm): even lane 2m ends with row m
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1_ = lane & 2;
+    float w8[8], w4[4], w2r[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float send = b4 ? acc[c][i] : acc[c][i + 8];
+      float keep = b4 ? acc[c][i + 8] : acc[c][i];
+      w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float send = b3 ? w8[i] : w8[i + 4];
+      float keep = b3 ? w8[i + 4] : w8[i];
+      w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = b2 ? w4[i] : w4[i + 2];
+      float keep = b2 ? w4[i + 2] : w4[i];
+      w2r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    float send = b1_ ? w2r[0] : w2r[1];
+    float keep = b1_ ? w2r[1] : w2r[0];
+    float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    float v = w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
+    if ((lane & 1) == 0) {
+      v += c ? bias1 : bias0;
+      sm.hs[lane >> 1][u0 + c] = v / (1.0f + expf(-v));  // SiLU
+    }
+  }
+  __syncthreads();
+  fine_stamp(sm, tag + 2);
+  // rank-16 update: thread n owns output column n for all rows
+  float* Pj = P + (int64_t)j * PMR * PD;
+  for (int m = 0; m < M; ++m) {
+    float a = 0.f;
+#pragma unroll
+    for (int u4 = 0; u4 < FFN_UNITS / 4; ++u4) {
+      const float4 hv = *reinterpret_cast<const float4*>(&sm.hs[m][u4 * 4]);
+      a = fmaf(hv.x, w2[u4 * 4], a);
+      a = fmaf(hv.y, w2[u4 * 4 + 1], a);
+      a = fmaf(hv.z, w2[u4 * 4 + 2], a);
+      a = fmaf(hv.w, w2[u4 * 4 + 3], a);
+    }
+    Pj[m * PD + threadIdx.x] = a;
+  }
+  fine_stamp(sm, tag + 3);
+}
+
+// x[m][n] = res(x[m][n]) + alpha * (sum_j P[j][m][n] + b2[n]); res = LN_pre when pre_g != nullptr (row statistics in sm.fin_*
+// from this CTA's own staging in phase A).  CTA c owns the 32 consecutive outputs starting at 32 c.
+template <int FFN>
+__device__ void phase_ffn_reduce(Smem& sm, float* x, const float* P, const float* __restrict__ b2, float alpha,
+                                 const float* __restrict__ pre_g, const float* __restrict__ pre_b, int M, int tag) {
+  constexpr int NJ = FFN / FFN_UNITS;
+  static_assert(NJ % PW == 0, "partials split evenly over the warps");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  fine_stamp(sm, tag);
+  const int o = blockIdx.x * 32 + lane;
+  if (blockIdx.x * 32 >= M * PD) return;   // (CTA-uniform)
+  float s = 0.f;
+  float v[NJ / PW];
+#pragma unroll
+  for (int i = 0; i < NJ / PW; ++i) v[i] = P[(int64_t)(warp + i * PW) * PMR * PD + o];  // plain loads: written by other CTAs before the barrier
+#pragma unroll
+  for (int i = 0; i < NJ / PW; ++i) s += v[i];
+  sm.rsum[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float t = sm.rsum[0][lane];
+#pragma unroll
+    for (int w = 1; w < PW; ++w) t += sm.rsum[w][lane];
+    const int m = o / PD, n = o - m * PD;
+    float r = x[o];
+    if (pre_g != nullptr) r = (r - sm.fin_mean[m]) * sm.fin_rstd[m] * pre_g[n] + pre_b[n];
+    x[o] = alpha * (t + b2[n]) + r;
+  }
+  fine_stamp(sm, tag + 1);
+}
+
 // rel-pos attention for the active rows: one CTA per (row, head) task
 __device__ void phase_attention(Smem& sm, const float* q, const float* kc, const float* vc, const float* __restrict__ pos, int Tpos,
                                 const float* __restrict__ bias_u, const float* __restrict__ bias_v, float* out, int nA, int a0, int T, int D,
@@ -526,7 +662,8 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
                                                                           float* hid, float* qb, float* att, float* dw, float* kc_all,
                                                                           float* vc_all, float* gc_all, int nA, int a0, int T, int H, int Tpos,
                                                                           int chunk, int conv_chunk, int dw_k, unsigned long long* ts,
-                                                                          unsigned* bar_ctr, unsigned bar_target, int prefetch) {
+                                                                          unsigned* bar_ctr, unsigned bar_target, int prefetch,
+                                                                          float* ffn_scratch) {
   constexpr int D = PD;
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) Smem sm;
@@ -567,12 +704,19 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
     float* gc = gc_all + (size_t)li * Tpos * D;
     GemmEpi e;
     // x = x + 0.5 * W2(SiLU(W1 LN(x)))
+    if (ffn_scratch != nullptr) {
+      phase_ffn_partial<FFN>(sm, x, pre_g, pre_b, L.ffn1_g, L.ffn1_b, L.ffn1_w1, L.ffn1_b1, L.ffn1_w2t, ffn_scratch, nA, 10);
+      PHASE_END(15);
+      phase_ffn_reduce<FFN>(sm, x, ffn_scratch, L.ffn1_b2, 0.5f, pre_g, pre_b, nA, 20);
+      PHASE_END(25);
+    } else {
     e = GemmEpi(); e.bias = L.ffn1_b1; e.act = ACT_SILU; e.out = hid; e.ldo = FFN;
     phase_gemm<4, false, 2, D, STAGE_LN>(sm, x, pre_g, pre_b, L.ffn1_g, L.ffn1_b, L.ffn1_w1, nA, FFN, e, nullptr, 10);
     PHASE_END(15);
     e = GemmEpi(); e.bias = L.ffn1_b2; e.alpha = 0.5f; e.out = x; e.ldo = D; e.residual = true; e.res_ln_g = pre_g; e.res_ln_b = pre_b;
     phase_gemm<2, false, 8, FFN, STAGE_NONE>(sm, hid, nullptr, nullptr, nullptr, nullptr, L.ffn1_w2, nA, D, e, nullptr, 20);
     PHASE_END(25);
+    }
     // q -> qb, k / v -> cache rows a0..
     e = GemmEpi(); e.bias = L.bqkv; e.out = qb; e.ldo = D; e.split_n = D; e.out2 = kc + (size_t)a0 * D; e.ldo2 = D; e.out3 = vc + (size_t)a0 * D; e.ldo3 = D;
     phase_gemm<2, false, 2, D, STAGE_LN>(sm, x, nullptr, nullptr, L.attn_g, L.attn_b, L.wqkv, nA, 3 * D, e, nullptr, 30);
@@ -591,12 +735,19 @@ __global__ void __launch_bounds__(PT, 1) encoder_layers_persistent_kernel(const 
     e = GemmEpi(); e.bias = L.pw2_b; e.out = x; e.ldo = D; e.residual = true;
     phase_gemm<1, false, 2, D, STAGE_COPY>(sm, dw, nullptr, nullptr, nullptr, nullptr, L.pw2, nA, D, e, nullptr, 70);
     PHASE_END(75);
+    if (ffn_scratch != nullptr) {
+      phase_ffn_partial<FFN>(sm, x, nullptr, nullptr, L.ffn2_g, L.ffn2_b, L.ffn2_w1, L.ffn2_b1, L.ffn2_w2t, ffn_scratch, nA, 80);
+      PHASE_END(85);
+      phase_ffn_reduce<FFN>(sm, x, ffn_scratch, L.ffn2_b2, 0.5f, nullptr, nullptr, nA, 90);
+      PHASE_END(95);
+    } else {
     e = GemmEpi(); e.bias = L.ffn2_b1; e.act = ACT_SILU; e.out = hid; e.ldo = FFN;
     phase_gemm<4, false, 2, D, STAGE_LN>(sm, x, nullptr, nullptr, L.ffn2_g, L.ffn2_b, L.ffn2_w1, nA, FFN, e, nullptr, 80);
     PHASE_END(85);
     e = GemmEpi(); e.bias = L.ffn2_b2; e.alpha = 0.5f; e.out = x; e.ldo = D; e.residual = true;
     phase_gemm<2, false, 8, FFN, STAGE_NONE>(sm, hid, nullptr, nullptr, nullptr, nullptr, L.ffn2_w2, nA, D, e, nullptr, 90);
     PHASE_END(95);
+    }
   }
 #undef PHASE_END
 #undef GRID_SYNC
@@ -611,7 +762,8 @@ bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, i
 
 int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
-                              unsigned long long* ts, unsigned* bar_ctr, unsigned* bar_target_host, int prefetch, cudaStream_t st) {
+                              unsigned long long* ts, unsigned* bar_ctr, unsigned* bar_target_host, int prefetch, float* ffn_scratch,
+                              cudaStream_t st) {
   ++g_launches;
   (void)D;
   (void)FFN;
@@ -624,9 +776,10 @@ int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, floa
   const int grid = current_device_sms();
   if (grid <= 0) return -1;
   unsigned bar_target = bar_target_host ? *bar_target_host : 0u;
+  if (grid < 2048 / FFN_UNITS) ffn_scratch = nullptr;  // the fused FFN phases give every hidden-unit group its own CTA
   void* args[] = {(void*)&layers_dev, (void*)&n_layers, (void*)&x, (void*)&hid, (void*)&qb, (void*)&att, (void*)&dw, (void*)&kc, (void*)&vc,
                   (void*)&gc, (void*)&nA, (void*)&a0, (void*)&T, (void*)&H, (void*)&Tpos, (void*)&chunk, (void*)&conv_chunk, (void*)&dw_k,
-                  (void*)&ts, (void*)&bar_ctr, (void*)&bar_target, (void*)&prefetch};
+                  (void*)&ts, (void*)&bar_ctr, (void*)&bar_target, (void*)&prefetch, (void*)&ffn_scratch};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(PT), args, 0, st);
   if (e != cudaSuccess) return -2;
   if (bar_ctr != nullptr && bar_target_host != nullptr) *bar_target_host += (unsigned)grid * (unsigned)(9 * n_layers + (ts != nullptr ? 2 : 0));

@@ -14,6 +14,7 @@ struct PersistLayer {  // device pointers of one Conformer layer (fp32, layouts 
   const float *conv_g, *conv_b, *pw1, *pw1_b, *dw_w, *bn_scale, *bn_shift, *pw2, *pw2_b;
   const float *ffn2_g, *ffn2_b, *ffn2_w1, *ffn2_b1, *ffn2_w2, *ffn2_b2;
   const float *fin_g, *fin_b;
+  const float *ffn1_w2t, *ffn2_w2t;   // W2 transposed [FFN][D] (fused FFN phases of kernels_persist.cu)
 };
 
 bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, int dw_k);
@@ -21,7 +22,8 @@ bool encoder_layers_persistent_supported(int nA, int D, int FFN, int H, int T, i
 int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, float* x, float* hid, float* qb, float* att, float* dw, float* kc,
                               float* vc, float* gc, int nA, int a0, int T, int D, int FFN, int H, int Tpos, int chunk, int conv_chunk, int dw_k,
                               unsigned long long* timestamps_or_null, unsigned* barrier_counter_dev_or_null,
-                              unsigned* barrier_target_host, int prefetch /*0 off, 1 next layer, 2 also layer 0*/, cudaStream_t st);
+                              unsigned* barrier_target_host, int prefetch /*0 off, 1 next layer, 2 also layer 0*/,
+                              float* ffn_scratch_or_null /* [FFN/16][16][D]: fused FFN phases; nullptr = W1 / W2 phases */, cudaStream_t st);
 
 // ---- MT decoder, single-token greedy steps (kernels_persist_mt.cu)
 struct MtLayerP {  // device pointers of one pre-LN decoder layer (fp32, [N][K] weights)
@@ -44,5 +46,11 @@ bool mt_decode_persistent_supported(int dim, int ffn, int heads, int vocab, int 
 // enqueue `nsteps` greedy steps starting with the token at position step0; returns 0, or < 0 if the launch was refused
 int mt_decode_persistent(const MtDecodeParams& P, const MtLayerP* layers_dev, int step0, int nsteps, int max_len, int T,
                          unsigned* barrier_counter_dev, unsigned* barrier_target_host, cudaStream_t st);
+
+// ---- MT decoder, prefix pass over M <= 64 rows (kernels_persist_mtp.cu): fills self-attention cache rows 0 .. M-1 and feature
+// rows 0 .. M-1 from P.tok[0 .. M-1]; P.x / P.q / P.attn hold M x dim floats, P.hid M x ffn
+bool mt_prefix_persistent_supported(int dim, int ffn, int heads, int M, int T);
+int mt_prefix_persistent(const MtDecodeParams& P, const MtLayerP* layers_dev, int M, int T, unsigned* barrier_counter_dev,
+                         unsigned* barrier_target_host, cudaStream_t st);
 
 }  // namespace ss

@@ -70,6 +70,7 @@ def load_library() -> ctypes.CDLL:
     lib.ss_encoder_stream_step.argtypes = [vp, vp, vp, i32, vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.ss_ctc_greedy.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
     lib.ss_ctc_greedy_rows.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
+    lib.ss_ctc_greedy_pair.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     lib.ss_mt_greedy.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, vp, i32, ctypes.POINTER(i32), vp]
     lib.ss_mt_stable_rows.argtypes = [vp, i32]
     lib.ss_mt_incremental_reset.argtypes = [vp]
@@ -90,6 +91,11 @@ def load_library() -> ctypes.CDLL:
     lib.ss_launch_count.argtypes = [vp]
     lib.ss_launch_count.restype = i64
     lib.ss_async_error.argtypes = [vp]
+    lib.ss_pool_create.argtypes = [vp, i32, i32]
+    lib.ss_pool_reset.argtypes = [vp, i32]
+    lib.ss_pool_push_audio.argtypes = [vp, vp, i32, vp, i32]
+    lib.ss_pool_info.argtypes = [vp, i32, ctypes.POINTER(i64), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    lib.ss_pool_step.argtypes = [vp, vp, i32, vp, i32, vp, i64, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -98,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_ctc_greedy_rows", "ss_mt_greedy",
     "ss_mt_features", "ss_mt_stable_rows", "ss_t2u_unit_decode", "ss_unit_position_row", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
-    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count", "ss_async_error", "ss_mt_incremental_reset", "ss_mt_greedy_incremental",
+    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count", "ss_async_error", "ss_mt_incremental_reset", "ss_mt_greedy_incremental", "ss_ctc_greedy_pair", "ss_pool_create", "ss_pool_reset", "ss_pool_push_audio", "ss_pool_info", "ss_pool_step",
 ]
 
 
@@ -185,6 +191,8 @@ class Engine:
         self.set_option("umma_min_channels", int(os.environ.get("SS_UMMA_MIN_CHANNELS", "16")))
         self.set_option("persistent_encoder", int(os.environ.get("SS_PERSISTENT_ENCODER", "1")))
         self.set_option("persistent_mt", int(os.environ.get("SS_PERSISTENT_MT", "1")))
+        self.set_option("persistent_ffn_fused", int(os.environ.get("SS_PERSISTENT_FFN_FUSED", "1")))
+        self.set_option("persistent_mt_prefix", int(os.environ.get("SS_PERSISTENT_MT_PREFIX", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))
         self.set_option("unit_grouped", int(os.environ.get("SS_UNIT_GROUPED", "1")))
         self.set_option("vocoder_graph", int(os.environ.get("SS_VOCODER_GRAPH", "0")))
@@ -323,11 +331,16 @@ class Engine:
         assert enc.is_cuda and enc.is_contiguous() and enc.dim() == 2
         T = enc.shape[0]
         W = 2 * T + 2
-        out = torch.zeros(2 * W, dtype=torch.int64, device=self.device)  # per head: [count | tokens[T] | index (int32 pairs)]
-        for hd in (0, 1):
-            o = out[hd * W:(hd + 1) * W]
-            self._check(self.lib.ss_ctc_greedy_rows(self._h, self._stream(), hd, enc.data_ptr(), T, int(row0s[hd]), argmaxes[hd].data_ptr(),
-                                                    o[1:1 + T].data_ptr(), o[1 + T:].view(torch.int32)[:T].data_ptr(), o[:1].view(torch.int32).data_ptr()))
+        if int(row0s[0]) == int(row0s[1]):  # one projection over both heads + one arg-max / collapse kernel
+            out = torch.empty(2 * W, dtype=torch.int64, device=self.device)  # per head: [count | tokens[T] | index (int32 pairs)]
+            self._check(self.lib.ss_ctc_greedy_pair(self._h, self._stream(), enc.data_ptr(), T, int(row0s[0]), argmaxes[0].data_ptr(),
+                                                    argmaxes[1].data_ptr(), out.data_ptr()))
+        else:
+            out = torch.zeros(2 * W, dtype=torch.int64, device=self.device)
+            for hd in (0, 1):
+                o = out[hd * W:(hd + 1) * W]
+                self._check(self.lib.ss_ctc_greedy_rows(self._h, self._stream(), hd, enc.data_ptr(), T, int(row0s[hd]), argmaxes[hd].data_ptr(),
+                                                        o[1:1 + T].data_ptr(), o[1 + T:].view(torch.int32)[:T].data_ptr(), o[:1].view(torch.int32).data_ptr()))
         host = out.cpu()
         res = []
         for hd in (0, 1):
@@ -450,6 +463,49 @@ class Engine:
         buf = (ctypes.c_double * 3)()
         self._check(self.lib.ss_debug_copy(self._h, b"persist_time", buf, ctypes.sizeof(buf)))
         return float(buf[0]), int(buf[1]), float(buf[2])
+
+    # ------------------------------------------------------------------ multi-stream pool (ss_pool_*)
+    def pool_create(self, n_slots: int, max_seconds: int = 60):
+        self._check(self.lib.ss_pool_create(self._h, int(n_slots), int(max_seconds)))
+        self._pool_slots = int(n_slots)
+        self._pool_out = None
+
+    def pool_reset(self, slot: int):
+        self._check(self.lib.ss_pool_reset(self._h, int(slot)))
+
+    def pool_push_audio(self, slot: int, samples: torch.Tensor):
+        """samples: fp32 CPU tensor (contiguous); appended to the slot's device audio"""
+        assert samples.dtype == torch.float32 and not samples.is_cuda and samples.is_contiguous()
+        self._check(self.lib.ss_pool_push_audio(self._h, self._stream(), int(slot), samples.data_ptr(), samples.numel()))
+
+    def pool_info(self, slot: int):
+        na, nf, tf = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        enc, feats = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self.lib.ss_pool_info(self._h, int(slot), ctypes.byref(na), ctypes.byref(nf), ctypes.byref(tf), ctypes.byref(enc), ctypes.byref(feats)))
+        return {"n_audio": na.value, "n_feat": nf.value, "T_final": tf.value, "enc_out_ptr": enc.value, "feats_ptr": feats.value}
+
+    def pool_step(self, slots: Sequence[int], ctc_heads: int = 1, max_rows: int = 1024):
+        """One batched streaming step (fbank -> encoder -> CTC heads) of the listed slots.  Returns a list, per slot, of
+        {"T", "T_final", "ctc": [(tokens, index) per head]} with ONE device->host copy for all streams."""
+        n = len(slots)
+        cap = n * max(ctc_heads, 1) * (2 * max_rows + 2)
+        if self._pool_out is None or self._pool_out.numel() < cap:
+            self._pool_out = torch.empty(cap, dtype=torch.int64, device=self.device)
+        sl = (ctypes.c_int32 * n)(*[int(x) for x in slots])
+        T, Tf, off = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)(), (ctypes.c_int64 * n)()
+        self._check(self.lib.ss_pool_step(self._h, self._stream(), n, sl, int(ctc_heads), self._pool_out.data_ptr(), self._pool_out.numel(), T, Tf, off))
+        res = [{"T": int(T[i]), "T_final": int(Tf[i]), "ctc": []} for i in range(n)]
+        if ctc_heads:
+            used = int(off[n - 1]) + ctc_heads * (2 * int(T[n - 1]) + 2)
+            host = self._pool_out[:used].cpu()
+            for i in range(n):
+                Ti = int(T[i])
+                for hd in range(ctc_heads):
+                    o = int(off[i]) + hd * (2 * Ti + 2)
+                    row = host[o:o + 2 * Ti + 2]
+                    cnt = int(row[:1].view(torch.int32)[0])
+                    res[i]["ctc"].append((row[1:1 + cnt].tolist(), row[1 + Ti:].view(torch.int32)[:cnt].tolist()))
+        return res
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.ss_set_option(self._h, name.encode(), int(value)))

@@ -581,3 +581,46 @@ def test_grid_barrier_error_flag_is_clear_after_the_suite(full):
     """ss_async_error: no persistent-kernel grid barrier timed out during the tests above on this handle."""
     cfg, e, o = full
     e.check_async_error()
+
+
+def test_ctc_pair_equals_single_heads(eng3, gold):
+    """ss_ctc_greedy_pair (one [rows][2V] projection + fused arg-max / collapse with the last-block ticket) against the
+    single-head entry point and the reference fixture, full sequence and incremental (row0 > 0) forms."""
+    g = gold["decoders"]
+    enc = cuda(g["enc_out"])
+    T = enc.shape[0]
+    am = [torch.zeros(T, dtype=torch.int64, device="cuda") for _ in range(2)]
+    for row0 in (0, T - 9, T):
+        if row0 > 0:  # rows below row0 must already hold their arg-max
+            for hd in (0, 1):
+                am[hd][:row0] = eng3.ctc_greedy(hd, enc)["argmax"][:row0]
+                am[hd][row0:] = -7
+        a, b = eng3.ctc_greedy_rows_pair(enc, [row0, row0], am)
+        for hd, name, (toks, idx) in ((0, "source_unigram", a), (1, "ctc_target_unigram", b)):
+            assert am[hd].tolist() == g[f"ctc_{name}_argmax"].tolist(), (row0, name)
+            assert toks == g[f"ctc_{name}_tokens"].tolist() and idx == g[f"ctc_{name}_index"].tolist(), (row0, name)
+
+
+@pytest.mark.parametrize("option", ["persistent_ffn_fused", "persistent_mt_prefix"])
+def test_persistent_kernel_variants_agree(full, option):
+    """A / B of the round-2 persistent-kernel restructurings against the paths they replace: fused FFN phases (hidden-split
+    rank-16 updates + deterministic reduce) vs separate W1 / W2 phases in the encoder step; cooperative MT prefix pass vs the
+    per-kernel prefix pass.  Same function, different summation order."""
+    cfg, e, o = full
+    e.set_chunk(8, 8)
+    feats = e.fbank(cuda(synth.make_audio(3.0, seed=5)))
+    outs = {}
+    for v in (0, 1):
+        e.set_option(option, v)
+        buf = torch.zeros(1024, cfg.enc_dim, device="cuda")
+        e.encoder_stream_reset()
+        T = 0
+        for F in list(range(30, feats.shape[0], 32)) + [feats.shape[0]]:
+            T, _ = e.encoder_stream_step(feats[:F].contiguous(), buf)
+        toks, mt_feats = e.mt_greedy(buf[:T].contiguous(), [17, 256, 4099, 31, 5, 977, 1203, 44], 3)
+        outs[v] = (buf[:T].clone(), toks, mt_feats.clone())
+    e.set_option(option, 1)
+    d_enc, d_mt = maxdiff(outs[0][0], outs[1][0]), maxdiff(outs[0][2], outs[1][2])
+    report("persistent_variant_" + option, enc=d_enc, mt_feats=d_mt)
+    assert outs[0][1] == outs[1][1] and d_enc < 2e-5 and d_mt < 1e-4, (d_enc, d_mt)
+    e.encoder_stream_reset()
