@@ -82,6 +82,16 @@ int64_t ss_fbank_num_frames(int64_t n_samples);
 int ss_fbank(ss_engine* h, void* stream, const float* samples_dev, int64_t n_samples, int64_t frame0, int64_t n_frames,
              float* out_dev);
 
+/* ---- F1, wire format: convert_waveform(..., to_sample_rate=16000) (fairseq/fairseq/data/audio/audio_utils.py:53-62), called by
+ * OnlineFeatureExtractor with sr = 48000 (agent:32-35,66).  The reference resamples with sox `rate` through torchaudio.sox_effects
+ * (third party, not in this image); here: windowed-sinc decimation by 3 with the filter of torchaudio.functional.resample
+ * (Hann-windowed sinc, lowpass_filter_width 6, rolloff 0.99, 41 taps), loaded as "__const__.resample_3to1".
+ * out_dev[i] for i in [out0, out0 + n_out) (absolute 16 kHz sample index) from in_dev[0 .. n_in) at 48 kHz.
+ * ss_resample_out_len: 16 kHz samples that are FINAL given n 48 kHz samples so far (filter support complete), or the whole-signal
+ * length ceil(n / 3) once the source is finished -- the streaming agent only consumes final samples. enqueue only */
+int64_t ss_resample_out_len(int64_t n_in_48k, int finished);
+int ss_resample_48k_to_16k(ss_engine* h, void* stream, const float* in_dev, int64_t n_in, int64_t out0, int64_t n_out, float* out_dev);
+
 /* ---- E1-E6: ChunkS2SConformerEncoder.forward (chunk_unity/models/s2t_conformer.py:111-163) -------------- */
 /* encoder frames for F fbank frames: two stride-2 convs (chunk_unity/modules/convolution.py:75-79) */
 int64_t ss_encoder_out_frames(int64_t n_fbank_frames);

@@ -88,16 +88,29 @@ def load_vocoder(args, cfg: ModelConfig):
 
 
 class _DeviceAudio:
-    """states.source mirrored on the device; only new samples cross PCIe."""
+    """states.source mirrored on the device; only new samples cross PCIe.  With a 48 kHz source (the reference's default,
+    agent:32-35: OnlineFeatureExtractor resamples states.source to 16 kHz on every call) the raw samples are kept at 48 kHz and
+    the 16 kHz signal the fbank reads is extended on the device (ss_resample_48k_to_16k): only samples whose filter support is
+    complete are produced while the source is open, the rest when it finishes."""
 
-    def __init__(self, device, capacity=16000 * 60):
-        self.buf = torch.zeros(capacity, dtype=torch.float32, device=device)
+    def __init__(self, device, capacity=16000 * 60, engine=None, sample_rate=SAMPLE_RATE):
+        self.rate = sample_rate
+        self.engine = engine
+        self.buf = torch.zeros(capacity * (sample_rate // SAMPLE_RATE), dtype=torch.float32, device=device)
         self.n = 0
+        if sample_rate != SAMPLE_RATE:
+            self.buf16 = torch.zeros(capacity, dtype=torch.float32, device=device)
+            self.n16 = 0
 
-    def sync(self, source: List[float]):
+    def reset(self):
+        self.n = 0
+        if self.rate != SAMPLE_RATE:
+            self.n16 = 0
+
+    def sync(self, source: List[float], finished: bool = False):
         n = len(source)
         if n < self.n:
-            self.n = 0
+            self.reset()
         if n > self.buf.numel():
             nb = torch.zeros(max(n * 2, self.buf.numel() * 2), dtype=torch.float32, device=self.buf.device)
             nb[: self.n] = self.buf[: self.n]
@@ -106,13 +119,23 @@ class _DeviceAudio:
             new = torch.tensor(source[self.n:], dtype=torch.float32).pin_memory()
             self.buf[self.n:n].copy_(new, non_blocking=True)
             self.n = n
-        return self.buf[:n]
+        if self.rate == SAMPLE_RATE:
+            return self.buf[:n]
+        n16 = self.engine.resample_out_len(n, finished)
+        if n16 > self.buf16.numel():
+            nb = torch.zeros(max(n16 * 2, self.buf16.numel() * 2), dtype=torch.float32, device=self.buf16.device)
+            nb[: self.n16] = self.buf16[: self.n16]
+            self.buf16 = nb
+        if n16 > self.n16:
+            self.engine.resample_48k_to_16k(self.buf[:n], self.buf16, self.n16, n16 - self.n16)
+            self.n16 = n16
+        return self.buf16[: self.n16]
 
 
 class _EngineAgentMixin:
     def _init_engine(self, args, need_vocoder: bool):
-        if args.sample_rate != SAMPLE_RATE:
-            raise NotImplementedError("the B200 front-end takes 16 kHz input; resample upstream (SURVEY.md §8f.3)")
+        if args.sample_rate not in (SAMPLE_RATE, ORG_SAMPLE_RATE):
+            raise NotImplementedError("the B200 front-end takes 16 kHz or 48 kHz input (the reference's two cases: agent:32-35)")
         override = getattr(args, "checkpoint_override", None)  # (cfg, model state dict, vocoder state dict, gcmvn) already in memory
         if override is not None:                                # (bench.py: the NCCL-broadcast copy of rank 0's checkpoint)
             cfg, sd, vsd_o, gcmvn = override
@@ -132,7 +155,7 @@ class _EngineAgentMixin:
         dev = getattr(args, "device_index", 0)
         self.engine = Engine(cfg, sd, vsd, gcmvn, device=dev, max_enc_frames=getattr(args, "max_enc_frames", 1024))
         self.torch_device = self.engine.device
-        self.audio = _DeviceAudio(self.torch_device)
+        self.audio = _DeviceAudio(self.torch_device, engine=self.engine, sample_rate=args.sample_rate)
         self.feat_cache = torch.zeros(6000, cfg.feat_dim, dtype=torch.float32, device=self.torch_device)
         self.n_feat = 0
         self._resident = None
@@ -165,7 +188,7 @@ class _EngineAgentMixin:
     def _reset_caches(self):
         """new utterance: drop the device audio mirror and the fbank frame cache"""
         if hasattr(self, "audio"):
-            self.audio.n = 0
+            self.audio.reset()
             self.n_feat = 0
             self.engine.encoder_stream_reset()
         self._enc_final = 0
@@ -176,7 +199,7 @@ class _EngineAgentMixin:
         if self._resident is not None:  # bench "value" leg: the utterance already lives in HBM
             samples = self._resident[0][: self._resident[1]]
         else:
-            samples = self.audio.sync(self.states.source)
+            samples = self.audio.sync(self.states.source, self.states.source_finished)
         F = self.engine.num_fbank_frames(samples.numel())
         if F < self.n_feat:
             self.n_feat = 0

@@ -63,3 +63,25 @@ def mel_bank(num_bins: int = 80, padded: int = 512, sample_freq: float = 16000.0
     down = (right - melf) / (right - center)
     bins = torch.max(torch.zeros(1), torch.min(up, down))
     return torch.nn.functional.pad(bins, (0, 1)).contiguous()
+
+
+def resample_kernel_3to1(lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Windowed-sinc decimation filter 48 kHz -> 16 kHz (orig / gcd = 3, new / gcd = 1): the kernel of
+    torchaudio.functional.resample's default method (sinc_interp_hann; torchaudio/functional/functional.py
+    _get_sinc_resample_kernel), restated.  Returns (kernel [2 * width + 3], width): out[i] = sum_k kernel[k] * x[3 i + k - width].
+
+    The reference resamples with sox's `rate` effect (fairseq/fairseq/data/audio/audio_utils.py:53-62 through
+    torchaudio.sox_effects, which this image does not have): a different (longer) filter; see DESIGN.md."""
+    orig, new = 3, 1
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=torch.float64)[:, None, None] / new + idx
+    t = t * base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    scale = base_freq / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), t.sin() / t)
+    kernels = kernels * window * scale
+    return kernels.to(torch.float32).view(-1).contiguous(), width

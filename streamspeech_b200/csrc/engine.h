@@ -132,6 +132,8 @@ struct ss_engine {
   float* window = nullptr;
   float* cmvn_mean = nullptr;
   float* cmvn_std = nullptr;
+  float* resample_h = nullptr;      // 48 kHz -> 16 kHz decimation filter ("__const__.resample_3to1"), taps / half width below
+  int resample_taps = 0, resample_width = 0;
   int* mask_pad_unk = nullptr;      // device [3] = {pad, unk, eos}
   int* mask_pad_eos = nullptr;      // device [2] = {pad, eos}
   // vocoder

@@ -260,6 +260,22 @@ int ss_fbank(ss_engine* h, void* stream, const float* samples_dev, int64_t n_sam
   return check_launch(h, "ss_fbank");
 }
 
+int64_t ss_resample_out_len(int64_t n_in_48k, int finished) {
+  if (n_in_48k <= 0) return 0;
+  if (finished) return (n_in_48k + 2) / 3;                 // ceil(n / 3): the whole-signal length of torchaudio.functional.resample
+  const int64_t last = (n_in_48k - 22) / 3;                // outputs whose 41-tap support [3i - 19, 3i + 21] is complete
+  return n_in_48k >= 22 ? last + 1 : 0;
+}
+
+int ss_resample_48k_to_16k(ss_engine* h, void* stream, const float* in_dev, int64_t n_in, int64_t out0, int64_t n_out, float* out_dev) {
+  if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
+  if (!h->resample_h) return h->fail(SS_ERR_MISSING, "__const__.resample_3to1 was not loaded");
+  if (n_out <= 0) return SS_OK;
+  if (out0 < 0 || n_in < 0 || out0 + n_out > (n_in + 2) / 3) return h->fail(SS_ERR_INVALID, "resample output range exceeds ceil(n_in / 3)");
+  resample_3to1(in_dev, n_in, h->resample_h, h->resample_taps, h->resample_width, out0, (int)n_out, out_dev, S(stream));
+  return check_launch(h, "ss_resample_48k_to_16k");
+}
+
 int ss_encoder_forward(ss_engine* h, void* stream, const float* feats_dev, const int32_t* lengths_host, int B, int F, float* out_dev) {
   if (h) route_from(h);
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;

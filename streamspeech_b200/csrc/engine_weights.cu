@@ -180,6 +180,13 @@ void finalize_impl(ss_engine* h) {
       h->cmvn_mean = upload(h, get(h, "__const__.gcmvn_mean").data);
       h->cmvn_std = upload(h, get(h, "__const__.gcmvn_std").data);
     }
+    if (h->host.count("__const__.resample_3to1")) {
+      const HostTensor& r = get(h, "__const__.resample_3to1");
+      if (r.numel() < 4 || r.numel() > 64 || (r.numel() - 3) % 2 != 0) throw std::runtime_error("bad __const__.resample_3to1");
+      h->resample_h = upload(h, r.data);
+      h->resample_taps = (int)r.numel();
+      h->resample_width = ((int)r.numel() - 3) / 2;
+    }
     int m[3] = {c.pad, c.unk, c.eos};
     h->mask_pad_unk = dev_alloc<int>(h, 3);
     cudaMemcpy(h->mask_pad_unk, m, sizeof(m), cudaMemcpyHostToDevice);

@@ -150,6 +150,8 @@ void expand_frames(const float* emb /*[U][C]*/, const int* cumsum /*[U+1]*/, int
 void conv_post_tanh(const float* x, int L, int C, const float* w /*[k][C]*/, float bias, int k, float pre_slope, float* out,
                     cudaStream_t st);
 void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
+// 48 kHz -> 16 kHz: out[i] = sum_k h[k] * x[3 i + k - width] for i in [i0, i0 + n) (taps <= 64); out is indexed by absolute i
+void resample_3to1(const float* x, int64_t n_in, const float* h, int taps, int width, int64_t i0, int n, float* out, cudaStream_t st);
 // out = c + (b + a), elementwise (n % 4 == 0): joins the vocoder's three resblock streams in the reference's summation order
 void add3_f32(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t st);
 

@@ -489,6 +489,36 @@ void ctc_argmax_collapse_pair(const float* logits, int ld, int V, int n_new, int
              blank, pad, am0, am1, out, out_stride, ticket);
 }
 
+// out[i] = sum_k h[k] * x[3 i + k - width], i in [i0, i0 + n): 48 kHz -> 16 kHz windowed-sinc decimation (x zero outside [0, n_in))
+__global__ void __launch_bounds__(256) resample_3to1_kernel(const float* __restrict__ x, int64_t n_in, const float* __restrict__ h, int taps,
+                                                           int width, int64_t i0, int n, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float hs[64];
+  __shared__ float xs[3 * 256 + 64];
+  const int tid = threadIdx.x;
+  if (tid < taps) hs[tid] = h[tid];
+  const int64_t ib = i0 + (int64_t)blockIdx.x * 256;       // first output of this block
+  const int64_t base = 3 * ib - width;                      // first input sample the block touches
+  const int span = 3 * 255 + taps;                          // inputs touched by 256 outputs
+  for (int j = tid; j < span; j += 256) {
+    const int64_t p = base + j;
+    xs[j] = (p >= 0 && p < n_in) ? x[p] : 0.f;
+  }
+  __syncthreads();
+  const int64_t i = ib + tid;
+  if (i >= i0 + n) return;
+  float acc = 0.f;
+  for (int k = 0; k < taps; ++k) acc = fmaf(hs[k], xs[3 * tid + k], acc);
+  out[i] = acc;
+}
+
+void resample_3to1(const float* x, int64_t n_in, const float* h, int taps, int width, int64_t i0, int n, float* out, cudaStream_t st) {
+  ++g_launches;
+  if (n <= 0) return;
+  launch_pdl(resample_3to1_kernel, dim3((n + 255) / 256), dim3(256), 0, st, x, n_in, h, taps, width, i0, n, out);
+}
+
 void gather_rows(const int64_t* idx, int n, int idx_offset, const float* table, int C, float* out, cudaStream_t st) {
   ++g_launches;
   if (n <= 0) return;

@@ -91,6 +91,9 @@ def load_library() -> ctypes.CDLL:
     lib.ss_launch_count.argtypes = [vp]
     lib.ss_launch_count.restype = i64
     lib.ss_async_error.argtypes = [vp]
+    lib.ss_resample_out_len.argtypes = [i64, i32]
+    lib.ss_resample_out_len.restype = i64
+    lib.ss_resample_48k_to_16k.argtypes = [vp, vp, vp, i64, i64, i64, vp]
     lib.ss_pool_create.argtypes = [vp, i32, i32]
     lib.ss_pool_reset.argtypes = [vp, i32]
     lib.ss_pool_push_audio.argtypes = [vp, vp, i32, vp, i32]
@@ -104,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "ss_create", "ss_destroy", "ss_last_error", "ss_version", "ss_load_tensor", "ss_finalize", "ss_set_chunk",
     "ss_fbank_num_frames", "ss_fbank", "ss_encoder_out_frames", "ss_encoder_forward", "ss_encoder_stream_reset", "ss_encoder_stream_step", "ss_ctc_greedy", "ss_ctc_greedy_rows", "ss_mt_greedy",
     "ss_mt_features", "ss_mt_stable_rows", "ss_t2u_unit_decode", "ss_unit_position_row", "ss_vocoder_durations", "ss_vocoder_generate", "ss_vocoder_hop",
-    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count", "ss_async_error", "ss_mt_incremental_reset", "ss_mt_greedy_incremental", "ss_ctc_greedy_pair", "ss_pool_create", "ss_pool_reset", "ss_pool_push_audio", "ss_pool_info", "ss_pool_step",
+    "ss_vocoder_receptive_field", "ss_op_linear", "ss_op_linear_umma", "ss_op_conv1d", "ss_set_option", "ss_debug_copy", "ss_op_layer_norm", "ss_launch_count", "ss_async_error", "ss_mt_incremental_reset", "ss_mt_greedy_incremental", "ss_ctc_greedy_pair", "ss_resample_out_len", "ss_resample_48k_to_16k", "ss_pool_create", "ss_pool_reset", "ss_pool_push_audio", "ss_pool_info", "ss_pool_step",
 ]
 
 
@@ -172,6 +175,7 @@ class Engine:
                     self._load("vocoder." + k, v)
             self._load("__const__.mel_bank", constants.mel_bank())
             self._load("__const__.window", constants.povey_window())
+            self._load("__const__.resample_3to1", constants.resample_kernel_3to1()[0])
             self._load("__const__.enc_pe", constants.rel_pos_table(max_enc_frames, cfg.enc_dim))
             self._load("__const__.mt_pos_table", constants.sinusoidal_table(max_mt_positions + cfg.pad + 2, cfg.mt_dim, cfg.pad))
             self._load("__const__.unit_pos_row", constants.sinusoidal_table(cfg.pad + 4, cfg.unit_dim, cfg.pad)[cfg.pad + 1])
@@ -272,6 +276,14 @@ class Engine:
         if n_frames > 0:
             self._check(self.lib.ss_fbank(self._h, self._stream(), samples.data_ptr(), samples.numel(), frame0, n_frames, out.data_ptr()))
         return out
+
+    def resample_out_len(self, n_in_48k: int, finished: bool) -> int:
+        return int(self.lib.ss_resample_out_len(int(n_in_48k), int(finished)))
+
+    def resample_48k_to_16k(self, x48: torch.Tensor, out16: torch.Tensor, out0: int, n_out: int):
+        """x48: all 48 kHz samples so far (device fp32); writes out16[out0 : out0 + n_out]"""
+        assert x48.is_cuda and out16.is_cuda and x48.is_contiguous() and out16.is_contiguous() and out16.numel() >= out0 + n_out
+        self._check(self.lib.ss_resample_48k_to_16k(self._h, self._stream(), x48.data_ptr(), x48.numel(), int(out0), int(n_out), out16.data_ptr()))
 
     def encoder(self, feats: torch.Tensor, lengths: Optional[Sequence[int]] = None) -> torch.Tensor:
         """feats [B, F, 80] -> [B, T, enc_dim] (batch-major; the reference's encoder_out is the T x B x C transpose)."""

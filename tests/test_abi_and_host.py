@@ -155,3 +155,137 @@ def test_agent_files_load_the_way_simuleval_loads_them():
                      "extra_output_dir", "max_len", "force_finish"):
             assert hasattr(a, flag), (fname, flag)
         assert a.sample_rate == 48000  # the reference's default (agent:32-35)
+
+
+def test_resample_filter_matches_torchaudio():
+    """constants.resample_kernel_3to1 restates torchaudio's windowed-sinc kernel (the oracle of the 48 kHz -> 16 kHz front end)."""
+    import math
+
+    import torch
+    from torchaudio.functional.functional import _get_sinc_resample_kernel
+
+    from streamspeech_b200.constants import resample_kernel_3to1
+
+    k, w = _get_sinc_resample_kernel(48000, 16000, math.gcd(48000, 16000))
+    k2, w2 = resample_kernel_3to1()
+    assert w == w2 == 19 and k2.numel() == 41 and float((k.view(-1) - k2).abs().max()) == 0.0
+
+
+class _FakeEngine:
+    """records the calls the fairseq-surface shims make (CPU test double; no compute)"""
+
+    def __init__(self):
+        import torch
+
+        self.device = torch.device("cpu")
+        self.calls = []
+
+    def set_chunk(self, attn, conv=None):
+        self.calls.append(("set_chunk", attn, conv))
+
+
+def test_fairseq_surface_attribute_pokes_reach_the_engine():
+    """agent:395-413: the agent assigns encoder.chunk_size and the conv chunk sizes on the model object; the shims of
+    streamspeech_b200/fairseq_surface.py must translate every assignment into ss_set_chunk with the agent's values."""
+    import sys
+    import types
+
+    import torch
+
+    from streamspeech_b200 import synth
+    from streamspeech_b200.config import ModelConfig
+    from streamspeech_b200.fairseq_surface import B200Encoder, StreamSpeechB200Model, register_with_fairseq
+
+    cfg = ModelConfig()
+    eng = _FakeEngine()
+    enc = B200Encoder(eng, cfg)
+    assert len(enc.conformer_layers) == cfg.enc_layers and len(enc.subsample.conv_layers) == 2
+    # the reference's own lines, verbatim in spirit (agent:404-413)
+    chunk_size = 320 // 40
+    enc.chunk_size = chunk_size
+    chunk_size = 16 if chunk_size >= 16 else 8
+    for conv in enc.subsample.conv_layers:
+        conv.chunk_size = chunk_size
+    for layer in enc.conformer_layers:
+        layer.conv_module.depthwise_conv.chunk_size = chunk_size
+    assert eng.calls[0] == ("set_chunk", 8, 8) and eng.calls[-1] == ("set_chunk", 8, 8)
+    assert enc.chunk_size == 8 and enc.subsample.conv_layers[1].chunk_size == 8
+    # ASR agent rule (speech_to_text.asr agent :361-375): 160 ms -> attention 4, conv min(4, 16) = 4
+    enc.chunk_size = 4
+    for conv in enc.subsample.conv_layers:
+        conv.chunk_size = 4
+    assert eng.calls[-1] == ("set_chunk", 4, 4)
+    # offline model (--chunk-size 999999, N10)
+    enc.chunk_size = 999999
+    assert eng.calls[-1] == ("set_chunk", None, None)
+    # registration with a fairseq that offers the two decorators
+    reg = {}
+    fm = types.ModuleType("fairseq.models")
+    fm.register_model = lambda name: (lambda cls: reg.setdefault("model:" + name, cls))
+    fm.register_model_architecture = lambda m, a: (lambda fn: reg.setdefault("arch:" + a, fn))
+    saved = {k: sys.modules.get(k) for k in ("fairseq", "fairseq.models")}
+    sys.modules["fairseq"] = types.ModuleType("fairseq")
+    sys.modules["fairseq.models"] = fm
+    try:
+        assert register_with_fairseq() and reg["model:streamspeech_b200"] is StreamSpeechB200Model and "arch:streamspeech_b200" in reg
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_checkpoint_files_round_trip(tmp_path):
+    """`--model-path file.pt --config-yaml ... --multitask-config-yaml ... --vocoder g.pt --vocoder-cfg config.json`
+    (agent:355-393, agent/tts/vocoder.py:31-45): everything the agent reads from disk -- fairseq .pt with a "model" entry, gcmvn
+    npz behind the yaml, SPM-style dictionary files behind the multitask yaml, weight-normed vocoder checkpoint + JSON -- comes
+    back as the tensors / config / dictionaries of the synthetic checkpoint it was written from."""
+    import argparse
+    import json
+
+    import numpy as np
+    import torch
+    import yaml
+
+    from streamspeech_b200 import synth
+    from streamspeech_b200.agent import load_streamspeech_checkpoint, load_vocoder
+    from streamspeech_b200.config import ModelConfig
+    from streamspeech_b200.dictionary import Dictionary
+    from streamspeech_b200.engine import remove_weight_norm
+
+    cfg = ModelConfig().tiny()
+    cfg.src_vocab = cfg.tgt_vocab = 64
+    sd = synth.make_model_state_dict(cfg, 0)
+    vsd = synth.make_vocoder_state_dict(cfg.vocoder, 1, weight_norm=True)
+    d = tmp_path
+    torch.save({"model": sd, "cfg": None, "args": None}, d / "model.pt")
+    torch.save({"generator": vsd}, d / "g_00500000")
+    json.dump(cfg.vocoder.to_json_dict(), open(d / "config.json", "w"))
+    g = synth.make_gcmvn(cfg)
+    np.savez(d / "gcmvn.npz", mean=g["mean"], std=g["std"])
+    yaml.safe_dump({"global_cmvn": {"stats_npz_path": str(d / "gcmvn.npz")}, "input_feat_per_channel": 80}, open(d / "config_gcmvn.yaml", "w"))
+    mt = {}
+    for name in ("source_unigram", "ctc_target_unigram", "target_unigram"):
+        sub = d / name
+        sub.mkdir()
+        dic = Dictionary.synthetic(64)
+        with open(sub / "spm_unigram.txt", "w", encoding="utf-8") as f:
+            for sym in dic.symbols[4:]:
+                f.write(f"{sym} 1\n")
+        mt[name] = {"decoder_type": "transformer" if name == "target_unigram" else "ctc", "dict": str(sub / "spm_unigram.txt")}
+    yaml.safe_dump(mt, open(d / "config_mtl.yaml", "w"))
+    args = argparse.Namespace(model_path=str(d / "model.pt"), data_bin=str(d), config_yaml="config_gcmvn.yaml", multitask_config_yaml="config_mtl.yaml",
+                              vocoder=str(d / "g_00500000"), vocoder_cfg=str(d / "config.json"))
+    cfg2, sd2, gc2, dicts = load_streamspeech_checkpoint(args)
+    for k in ("enc_dim", "enc_ffn", "enc_heads", "enc_layers", "dw_kernel", "conv_channels", "conv_kernel", "src_vocab", "tgt_vocab", "mt_dim", "mt_ffn",
+              "mt_layers", "t2u_layers", "unit_dim", "unit_layers", "unit_vocab"):
+        assert getattr(cfg2, k) == getattr(cfg, k), k
+    assert set(sd2) == set(sd) and all(torch.equal(sd2[k], sd[k]) for k in sd)
+    assert np.array_equal(gc2["mean"], g["mean"]) and np.array_equal(gc2["std"], g["std"])
+    assert dicts["target_unigram"].symbols == Dictionary.synthetic(64).symbols and len(dicts["tgt"]) == cfg.unit_vocab
+    vc, vsd2 = load_vocoder(args, cfg2)
+    assert vc.upsample_rates == cfg.vocoder.upsample_rates and vc.dur_hidden == cfg.vocoder.dur_hidden
+    plain = synth.make_vocoder_state_dict(cfg.vocoder, 1, weight_norm=False)
+    folded = remove_weight_norm(vsd2)
+    assert set(folded) == set(plain) and all(float((folded[k] - plain[k]).abs().max()) < 1e-5 for k in plain)

@@ -624,3 +624,99 @@ def test_persistent_kernel_variants_agree(full, option):
     report("persistent_variant_" + option, enc=d_enc, mt_feats=d_mt)
     assert outs[0][1] == outs[1][1] and d_enc < 2e-5 and d_mt < 1e-4, (d_enc, d_mt)
     e.encoder_stream_reset()
+
+
+def test_resample_48k_to_16k_vs_torchaudio(eng3):
+    """f3 wire format: ss_resample_48k_to_16k against torchaudio.functional.resample (the CPU oracle of this front end; the
+    reference's sox `rate` is not available in this image) on whole signals of awkward lengths, and the streaming rule
+    (only samples with complete filter support while the source is open) reproducing the whole-signal result incrementally."""
+    import torchaudio
+
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 21, 22, 23, 480, 15360, 48000 + 1, 160001):
+        x = torch.rand(n, generator=g) * 2 - 1
+        ref = torchaudio.functional.resample(x, 48000, 16000)
+        xd = cuda(x)
+        out = torch.zeros(ref.numel(), device="cuda")
+        assert eng3.resample_out_len(n, True) == ref.numel()
+        # incrementally: chunks of 7001 input samples, final flush at the end
+        done = 0
+        for end in list(range(7001, n, 7001)) + [n]:
+            fin = end == n
+            avail = eng3.resample_out_len(end, fin)
+            if avail > done:
+                eng3.resample_48k_to_16k(xd[:end].contiguous(), out, done, avail - done)
+                done = avail
+        assert done == ref.numel()
+        d = maxdiff(out, ref)
+        assert d < 2e-6, (n, d)
+
+
+def test_s2st_agent_48k_source_equals_16k_agent_on_resampled_audio():
+    """The reference's default: states.source at 48 kHz (agent:32-35,66).  The agent with --sample-rate 48000 must behave like the
+    16 kHz agent fed the resampled signal, call by call."""
+    import torchaudio
+
+    from streamspeech_b200.agent import StreamSpeechS2STAgent
+    from streamspeech_b200.simuleval_compat import SpeechSegment
+
+    x48 = synth.make_audio(9.6, seed=8)[: 3 * 51200]  # any 48 kHz signal: 3.2 s
+    x16 = torchaudio.functional.resample(x48, 48000, 16000)
+    a48 = StreamSpeechS2STAgent(agent_args(sample_rate=48000))
+    a16 = StreamSpeechS2STAgent(agent_args(sample_rate=16000))
+    n = 5120
+    writes = 0
+    for i in range(0, x16.numel(), n):
+        fin = i + n >= x16.numel()
+        s48 = a48.pushpop(SpeechSegment(content=x48[3 * i:3 * (i + n)].tolist(), sample_rate=48000, finished=fin))
+        s16 = a16.pushpop(SpeechSegment(content=x16[i:i + n].tolist(), sample_rate=16000, finished=fin))
+        assert s48.is_empty == s16.is_empty, i // n
+        for k in ("asr_tokens", "st_tokens", "mt_tokens", "units", "dur"):
+            assert a48.trace.get(k) == a16.trace.get(k), (i // n, k)
+        if not s16.is_empty and len(s16.content):
+            assert len(s48.content) == len(s16.content)
+            assert float(np.abs(np.array(s48.content) - np.array(s16.content)).max()) < WAV_TOL
+            writes += 1
+    assert writes >= 1
+    a48.engine.close()
+    a16.engine.close()
+
+
+def test_fairseq_surface_model_on_the_engine(gold):
+    """§8b(ii): the nn.Module shims of fairseq_surface.py driven the way the reference agent drives its model object: chunk-size
+    pokes (agent:404-413), encoder.forward -> fairseq-shaped dict (s2t_conformer.py:154-163), CTC decoder modules, MT features."""
+    from streamspeech_b200.fairseq_surface import StreamSpeechB200Model
+
+    cfg = golden_cfg()
+    sd = synth.make_model_state_dict(cfg, 0)
+    model = StreamSpeechB200Model.from_checkpoint(sd, None, None)
+    assert model.cfg.enc_layers == 3 and model.mt_task_name == "target_unigram"
+    g = gold["encoder"]
+    model.encoder.chunk_size = 8
+    for conv in model.encoder.subsample.conv_layers:
+        conv.chunk_size = 8
+    for layer in model.encoder.conformer_layers:
+        layer.conv_module.depthwise_conv.chunk_size = 8
+    src = torch.from_numpy(g["feats"])
+    F = src.shape[0]
+    fb = torch.zeros(2, F, 80)
+    fb[0] = src
+    fb[1, :150] = src[:150]
+    out = model.encoder(fb, torch.tensor([F, 150]))
+    eo = out["encoder_out"][0]
+    assert eo.shape[1] == 2 and len(out["encoder_padding_mask"]) == 1 and out["encoder_padding_mask"][0].shape == (2, eo.shape[0])
+    assert g["batched_lens"].tolist() == [F, 150]
+    d = maxdiff(eo, g["batched_out"])
+    report("fairseq_surface_encoder", maxdiff=d)
+    assert d < FP_TOL, d
+    dg = gold["decoders"]
+    enc = cuda(dg["enc_out"]).unsqueeze(1)
+    for name in ("source_unigram", "ctc_target_unigram"):
+        logits = getattr(model, f"{name}_decoder")(enc)["encoder_out"]
+        lp = model.get_normalized_probs([logits], log_probs=True)
+        lp[:, :, cfg.pad] = float("-inf")
+        lp[:, :, cfg.unk] = float("-inf")
+        assert lp.argmax(-1)[:, 0].tolist() == dg[f"ctc_{name}_argmax"].tolist(), name
+    x, extra = model.target_unigram_decoder(torch.from_numpy(dg["mt_tokens"]), encoder_out={"encoder_out": [enc]}, features_only=True)
+    assert maxdiff(x[0], dg["mt_feats"]) < FP_TOL
+    model.engine.close()
