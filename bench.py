@@ -205,6 +205,121 @@ def gemm_rooflines(engine, peaks):
     return out
 
 
+def asr_streams_leg(eng, n_streams=32, seconds=10.0, chunk_ms=160, rank=0):
+    """BASELINE configs[3]: streaming ASR at chunk = 160 ms, 256 concurrent utterances sharded over 8 GPUs = 32 streams per GPU.
+    All streams of a GPU advance together through the stream pool (ss_pool_step: batched fbank -> encoder -> ASR CTC head); the timed
+    region includes the host->device copy of every chunk and the device->host read of every stream's tokens (e2e style)."""
+    import torch
+
+    from streamspeech_b200 import synth
+    from streamspeech_b200.scheduler import StreamPool
+
+    eng.set_chunk(chunk_ms // 40, min(chunk_ms // 40, 16))  # speech_to_text.asr agent :361-375
+    pool = StreamPool(eng, n_slots=n_streams, max_seconds=int(seconds) + 1, ctc_heads=1)
+    n = SAMPLE_RATE * chunk_ms // 1000
+    wavs = [synth.make_audio(seconds, seed=5000 + 97 * rank + j).contiguous() for j in range(n_streams)]
+    slots = [pool.acquire() for _ in range(n_streams)]
+
+    def run():
+        for sl in slots:
+            pool.reset(sl)
+        ntok = 0
+        for i in range(0, wavs[0].numel(), n):
+            for j, sl in enumerate(slots):
+                pool.push(sl, wavs[j][i:i + n])
+            pool.flush()
+            ntok = sum(len(pool.results[sl]["ctc"][0][0]) for sl in slots)
+        return ntok
+
+    run()  # warm-up (workspace growth, packed weight caches)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    ntok = run()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    eng.set_chunk(CHUNK_MS // 40)  # back to the S2ST setting
+    return {"workload": f"streaming ASR, chunk {chunk_ms} ms, {n_streams} concurrent {seconds:.0f} s utterances per GPU (BASELINE.json configs[3])",
+            "value": n_streams * seconds / (ms * 1e-3), "unit": "audio-s/s", "ms": ms, "streams": n_streams, "steps": pool.steps // 2,
+            "rows_per_step": n_streams * 2 * (chunk_ms // 40), "gpu_launches": eng.launch_count() - l0, "tokens_final": ntok,
+            "h2d_bytes": int(n_streams * seconds * SAMPLE_RATE * 4)}
+
+
+def offline_leg(agent, peaks, B=32, seconds=15.0):
+    """BASELINE configs[2]: offline S2ST, batch of 32 padded 15 s utterances on one GPU: batched encoder over B x T = 12,000 rows
+    (tcgen05 GEMMs), CTC prints, greedy MT, T2U + unit decoder and the vocoder per utterance (the reference's vocoder script is
+    batch 1 too: generate_waveform_from_code.py:40-78).  Also times the two kernels the config is quoted for: the FFN GEMM at
+    M = 12,000 and the vocoder generator on 750 frames."""
+    import torch
+
+    from streamspeech_b200 import synth
+    from streamspeech_b200.offline import OfflineS2STGenerator
+
+    eng = agent.engine
+    gen = OfflineS2STGenerator(eng, max_len_b_mt=100)
+    feats = []
+    for b in range(B):
+        w = synth.make_audio(seconds, seed=7000 + b).cuda()
+        feats.append(eng.fbank(w))
+    F = max(f.shape[0] for f in feats)
+    src = torch.zeros(B, F, eng.cfg.feat_dim, device="cuda")
+    for b, f in enumerate(feats):
+        src[b, : f.shape[0]] = f
+    lens = [f.shape[0] for f in feats]
+
+    def timed(fn, reps=1):
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            r = fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps, r
+
+    eng.encoder(src, lens)  # warm-up
+    ms_enc, _ = timed(lambda: eng.encoder(src, lens), 3)
+    ms_gen, res = timed(lambda: gen.generate(src, lens))
+    codes = [gen.units_to_codes(r["units"]) for r in res]
+    ms_voc, wavs = timed(lambda: [gen.synthesize(c) for c in codes if len(c)])
+    out_s = sum(w.numel() for w in wavs) / SAMPLE_RATE
+    T = eng.encoder_out_frames(F)
+    rows = B * T
+    enc_flops = 2.0 * rows * (37_606_400 - 3_072_000 + 12_288 * T)  # SURVEY.md §8(d): MAC per encoder frame without the CTC heads
+    line = {"workload": f"offline S2ST, batch {B} x {seconds:.0f} s padded (BASELINE.json configs[2])", "unit": "audio-s/s",
+            "value": B * seconds / ((ms_gen + ms_voc) * 1e-3), "ms_encoder_batched": ms_enc, "ms_generate": ms_gen, "ms_vocoder": ms_voc,
+            "encoder_rows": rows, "encoder_tflops_fp32_equivalent": enc_flops / (ms_enc * 1e-3) / 1e12, "output_audio_s": out_s}
+    # the FFN GEMMs of the batched encoder on the tcgen05 kernel (bf16 x 6 split = fp32-grade), M = B x T rows
+    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+    g = {}
+    x = torch.randn(rows, 256, device="cuda")
+    hbuf = torch.randn(rows, 2048, device="cuda")
+    w1 = torch.randn(2048, 256, device="cuda") / 16
+    w2 = torch.randn(256, 2048, device="cuda") / 45
+    b1, b2 = torch.zeros(2048, device="cuda"), torch.zeros(256, device="cuda")
+    for name, a, w, b, K, N in (("ffn_w1 M x 256 -> 2048", x, w1, b1, 256, 2048), ("ffn_w2 M x 2048 -> 256", hbuf, w2, b2, 2048, 256)):
+        for pieces in (2, 3):
+            eng.op_linear_umma(a, w, b, 0, pieces)
+            ms, _ = timed(lambda: eng.op_linear_umma(a, w, b, 0, pieces), 10)
+            fl = 2.0 * rows * K * N
+            mm = 3 if pieces == 2 else 6
+            g[f"{name}, bf16x{mm}"] = {"us": ms * 1e3, "tflops_fp32_equivalent": fl / (ms * 1e-3) / 1e12,
+                                      "tensor_pipe_frac": mm * fl / (ms * 1e-3) / 1e12 / peak}
+    line["ffn_gemm_umma2"] = {"M": rows, "peak_tflops": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "kernels": g}
+    # vocoder generator on 750 frames (15 s of output audio)
+    codes750 = torch.randint(0, 1000, (750,), device="cuda")
+    eng.vocoder_durations(codes750, False)
+    eng.vocoder_generate(750, 0, 750, 0)
+    ms750, _ = timed(lambda: eng.vocoder_generate(750, 0, 750, 0), 5)
+    fl = 750 * 320.8e6  # SURVEY.md §8(d): 320.8 MFLOP per unit frame
+    line["vocoder_750_frames"] = {"ms": ms750, "tflops_fp32_equivalent": fl / (ms750 * 1e-3) / 1e12, "tensor_pipe_frac": 3 * fl / (ms750 * 1e-3) / 1e12 / peak,
+                                  "audio_s_per_s": 15.0 / (ms750 * 1e-3)}
+    eng.set_chunk(CHUNK_MS // 40)
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,6 +328,7 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--encoder-mode", type=str, default="cached", choices=["cached", "recompute"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] / configs[3] legs (extra keys of the JSON line)")
     ap.add_argument("--ncu-window", action="store_true",
                     help="after the timed runs, stream one more resident utterance between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -325,6 +441,23 @@ def main():
     ms_res, out_res, launches = timed(stream_resident, utts_dev, args.steps, args.warmup)
     utts_host = [u.tolist() for u in utts]
     ms_e2e, out_e2e, _ = timed(stream_e2e, utts_host, args.steps, max(1, args.warmup // 2))
+    extra_asr = None
+    if not args.no_extras:
+        try:
+            extra_asr = asr_streams_leg(eng, rank=rank)
+            t = torch.tensor([extra_asr["ms"]], device="cuda")
+            if dist is not None:
+                dist.barrier()
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            extra_asr["ms"] = float(t.item())
+            extra_asr["value"] = extra_asr["streams"] * world * UTT_SECONDS / (extra_asr["ms"] * 1e-3)
+            extra_asr["streams_total"] = extra_asr["streams"] * world
+        except Exception as ex:  # noqa: BLE001 -- an extra leg must never take the headline down
+            extra_asr = {"error": repr(ex)}
+            if dist is not None:
+                t = torch.tensor([0.0], device="cuda")
+                dist.barrier()
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     if args.ncu_window and rank == 0:
         torch.cuda.synchronize()
@@ -360,6 +493,13 @@ def main():
 
     line["roofline"] = encoder_roofline(eng, peaks, one_more)
     line["roofline_large_gemm"] = gemm_rooflines(eng, peaks)
+    if extra_asr is not None:
+        line["extra_asr_streams"] = extra_asr
+    if world == 1 and not args.no_extras:
+        try:
+            line["extra_offline_batch32"] = offline_leg(agent, peaks)
+        except Exception as ex:  # noqa: BLE001
+            line["extra_offline_batch32"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample: the first 4 s of the same utterance through the oracle agent (reference semantics)
         from oracle.agent_oracle import OracleS2STAgent

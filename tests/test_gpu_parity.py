@@ -720,3 +720,24 @@ def test_fairseq_surface_model_on_the_engine(gold):
     x, extra = model.target_unigram_decoder(torch.from_numpy(dg["mt_tokens"]), encoder_out={"encoder_out": [enc]}, features_only=True)
     assert maxdiff(x[0], dg["mt_feats"]) < FP_TOL
     model.engine.close()
+
+
+def test_generate_waveform_from_code_front_door(tmp_path, gold):
+    """§8 f4: the reference's vocoder script interface (generate_waveform_from_code.py:40-111) on the engine: code file in,
+    <i>_pred.wav out, waveform = the fixture of the reference CodeGenerator within the 16-bit quantisation of the file."""
+    import json
+    import wave
+
+    from streamspeech_b200.generate_waveform_from_code import cli_main
+
+    g = gold["vocoder"]
+    (tmp_path / "unit.txt").write_text(" ".join(str(int(c)) for c in g["code"][0]) + "\\n" + "5 5 17 900\\n")
+    json.dump(VocoderConfig().to_json_dict(), open(tmp_path / "config.json", "w"))
+    n = cli_main(["--in-code-file", str(tmp_path / "unit.txt"), "--vocoder", "synthetic", "--vocoder-cfg", str(tmp_path / "config.json"),
+                  "--results-path", str(tmp_path / "out"), "--dur-prediction"])
+    assert n == 2
+    with wave.open(str(tmp_path / "out" / "0_pred.wav")) as w:
+        assert w.getframerate() == 16000 and w.getnchannels() == 1
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768.0
+    assert pcm.shape[0] == g["wav"].shape[0]
+    assert float(np.abs(pcm - np.clip(g["wav"], -1, 32767 / 32768)).max()) < 1e-3 + 1.0 / 32768
