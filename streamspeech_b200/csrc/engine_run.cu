@@ -169,14 +169,22 @@ void dec_layer(const DecLayerW& L, float* x, int n, int dim, int ffn, int heads,
   linear(s.hid, ffn, n, L.fc2, ep_residual(x, dim), st);
 }
 
-int ensure_mt_cross(ss_engine* h, int T) {
+// keep_rows > 0: rows [0, keep_rows) of every layer survive a reallocation (incremental-state decoding keeps cross K / V across calls)
+int ensure_mt_cross(ss_engine* h, int T, int keep_rows = 0) {
   if (T <= h->mt_cross_cap) return SS_OK;
-  if (h->mt_cross_kv) cudaFree(h->mt_cross_kv);
-  h->mt_cross_kv = nullptr;
+  const int cap = std::max(T + T / 2, 512);
+  const size_t row = (size_t)2 * h->cfg.mt_dim;
+  float* fresh = nullptr;
+  if (cudaMalloc((void**)&fresh, (size_t)h->cfg.mt_layers * cap * row * sizeof(float)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc(mt cross kv) failed");
+  if (h->mt_cross_kv) {
+    cudaDeviceSynchronize();  // earlier launches may still read the old buffer
+    if (keep_rows > 0)
+      for (int l = 0; l < h->cfg.mt_layers; ++l)
+        cudaMemcpy(fresh + (size_t)l * cap * row, h->mt_cross_kv + (size_t)l * h->mt_cross_cap * row, (size_t)keep_rows * row * sizeof(float), cudaMemcpyDeviceToDevice);
+    cudaFree(h->mt_cross_kv);
+  }
+  h->mt_cross_kv = fresh;
   h->mt_cross_final = 0;
-  int cap = std::max(T + T / 2, 512);
-  size_t bytes = (size_t)h->cfg.mt_layers * cap * 2 * h->cfg.mt_dim * sizeof(float);
-  if (cudaMalloc((void**)&h->mt_cross_kv, bytes) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc(mt cross kv) failed");
   h->mt_cross_cap = cap;
   return SS_OK;
 }
@@ -723,9 +731,8 @@ int ss_mt_greedy_incremental(ss_engine* h, void* stream, const float* enc_dev, i
   if (max_len + kv_off + 2 > c.max_mt_positions || max_len > max_out) return h->fail(SS_ERR_CAPACITY, "MT hypothesis longer than capacity");
   if (!h->persistent_mt || !h->persist_bar || !mt_decode_persistent_supported(c.mt_dim, c.mt_ffn, c.mt_heads, c.tgt_vocab, c.max_mt_positions, std::max(T, h->mt_inc_cross_rows)))
     return h->fail(SS_ERR_STATE, "incremental MT decoding runs on the persistent MT kernel, which is off or does not support this shape");
-  int rc = ensure_mt_cross(h, std::max(T, h->mt_inc_cross_rows));
+  int rc = ensure_mt_cross(h, std::max(T, h->mt_inc_cross_rows), h->mt_inc_cross_rows);
   if (rc) return rc;
-  if (h->mt_cross_cap < std::max(T, h->mt_inc_cross_rows)) return h->fail(SS_ERR_CAPACITY, "cross-attention cache too small");
   const int dim = c.mt_dim;
   if (!ws_begin(h, ((size_t)(dim * 8 + c.mt_ffn) + c.tgt_vocab + (size_t)c.max_mt_positions * dim + 4096) * sizeof(float))) return h->fail(SS_ERR_CUDA, "workspace allocation failed");
   DecScratch s = dec_scratch(h, 1, dim, c.mt_ffn);
