@@ -105,6 +105,7 @@ struct ss_engine {
   std::map<std::tuple<int, uintptr_t, int, int, int>, std::pair<cudaGraphExec_t, int>> voc_graphs;
   float* persist_ffn_scratch = nullptr;  // [enc_ffn / 16][16][enc_dim] partial sums of the fused FFN phases
   int persistent_ffn_fused = 1;          // fused FFN phases in the persistent encoder kernel (0: separate W1 / W2 phases)
+  int fbank_tma = 1;           // fbank frames staged by cp.async.bulk + transposed mel bank (0: plain loads, [80][257] mel bank)
   int persistent_encoder = 1;  // streaming encoder step as ONE cooperative kernel (kernels_persist.cu) when the shape fits
   std::map<std::string, ss::HostTensor> host;  // loaded tensors by key
   std::vector<void*> dev_allocs;
@@ -129,6 +130,7 @@ struct ss_engine {
   float* unit_emb = nullptr;
   float* unit_pos_row = nullptr;  // sinusoid row pad+1 (N1 quirk)
   float* mel_bank = nullptr;
+  float* melT = nullptr;            // mel bank transposed [257][80] (TMA-staged fbank kernels)
   float* window = nullptr;
   float* cmvn_mean = nullptr;
   float* cmvn_std = nullptr;

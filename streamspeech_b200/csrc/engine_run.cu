@@ -264,7 +264,10 @@ int ss_fbank(ss_engine* h, void* stream, const float* samples_dev, int64_t n_sam
   if (!h || !h->finalized) return h ? h->fail(SS_ERR_STATE, "engine not finalized") : SS_ERR_INVALID;
   if (n_frames <= 0) return SS_OK;
   if (frame0 < 0 || (frame0 + n_frames - 1) * 160 + 400 > n_samples) return h->fail(SS_ERR_INVALID, "fbank frame range exceeds samples");
-  fbank_cmvn(samples_dev, n_samples, (int)frame0, (int)n_frames, h->mel_bank, h->window, h->cmvn_mean, nullptr, h->cmvn_std, out_dev, S(stream));
+  if (h->fbank_tma && ((uintptr_t)samples_dev & 15) == 0)  // frames are complete (checked above): the bulk copy never leaves the buffer
+    fbank_cmvn_tma(samples_dev, (int)frame0, (int)n_frames, h->melT, h->window, h->cmvn_mean, h->cmvn_std, out_dev, S(stream));
+  else
+    fbank_cmvn(samples_dev, n_samples, (int)frame0, (int)n_frames, h->mel_bank, h->window, h->cmvn_mean, nullptr, h->cmvn_std, out_dev, S(stream));
   return check_launch(h, "ss_fbank");
 }
 
@@ -1135,6 +1138,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "unit_grouped") h->unit_grouped = value;
   else if (n == "vocoder_graph") h->vocoder_graph = value;
   else if (n == "graph_pdl") h->graph_pdl = value;
+  else if (n == "fbank_tma") h->fbank_tma = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
   else if (n == "persistent_ffn_fused") h->persistent_ffn_fused = value;
   else if (n == "vocoder_streams") h->vocoder_streams = value;

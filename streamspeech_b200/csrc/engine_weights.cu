@@ -173,6 +173,12 @@ void finalize_impl(ss_engine* h) {
     const HostTensor& mb = get(h, "__const__.mel_bank");
     expect_shape(mb, "__const__.mel_bank", {80, 257});
     h->mel_bank = upload(h, mb.data);
+    {
+      std::vector<float> t((size_t)257 * 80);
+      for (int m = 0; m < 80; ++m)
+        for (int k = 0; k < 257; ++k) t[(size_t)k * 80 + m] = mb.data[(size_t)m * 257 + k];
+      h->melT = upload(h, t);
+    }
     const HostTensor& w = get(h, "__const__.window");
     expect_shape(w, "__const__.window", {400});
     h->window = upload(h, w.data);

@@ -102,6 +102,11 @@ void fbank_cmvn(const float* samples, int64_t n_samples, int f0, int nf, const f
                 const float* window /*[400]*/, const float* cmvn_mean, const float* cmvn_inv_std_or_null,
                 const float* cmvn_std, float* out /*[nf][80]*/, cudaStream_t st);
 
+// the same frames with the sample window staged by cp.async.bulk (TMA 1-D) and the mel bank transposed to [257][80]; `samples`
+// must be 16-byte aligned and hold every requested frame completely
+void fbank_cmvn_tma(const float* samples, int f0, int nf, const float* melT, const float* window, const float* cmvn_mean, const float* cmvn_std,
+                    float* out, cudaStream_t st);
+
 // Relative-position self-attention of the chunk-Conformer (espnet_multihead_attention.py:154-209).
 // q: [B*nQ][ldq] rows for absolute query positions q_offset .. q_offset+nQ-1; k, v: [B*T][ld] rows for absolute
 // key positions 0..T-1; pos: [2*Tpos-1][D] rows indexed by (i-j) + Tpos-1; out: [B*nQ][D].
