@@ -602,18 +602,18 @@ __device__ void phase_attention(Smem& sm, const float* q, const float* kc, const
     for (int x = 1; x < PW; ++x) sum += sm.red[x];
     // out[d] = sum_j p_j V[j][d]: warp w takes keys j = w (mod 8), 8 keys in flight; lane owns dims 2*lane, 2*lane+1
     float a0_ = 0.f, a1_ = 0.f;
-    for (int j0 = w; j0 < n; j0 += PW * 8) {
-      float2 vv[8];
-      float p[8];
+    for (int j0 = w; j0 < n; j0 += PW * 16) {  // 16 keys (independent 8-byte loads) in flight per lane: 2 rounds at T = 250
+      float2 vv[16];
+      float p[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 16; ++u) {
         const int j = j0 + u * PW;
         const bool ok = j < n;
         vv[u] = ok ? *reinterpret_cast<const float2*>(vb + (int64_t)j * D + 2 * lane) : make_float2(0.f, 0.f);
         p[u] = ok ? sm.S[j] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 16; ++u) {
         a0_ = fmaf(p[u], vv[u].x, a0_);
         a1_ = fmaf(p[u], vv[u].y, a1_);
       }
