@@ -181,7 +181,7 @@ def encoder_roofline(engine, peaks, run_utterance):
 
 def gemm_rooflines(engine, peaks):
     """Secondary: the GEMM / conv kernels at the vocoder's heaviest conv shape (L = 5*500 rows, 256 -> 256 channels, k = 11):
-    fp32 CUDA cores, the first tcgen05 kernel (im2col gather) and the tap-shift tcgen05 kernel with pre-packed weights.
+    fp32 CUDA cores and the tap-shift tcgen05 kernel with pre-packed weights.
     FLOPs are fp32-equivalent (2*L*C*C*k); the tcgen05 kernels spend 3 bf16 MMAs per product (bf16x3 split)."""
     import torch
 
@@ -190,7 +190,7 @@ def gemm_rooflines(engine, peaks):
     w = torch.randn(C, C * k, device=engine.device) / (C * k) ** 0.5
     b = torch.zeros(C, device=engine.device)
     out = {}
-    for name, mode, mmas in (("gemm_kernel<128,64> fp32 CUDA cores", 0, 0), ("umma_gemm_kernel tcgen05 bf16x3, im2col gather (v1)", 2, 3),
+    for name, mode, mmas in (("gemm_kernel<128,64> fp32 CUDA cores", 0, 0),
                              ("umma2_kernel tcgen05 bf16x3, tap-shift + cp.async.bulk weights (default path)", 12, 3)):
         fn = lambda: engine.op_conv1d(x, w, b, k, 1, k // 2, 0.1, mode)
         for _ in range(3):

@@ -213,16 +213,16 @@ int ss_pool_step(ss_engine* h, void* stream, int n, const int32_t* slots_host, i
 /* ---- single ops exported for the parity tests (same kernels the entry points above launch) ------------- */
 int ss_op_linear(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N,
                  int act, float* out_dev);
-/* same GEMM on the tcgen05 tensor-core kernel (bf16 operand splitting, pieces = 2 or 3); parity-test hook */
+/* same GEMM on the tcgen05 tensor-core kernel (kernels_umma2.cu, bf16 operand splitting, pieces = 2: 3 MMAs, 3: 6 MMAs per product);
+ * parity-test / roofline hook */
 int ss_op_linear_umma(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N,
                       int act, int pieces, float* out_dev);
 /* out[L][N] = conv1d(pre_lrelu(x[L][C_in]), w[N][ksize*C_in] (tap-major), stride 1, dilation dil, left padding pad_left) + bias on
- * the kernel selected by mode: 0 = fp32 CUDA cores, 2 / 3 = tcgen05 im2col kernel, 12 / 13 = tcgen05 tap-shift kernel with
- * pre-packed weights (kernels_umma2.cu); parity-test hook */
+ * the kernel selected by mode: 0 = fp32 CUDA cores, 12 / 13 = tcgen05 tap-shift kernel with pre-packed weights (kernels_umma2.cu,
+ * 2 / 3 bf16 pieces per operand); parity-test hook */
 int ss_op_conv1d(ss_engine* h, void* stream, const float* x_dev, int L, int C_in, const float* w_dev, const float* bias_dev, int N,
                  int ksize, int dil, int pad_left, float pre_lrelu, int mode, float* out_dev);
-/* engine options: "umma_vocoder" / "umma_linear" = 0 (fp32 CUDA cores), 2 or 3 (tcgen05, bf16 pieces per operand), 12 or 13
- * (second-generation tcgen05 kernel, 2 or 3 pieces); "umma_min_rows" / "umma_min_channels": smaller GEMMs / convs stay on
+/* engine options: "umma_vocoder" / "umma_linear" = 0 (fp32 CUDA cores), 12 or 13 (tcgen05 kernel, 2 or 3 bf16 pieces per operand); "umma_min_rows" / "umma_min_channels": smaller GEMMs / convs stay on
  * the fp32 kernels; "umma2_cache_clear": drop the packed weight copies;
  * "persistent_encoder" = 1 (default): ss_encoder_stream_step runs the layer stack as one cooperative kernel when the
  * shape fits, 0: one kernel per op; "persistent_barrier" = 1 (default): that kernel's own counter barrier instead of

@@ -34,14 +34,12 @@ void route_from(ss_engine* h) {
   g_umma2_cache = h->umma2_cache;
 }
 
-// conv-as-GEMM dispatch: a tcgen05 split-bf16 kernel when enabled and the shape fits, fp32 CUDA-core kernel otherwise
-// (mode 2 / 3: kernels_umma.cu with that many pieces, 12 / 13: kernels_umma2.cu)
+// conv-as-GEMM dispatch: the tcgen05 split-bf16 kernel (kernels_umma2.cu; mode 12 / 13 = 2 / 3 bf16 pieces per operand) when enabled and
+// the shape fits, the fp32 CUDA-core kernel otherwise
 void conv_gemm(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaStream_t st) {
   const int rows = a.B * a.L_rows;
   if (g_umma_conv >= 12 && g_umma2_cache && rows >= g_umma_min_rows && a.C_in >= g_umma_min_channels && umma2_supported(a, N, ep))
     umma2_conv(g_umma2_cache, a, W, N, ep, g_umma_conv - 10, st);
-  else if (g_umma_conv >= 2 && g_umma_conv < 10 && rows >= 128 && umma_gemm_supported(a, N, ep))
-    umma_gemm_conv(a, W, N, ep, g_umma_conv, st);
   else
     gemm_conv(a, W, N, ep, st);
 }
@@ -55,8 +53,6 @@ void linear(const float* x, int ldx, int M, const Linear& l, Epilogue ep, cudaSt
     skinny_gemm(x, ldx, l.w, M, l.N, l.K, ep, st);
   else if (g_umma_linear >= 12 && g_umma2_cache && M >= g_umma_min_rows && umma2_supported(a, l.N, ep))
     umma2_conv(g_umma2_cache, a, l.w, l.N, ep, g_umma_linear - 10, st);
-  else if (g_umma_linear >= 2 && g_umma_linear < 10 && M >= 128 && (ldx & 3) == 0 && umma_gemm_supported(a, l.N, ep))
-    umma_gemm_conv(a, l.w, l.N, ep, g_umma_linear, st);
   else
     gemm_conv(a, l.w, l.N, ep, st);
 }
@@ -1213,12 +1209,14 @@ int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes) 
 int ss_op_linear_umma(ss_engine* h, void* stream, const float* x_dev, int M, int K, const float* w_dev, const float* bias_dev, int N, int act,
                       int pieces, float* out_dev) {
   if (!h) return SS_ERR_INVALID;
+  route_from(h);
+  if (pieces != 2 && pieces != 3) return h->fail(SS_ERR_INVALID, "pieces must be 2 (bf16x3) or 3 (bf16x6)");
   ConvA a;
   a.x = x_dev; a.B = 1; a.L_in = M; a.L_rows = M; a.C_in = K; a.ldx = K;
   Epilogue ep = ep_out(out_dev, N, act);
   ep.bias = bias_dev;
-  if (!umma_gemm_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 GEMM");
-  umma_gemm_conv(a, w_dev, N, ep, pieces, S(stream));
+  if (!umma2_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 kernel");
+  umma2_conv(h->umma2_cache, a, w_dev, N, ep, pieces, S(stream));
   return check_launch(h, "ss_op_linear_umma");
 }
 
@@ -1235,8 +1233,7 @@ int ss_op_conv1d(ss_engine* h, void* stream, const float* x_dev, int L, int C_in
     if (!umma2_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 conv kernel");
     umma2_conv(h->umma2_cache, a, w_dev, N, ep, mode - 10, S(stream));
   } else if (mode >= 2) {
-    if (!umma_gemm_supported(a, N, ep)) return h->fail(SS_ERR_INVALID, "shape not supported by the tcgen05 GEMM");
-    umma_gemm_conv(a, w_dev, N, ep, mode, S(stream));
+    return h->fail(SS_ERR_INVALID, "modes 2 / 3 (first-generation tcgen05 kernel) were removed: use 12 / 13");
   } else {
     gemm_conv(a, w_dev, N, ep, S(stream));
   }

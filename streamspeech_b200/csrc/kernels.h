@@ -72,12 +72,7 @@ float* splitk_workspace(size_t bytes);
 void set_splitk_slot(int slot);
 void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, const Epilogue& ep, cudaStream_t st);
 
-// tcgen05 tensor-core GEMM with bf16 operand splitting (pieces = 2: 3 MMAs, ~2^-16 relative; pieces = 3: 6 MMAs,
-// ~fp32), same ConvA / Epilogue contract as gemm_conv.  See kernels_umma.cu.
-bool umma_gemm_supported(const ConvA& a, int N, const Epilogue& ep);
-void umma_gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, int pieces, cudaStream_t st);
-
-// Second-generation tcgen05 path (kernels_umma2.cu): stride-1 convolutions / linears over one sequence (B = 1) with
+// tcgen05 path (kernels_umma2.cu): stride-1 convolutions / linears over one sequence (B = 1) with
 // pre-packed bf16-split weights streamed by cp.async.bulk and activations converted once per channel chunk (taps are
 // descriptor row shifts).  The cache owns the packed weight copies (keyed by weight pointer and tiling).
 struct Umma2Cache;

@@ -3,7 +3,7 @@
 //
 // Why fp32 CUDA cores here: the parity bar is bit-exact arg-max tokens against the reference's fp32
 // CPU path (BASELINE.json north_star); every GEMM on the path feeds an arg-max within a few layers.
-// This kernel is the exact-precision baseline; the tcgen05 path (kernels_umma.cu) is opt-in per GEMM.
+// This kernel is the exact-precision baseline; the tcgen05 path (kernels_umma2.cu) takes the large-M GEMMs.
 #include <algorithm>
 
 #include "common.cuh"

@@ -1,10 +1,10 @@
-// tcgen05 implicit-GEMM convolution / linear kernel, second generation (warp-specialised, weights pre-packed).
+// tcgen05 implicit-GEMM convolution / linear kernel (warp-specialised, weights pre-packed).
 //
 //   out[t][n] = epilogue( sum_{tap j, channel ci}  pre(x[t + j*dil - pad_left][ci]) * W[n][j*C_in + ci] )
 //
 // for stride-1 convolutions over one channels-last sequence (B = 1; a plain linear layer is ksize = 1).  fp32 operands are
 // split into NP bf16 pieces (x = x0 + x1 [+ x2]) and the product is accumulated in TMEM as 3 (NP = 2, ~2^-16 relative) or
-// 6 (NP = 3, ~fp32) bf16 tcgen05 MMAs, exactly like kernels_umma.cu.  What is new:
+// 6 (NP = 3, ~fp32) bf16 tcgen05 MMAs.  Structure:
 //
 //   * weights are split and laid out ONCE (umma2_pack_kernel, cached per weight matrix) as ready-made shared-memory tiles
 //     [n-tile][channel chunk][tap][piece][BN x CK bf16, canonical no-swizzle K-major core matrices]; a producer thread
@@ -12,8 +12,7 @@
 //   * the activation rows of an output tile are converted ONCE per channel chunk, halo included: rows
 //     [m0 - pad_left, m0 + 128 + (k-1)*dil - pad_left) x CK channels.  In the no-swizzle layout a plane of 8 channels is a
 //     linear array of rows at a 16-byte pitch, so tap j is the same staged data with the descriptor's start address moved
-//     by j*dil rows: a k-tap convolution costs k MMAs per staged chunk instead of k conversions (kernels_umma.cu gathers
-//     and converts the im2col matrix, i.e. every activation k times);
+//     by j*dil rows: a k-tap convolution costs k MMAs per staged chunk instead of k im2col conversions;
 //   * roles: warps 0-7 convert (global fp32 -> registers, one chunk ahead -> bf16 pieces in smem), warp 8 issues the MMAs,
 //     warp 9 runs the weight ring; all hand-offs are mbarriers, so conversion of chunk c+1, the weight copies and the MMAs
 //     of chunk c overlap.  Warps 0-7 read the accumulator back with tcgen05.ld and run the fused epilogue.

@@ -186,7 +186,7 @@ class Engine:
         except Exception:
             self.close()
             raise
-        # tensor-core routing (kernels_umma.cu): vocoder convs tolerate the 3-MMA split (1e-3 waveform bar, measured 7e-6);
+        # tensor-core routing (kernels_umma2.cu): vocoder convs tolerate the 3-MMA split (1e-3 waveform bar, measured 7e-6);
         # linears that feed an arg-max stay on the exact fp32 kernels unless explicitly switched on
         self.set_option("prefer_shared", int(os.environ.get("SS_PREFER_SHARED", "0")))
         self.set_option("umma_vocoder", int(os.environ.get("SS_UMMA_VOCODER", "12")))
@@ -462,7 +462,7 @@ class Engine:
 
     def op_conv1d(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], ksize: int, dil: int = 1, pad_left: int = 0,
                   pre_lrelu: float = 1.0, mode: int = 0) -> torch.Tensor:
-        """x [L][C_in] channels-last, w [N][ksize*C_in] tap-major; mode 0 = fp32 CUDA cores, 2/3 = tcgen05 im2col, 12/13 = tcgen05 tap-shift"""
+        """x [L][C_in] channels-last, w [N][ksize*C_in] tap-major; mode 0 = fp32 CUDA cores, 12/13 = tcgen05 (bf16x3 / bf16x6)"""
         L, C = x.shape
         N = w.shape[0]
         out = self._f32(L, N)

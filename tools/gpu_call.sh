@@ -1,9 +1,10 @@
 #!/bin/bash
-P=gpurun_out; mkdir -p $P; rm -f $P/rc.log $P/t_*.log
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "480 or front_door" > $P/t_fix.log 2>&1; echo "pytest fix rc=$?" >> $P/rc.log
+P=gpurun_out; mkdir -p $P; rm -f $P/rc.log $P/t_*.log $P/parity_report.jsonl
+for f in test_gpu_parity test_multistream test_offline_batch; do
+  timeout 900 python -m pytest tests/$f.py -m "gpu" -q --durations=4 > $P/t_$f.log 2>&1; echo "pytest $f rc=$?" >> $P/rc.log
+done
 timeout 200 python tools/persist_phases.py > $P/phases_fused.log 2>&1
-SS_PERSISTENT_FFN_FUSED=0 timeout 200 python tools/persist_phases.py > $P/phases_unfused.log 2>&1
 timeout 200 python tools/mt_profile.py > $P/mt_profile.log 2>&1
-timeout 300 python bench.py --steps 5 --warmup 3 --no-extras > $P/bench_noextras.json 2> $P/bench_noextras.err; echo "bench rc=$?" >> $P/rc.log
-timeout 500 python bench.py --steps 5 --warmup 3 > $P/bench.json 2> $P/bench.err; echo "bench extras rc=$?" >> $P/rc.log
-cat $P/rc.log; tail -3 $P/t_fix.log; head -30 $P/phases_fused.log; tail -12 $P/phases_fused.log; head -25 $P/phases_unfused.log | tail -20; cat $P/mt_profile.log; cut -c1-700 $P/bench_noextras.json; tail -4 $P/bench.err
+timeout 120 python tools/stage_profile.py --out $P/stage.json > $P/stage.log 2>&1
+timeout 500 python bench.py --steps 5 --warmup 3 > $P/bench.json 2> $P/bench.err; echo "bench rc=$?" >> $P/rc.log
+cat $P/rc.log; grep -hE 'FAILED|ERROR|passed|failed' $P/t_*.log | tail -12; head -22 $P/phases_fused.log | tr -d '\n' | cut -c1-700; echo; grep "prefix_kernel 1" $P/mt_profile.log; grep -E "^(mt_greedy|t2u|vocoder_generate|encoder_stream|ctc|_total|_host)" $P/stage.log | cut -c1-110; cut -c1-500 $P/bench.json
