@@ -328,6 +328,54 @@ def offline_leg(agent, peaks, B=32, seconds=15.0):
     return line
 
 
+def mixed_pairs_leg(device_index=0, chunk_ms=640, seconds=10.0, lags=(0, 1, 2, 4)):
+    """BASELINE configs[4]: Es-En + De-En simultaneous S2ST in one process at chunk = 640 ms (whole-word policy), latency sweep over
+    lagging_k1.  Two language pairs = two weight sets = two engine handles on the same GPU (same shapes, different seeds stand in for
+    the two checkpoints); utterances of the two pairs alternate.  Handles share no device state, so this is the single-stream path twice."""
+    import torch
+
+    from streamspeech_b200 import synth
+    from streamspeech_b200.agent import StreamSpeechS2STAgent
+
+    agents = {}
+    for pair, seed in (("es-en", 11), ("de-en", 12)):
+        a = agent_args(device_index)
+        a.model_path, a.vocoder = f"synthetic:{seed}", "synthetic:1"
+        a.source_segment_size = chunk_ms
+        agents[pair] = StreamSpeechS2STAgent(a)
+    n = SAMPLE_RATE * chunk_ms // 1000
+    utts = {pair: synth.make_audio(seconds, seed=900 + i).cuda() for i, pair in enumerate(agents)}
+    out = {}
+    for lag in lags:
+        for ag in agents.values():
+            ag.lagging_k1 = lag
+
+        def run():
+            total = 0
+            for pair, ag in agents.items():  # the two pairs alternate utterance by utterance
+                u = utts[pair]
+                ag.reset()
+                for i in range(0, u.numel(), n):
+                    end = min(i + n, u.numel())
+                    w, wav = ag.step_resident(u, end, end >= u.numel())
+                    if w and wav is not None:
+                        total += wav.numel()
+            return total
+
+        run()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        samples = run()
+        e.record()
+        torch.cuda.synchronize()
+        out[f"lagging_k1={lag}"] = {"audio_s_per_s": 2 * seconds / (s.elapsed_time(e) * 1e-3), "ms": s.elapsed_time(e), "output_audio_s": samples / SAMPLE_RATE}
+    for ag in agents.values():
+        ag.engine.close()
+    return {"workload": f"Es-En + De-En simultaneous S2ST, chunk {chunk_ms} ms, two weight sets on one GPU, alternating {seconds:.0f} s utterances, "
+                        "latency sweep over lagging_k1 (BASELINE.json configs[4])", "unit": "audio-s/s", "sweep": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -513,6 +561,11 @@ def main():
             line["extra_offline_batch32"] = offline_leg(agent, peaks)
         except Exception as ex:  # noqa: BLE001
             line["extra_offline_batch32"] = {"error": repr(ex)}
+        note("extra: mixed language pairs leg")
+        try:
+            line["extra_mixed_pairs_640ms"] = mixed_pairs_leg(local)
+        except Exception as ex:  # noqa: BLE001
+            line["extra_mixed_pairs_640ms"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample: the first 4 s of the same utterance through the oracle agent (reference semantics)
         from oracle.agent_oracle import OracleS2STAgent

@@ -15,6 +15,7 @@ What differs on purpose, without changing results:
 """
 from __future__ import annotations
 
+import array
 import json
 import os
 import sys
@@ -116,8 +117,17 @@ class _DeviceAudio:
             nb[: self.n] = self.buf[: self.n]
             self.buf = nb
         if n > self.n:
-            new = torch.tensor(source[self.n:], dtype=torch.float32).pin_memory()
-            self.buf[self.n:n].copy_(new, non_blocking=True)
+            # python list -> fp32 through array('f') (3x faster than torch.tensor(list)) into a persistent pinned staging buffer
+            # (the previous chunk's copy has completed: policy() read results back since)
+            m = n - self.n
+            if getattr(self, "_stage", None) is None or self._stage.numel() < m:
+                self._stage = torch.empty(max(m, 16384), dtype=torch.float32).pin_memory()
+            if getattr(self, "_stage_ev", None) is not None:
+                self._stage_ev.synchronize()  # (normally long complete)
+            self._stage[:m].copy_(torch.frombuffer(array.array("f", source[self.n:]), dtype=torch.float32))
+            self.buf[self.n:n].copy_(self._stage[:m], non_blocking=True)
+            self._stage_ev = torch.cuda.Event()
+            self._stage_ev.record()
             self.n = n
         if self.rate == SAMPLE_RATE:
             return self.buf[:n]
@@ -312,7 +322,7 @@ class StreamSpeechS2STAgent(_EngineAgentMixin, SpeechToSpeechAgent):
         kind, wav, seg_finished, finished = self._policy_impl()
         if kind == "read":
             return ReadAction()
-        content = wav.tolist() if wav is not None else []  # agent:765 (device -> host -> python list)
+        content = wav.cpu().numpy().tolist() if wav is not None else []  # agent:765 (device -> host -> python list)
         return WriteAction(SpeechSegment(content=content, sample_rate=SAMPLE_RATE, finished=seg_finished), finished=finished)
 
     @torch.inference_mode()
