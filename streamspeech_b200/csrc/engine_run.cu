@@ -1135,6 +1135,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "vocoder_graph") h->vocoder_graph = value;
   else if (n == "graph_pdl") h->graph_pdl = value;
   else if (n == "fbank_tma") h->fbank_tma = value;
+  else if (n == "umma2_fused_reduce") g_umma2_fused_reduce = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
   else if (n == "persistent_ffn_fused") h->persistent_ffn_fused = value;
   else if (n == "vocoder_streams") h->vocoder_streams = value;

@@ -68,6 +68,7 @@ void gemm_conv(const ConvA& a, const float* W, int N, const Epilogue& ep, cudaSt
 
 // split-K scratch (one per process; launches of a handle are stream-ordered) and its fixed-order reduce + epilogue
 float* splitk_workspace(size_t bytes);
+unsigned* splitk_counters(int n_tiles);  // zeroed ticket counters of the current split-K slot (nullptr if n_tiles is too large)
 // split-K scratch region (0..2) used by the GEMM launches of the calling thread from now on; 0 is the default
 void set_splitk_slot(int slot);
 void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, const Epilogue& ep, cudaStream_t st);
@@ -77,6 +78,7 @@ void splitk_epilogue(const float* ws, int splits, int M, int N, int L_rows, cons
 // descriptor row shifts).  The cache owns the packed weight copies (keyed by weight pointer and tiling).
 struct Umma2Cache;
 extern int g_umma2_split_below, g_umma2_min_units;  // split heuristics (tuning knobs)
+extern int g_umma2_fused_reduce;                    // 1: the last CTA of a tile reduces the split partial sums in the kernel (no extra launch)
 extern unsigned long long* g_umma2_dbg;             // optional %globaltimer stamps of CTA (0,0,0)
 Umma2Cache* umma2_cache_create();
 void umma2_cache_clear(Umma2Cache* c);

@@ -280,6 +280,22 @@ float* splitk_region() {
 
 }  // namespace
 
+// per-slot ticket counters of the in-kernel split reduction (kernels_umma2.cu): zero at rest (the last CTA of a tile resets its counter)
+unsigned* splitk_counters(int n) {
+  constexpr int CAP = 1 << 16;
+  static unsigned* base = nullptr;
+  if (n > CAP) return nullptr;
+  if (!base) {
+    if (cudaMalloc((void**)&base, (size_t)CAP * SPLITK_SLOTS * sizeof(unsigned)) != cudaSuccess) {
+      base = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+    cudaMemset(base, 0, (size_t)CAP * SPLITK_SLOTS * sizeof(unsigned));
+  }
+  return base + (size_t)g_splitk_slot * CAP;
+}
+
 float* splitk_workspace(size_t bytes) {
   if (bytes > SPLITK_WS_BYTES) return nullptr;
   return splitk_region();

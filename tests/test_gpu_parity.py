@@ -741,3 +741,25 @@ def test_generate_waveform_from_code_front_door(tmp_path, gold):
         pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768.0
     assert pcm.shape[0] == g["wav"].shape[0]
     assert float(np.abs(pcm - np.clip(g["wav"], -1, 32767 / 32768)).max()) < 1e-3 + 1.0 / 32768
+
+
+def test_umma2_in_kernel_split_reduction_is_bit_identical(eng3, gold):
+    """The last-ticket CTA of an output tile reduces the split partial sums inside umma2_kernel (no splitk_epilogue launch): same
+    slice order and arithmetic as the separate reduce kernel, so the vocoder waveform and the unit-decoder logits must be
+    bit-identical with the option on and off."""
+    g = gold["vocoder"]
+    code = torch.from_numpy(g["code"][0]).cuda()
+    feats = cuda(gold["decoders"]["mt_feats"])
+    res = {}
+    for v in (0, 1):
+        eng3.set_option("umma2_fused_reduce", v)
+        l0 = eng3.launch_count()
+        dur, cum = eng3.vocoder_durations(code, True)
+        total = int(cum[-1].item())
+        wav = eng3.vocoder_generate(total, 0, total, 0).clone()
+        r = eng3.t2u_unit_decode(feats.repeat(5, 1).contiguous(), debug=True)
+        res[v] = (wav, r["logits"].clone(), eng3.launch_count() - l0)
+    eng3.set_option("umma2_fused_reduce", 1)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    report("umma2_fused_reduce", launches_separate=res[0][2], launches_fused=res[1][2])
+    assert res[1][2] < res[0][2]
