@@ -541,7 +541,10 @@ __global__ void umma2_pack_kernel(const float* __restrict__ W, int N, int C_in, 
 int g_umma2_split_below = 60;   // tile grids smaller than this are split over (chunk, tap) units (ss_set_option umma2_split_below;
                                 // measured: 60 beats 148 by 0.9 ms per utterance, the reduce launch costs more than the idle SMs)
 int g_umma2_min_units = 4;      // ... into slices of at least this many units
-int g_umma2_fused_reduce = 1;   // the last CTA of a tile reduces the split partial sums (0: separate splitk_epilogue_kernel launch)
+int g_umma2_fused_reduce = 0;   // 1: the last-ticket CTA of a tile reduces the split partial sums inside the kernel.  Measured on B200
+                                // (round 2, run 5): bit-identical but SLOWER -- one CTA reads splits x tile bytes alone (up to 22 x 64 KB) where
+                                // the separate splitk_epilogue_kernel spreads the same reads over the whole GPU: vocoder 10.6 -> 31 ms per
+                                // utterance.  Kept as an option (a reduction distributed over the split CTAs needs them co-resident).
 unsigned long long* g_umma2_dbg = nullptr;  // device buffer of 16 stamps when the debug option is on
 namespace {
 

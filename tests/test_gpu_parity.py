@@ -759,7 +759,7 @@ def test_umma2_in_kernel_split_reduction_is_bit_identical(eng3, gold):
         wav = eng3.vocoder_generate(total, 0, total, 0).clone()
         r = eng3.t2u_unit_decode(feats.repeat(5, 1).contiguous(), debug=True)
         res[v] = (wav, r["logits"].clone(), eng3.launch_count() - l0)
-    eng3.set_option("umma2_fused_reduce", 1)
+    eng3.set_option("umma2_fused_reduce", 0)  # the engine default (the in-kernel reduction measured slower, kernels_umma2.cu)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     report("umma2_fused_reduce", launches_separate=res[0][2], launches_fused=res[1][2])
     assert res[1][2] < res[0][2]
