@@ -192,6 +192,8 @@ struct ss_engine {
   int persistent_barrier = 1;        // 0: cooperative-groups grid.sync(), 1: own counter barrier (1.6 us cheaper per barrier)
   ss::MtLayerP* mt_persist_layers = nullptr;   // [mt_layers] device pointer table for kernels_persist_mt.cu
   int persistent_mt = 1;                       // single-token MT decode steps as one cooperative kernel per burst
+  int persistent_mt_v2 = 1;                    // single-token kernel with 6 grid barriers per layer (head-group partial projections)
+  float* mt_part = nullptr;                    // [9][mt_dim] scratch of that kernel (per-head partials + FFN delta)
   int persistent_mt_prefix = 1;                // ... and the forced-prefix pass (M <= 64 rows) as one cooperative kernel
   ss::PersistLayer* persist_layers = nullptr;  // [enc_layers] device copy of the per-layer pointer table
   int* lengths_dev = nullptr;     // [Bcap]

@@ -634,6 +634,7 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
     P.emb = h->mt_emb; P.pos = h->mt_pos; P.out_g = h->mt_ln.g; P.out_b = h->mt_ln.b;
     P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
     P.tok = h->mt_tok_dev; P.feats = feats_out_dev; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
+        if (h->persistent_mt_v2 && h->mt_part) { P.part = h->mt_part; P.delta = h->mt_part + (size_t)8 * c.mt_dim; }
     if (mt_prefix_persistent(P, h->mt_persist_layers, start, T, h->persist_bar, &h->persist_bar_target, st) == 0)
       fed = start;
     else
@@ -654,6 +655,7 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
         P.emb = h->mt_emb; P.pos = h->mt_pos; P.out_g = h->mt_ln.g; P.out_b = h->mt_ln.b;
         P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
         P.tok = h->mt_tok_dev; P.feats = feats_out_dev; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
+        if (h->persistent_mt_v2 && h->mt_part) { P.part = h->mt_part; P.delta = h->mt_part + (size_t)8 * c.mt_dim; }
         if (mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, T, h->persist_bar, &h->persist_bar_target, st) == 0) {
           fed = step + cnt;
           if (step + cnt - 1 >= max_len) done = true;
@@ -772,6 +774,7 @@ int ss_mt_greedy_incremental(ss_engine* h, void* stream, const float* enc_dev, i
     P.emb = h->mt_emb; P.pos = h->mt_pos; P.out_g = h->mt_ln.g; P.out_b = h->mt_ln.b;
     P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
     P.tok = h->mt_tok_dev; P.feats = feats; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
+        if (h->persistent_mt_v2 && h->mt_part) { P.part = h->mt_part; P.delta = h->mt_part + (size_t)8 * c.mt_dim; }
     if (mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, Tk, h->persist_bar, &h->persist_bar_target, st) != 0) {
       cudaGetLastError();
       return h->fail(SS_ERR_CUDA, "cooperative launch of the persistent MT kernel was refused");
@@ -1141,6 +1144,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "vocoder_streams") h->vocoder_streams = value;
   else if (n == "persistent_mt") h->persistent_mt = value;
   else if (n == "persistent_mt_prefix") h->persistent_mt_prefix = value;
+  else if (n == "persistent_mt_v2") h->persistent_mt_v2 = value;
   else if (n == "persistent_prefetch") h->persistent_prefetch = value;
   else if (n == "persistent_time") h->persistent_time = value;
   else if (n == "persistent_barrier") {

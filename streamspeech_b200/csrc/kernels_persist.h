@@ -41,6 +41,8 @@ struct MtDecodeParams {
   int64_t* tok;                             // device token buffer: tok[s] is fed at step s, the arg-max goes to tok[s + 1]
   float* feats;                             // [.][dim] final-LN features, row s
   float *x, *q, *attn, *hid, *logits;       // scratch: dim, dim, dim, ffn, vocab floats
+  float *part = nullptr, *delta = nullptr;  // version-2 step (6 barriers per layer): per-head out-projection partials [8][dim], FFN delta [dim];
+                                            // nullptr selects the 8-barrier kernel
 };
 bool mt_decode_persistent_supported(int dim, int ffn, int heads, int vocab, int max_pos, int T);
 // enqueue `nsteps` greedy steps starting with the token at position step0; returns 0, or < 0 if the launch was refused

@@ -359,6 +359,189 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel(MtDecodePa
   if (threadIdx.x == 0 && done_barriers < planned) atomicAdd(bar_ctr, (unsigned)(planned - done_barriers));
 }
 
+// ---- version 2 of the single-token step: 6 grid barriers per layer instead of 8.
+// The two phases [attention of head h on ONE CTA] | barrier | [out-projection over all CTAs] become one: the 16 CTAs of a head
+// group each compute the (tiny, M = 1) attention of their head redundantly and then the PARTIAL out-projection of their 32
+// output columns over that head's 64 inputs; the 8 per-head partial vectors are summed (fixed order) by every CTA while it stages
+// the next phase, together with bias and residual, so the residual stream x lives in shared memory of every CTA and is never
+// exchanged.  Same for the cross-attention block; the FFN output is handed over the same way (one 512-vector).
+//   per layer: [LN + QKV] | [self-attn + Wo partials] | [x += sum, LN + Wcq] | [cross-attn + Wco partials] |
+//              [x += sum, LN + FC1 + ReLU] | [FC2 -> delta]          (next layer / final LN: x += delta)
+constexpr int GRP = 16;                 // CTAs per head group (8 heads x 16 = 128 CTAs)
+constexpr int PCOLS = 512 / GRP;        // out-projection columns per CTA of a group
+
+// partial[h][32 j + c] = sum_{i < 64} a[i] * W[(32 j + c)][64 h + i]   (W row-major [512][512]); a = this CTA's attention output
+__device__ __forceinline__ void head_partial_proj(const float* a, const float* __restrict__ W, int h, int j, float* part_h) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float a0 = a[lane], a1 = a[lane + 32];
+#pragma unroll
+  for (int c = 0; c < PCOLS / MW; ++c) {  // 4 columns per warp
+    const int col = j * PCOLS + warp * (PCOLS / MW) + c;
+    const float* w = W + (int64_t)col * 512 + h * MHD;
+    float acc = fmaf(a0, __ldg(w + lane), a1 * __ldg(w + lane + 32));
+    acc = warp_sum(acc);
+    if (lane == 0) part_h[col] = acc;
+  }
+}
+
+// sm.x[c] += sum_h part[h][c] + bias[c]   (every CTA, identical order); part is [8][512] in global memory
+__device__ __forceinline__ void add_head_partials(MtSmem& sm, const float* part, const float* __restrict__ bias) {
+  for (int c = threadIdx.x; c < 512; c += MTT) {
+    float t = part[c];
+#pragma unroll
+    for (int h = 1; h < 8; ++h) t += part[h * 512 + c];
+    sm.x[c] = sm.x[c] + (t + (bias ? bias[c] : 0.f));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecodeParams P, const MtLayerP* __restrict__ layers, int step0,
+                                                                         int nsteps, int max_len, int T, unsigned* bar_ctr,
+                                                                         unsigned bar_target) {
+  __shared__ __align__(16) MtSmem sm;
+  __shared__ __align__(16) float att_h[MHD];
+  constexpr int DIM = 512, FFN = 2048;
+  const int tid = threadIdx.x;
+  const int barriers_per_step = P.n_layers * 6 + 1;
+  int done_barriers = 0;
+  const float emb_scale = sqrtf((float)DIM);
+  const int grp_h = blockIdx.x / GRP, grp_j = blockIdx.x % GRP;
+  const bool in_group = blockIdx.x < 8 * GRP;
+  float* part = P.part;    // [8][512]
+  float* delta = P.delta;  // [512]
+#define BAR()                          \
+  grid_barrier(bar_ctr, bar_target);   \
+  ++done_barriers;
+  for (int si = 0; si < nsteps; ++si) {
+    const int s = step0 + si;
+    {
+      const int64_t tok = (si == 0) ? P.tok[s] : (int64_t)sm.tok;
+      const int p = (tok == P.pad) ? P.pad : P.pad + 1 + s;
+      for (int c = tid; c < DIM; c += MTT) sm.x[c] = emb_scale * P.emb[tok * DIM + c] + P.pos[(int64_t)p * DIM + c];
+      __syncthreads();
+    }
+    for (int l = 0; l < P.n_layers; ++l) {
+      const MtLayerP L = layers[l];
+      float* kc = P.self_k + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
+      float* vc = P.self_v + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
+      // (1) x += FFN delta of the previous layer; q | k | v = LN(x) Wqkv^T
+      GemvW<DIM, 2> w_qkv;
+      gemv_issue(w_qkv, L.wqkv, 3 * DIM);
+      if (l > 0) {
+        for (int c = tid; c < DIM; c += MTT) sm.x[c] = sm.x[c] + delta[c];
+        __syncthreads();
+      }
+      ln_to_v(sm, L.self_g, L.self_b, DIM);
+      gemv_finish(w_qkv, sm.v, 3 * DIM, [&](int col, float acc) {
+        float y = acc + (L.bqkv ? L.bqkv[col] : 0.f);
+        if (col < DIM) P.q[col] = y;
+        else if (col < 2 * DIM) kc[col - DIM] = y;
+        else vc[col - 2 * DIM] = y;
+      });
+      BAR();
+      // (2) self-attention of head grp_h (every CTA of the group) + partial out-projection of this CTA's 32 columns
+      if (in_group) {
+        attend_head(sm, P.q + grp_h * MHD, P.self_k + (size_t)l * P.max_pos * DIM + grp_h * MHD, P.self_v + (size_t)l * P.max_pos * DIM + grp_h * MHD, DIM,
+                    s + P.kv_off + 1, att_h);
+        __syncthreads();
+        head_partial_proj(att_h, L.wo, grp_h, grp_j, part + grp_h * DIM);
+      }
+      BAR();
+      // (3) x += sum_h partials + bo; q = LN(x) Wcq^T
+      GemvW<DIM, 1> w_cq;
+      gemv_issue(w_cq, L.wcq, DIM);
+      add_head_partials(sm, part, L.bo);
+      ln_to_v(sm, L.cross_g, L.cross_b, DIM);
+      gemv_finish(w_cq, sm.v, DIM, [&](int col, float acc) { P.q[col] = acc + (L.bcq ? L.bcq[col] : 0.f); });
+      BAR();
+      // (4) cross-attention of head grp_h + partial out-projection
+      if (in_group) {
+        const float* cross = P.cross_kv + (size_t)l * P.cross_cap * 2 * DIM;
+        attend_head(sm, P.q + grp_h * MHD, cross + grp_h * MHD, cross + DIM + grp_h * MHD, 2 * DIM, T, att_h);
+        __syncthreads();
+        head_partial_proj(att_h, L.wco, grp_h, grp_j, part + grp_h * DIM);
+      }
+      BAR();
+      // (5) x += sum_h partials + bco; hid = relu(LN(x) W1^T)
+      GemvW<DIM, 2> w_1;
+      gemv_issue(w_1, L.w1, FFN);
+      add_head_partials(sm, part, L.bco);
+      ln_to_v(sm, L.fin_g, L.fin_b, DIM);
+      gemv_finish(w_1, sm.v, FFN, [&](int col, float acc) {
+        float y = acc + (L.b1 ? L.b1[col] : 0.f);
+        P.hid[col] = y > 0.f ? y : 0.f;
+      });
+      BAR();
+      // (6) delta = hid W2^T + b2
+      GemvW<FFN, 1> w_2;
+      gemv_issue(w_2, L.w2, DIM);
+      load_vec(sm.v, P.hid, FFN);
+      gemv_finish(w_2, sm.v, DIM, [&](int col, float acc) { delta[col] = acc + (L.b2 ? L.b2[col] : 0.f); });
+      BAR();
+    }
+    const bool forced_eos = s >= max_len;
+    GemvW<DIM, 6> w_out;
+    if (!forced_eos) gemv_issue(w_out, P.emb, P.vocab);
+    for (int c = tid; c < DIM; c += MTT) sm.x[c] = sm.x[c] + delta[c];
+    __syncthreads();
+    ln_to_v(sm, P.out_g, P.out_b, DIM);
+    if (blockIdx.x == 0)
+      for (int c = tid; c < DIM; c += MTT) P.feats[(size_t)s * DIM + c] = sm.v[c];
+    if (!forced_eos) gemv_finish(w_out, sm.v, P.vocab, [&](int col, float acc) { P.logits[col] = acc; });
+    BAR();
+    if (forced_eos) break;
+    {
+      const float* x = P.logits;
+      float mx = -INFINITY;
+      for (int c = tid; c < P.vocab; c += MTT) mx = fmaxf(mx, x[c]);
+      mx = block_reduce_max(sm, mx);
+      float su = 0.f;
+      for (int c = tid; c < P.vocab; c += MTT) su += expf(x[c] - mx);
+      su = block_reduce_sum(sm, su);
+      const float lse = logf(su);
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = tid; c < P.vocab; c += MTT) {
+        const bool masked = (c == P.pad) || (s < 1 && c == P.eos);
+        float lp = masked ? -INFINITY : (x[c] - mx) - lse;
+        if (lp > best || (lp == best && c < bi)) {
+          best = lp;
+          bi = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
+      }
+      __syncthreads();
+      if ((tid & 31) == 0) {
+        sm.rbest[tid >> 5] = best;
+        sm.ridx[tid >> 5] = bi;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int i = 1; i < MW; ++i)
+          if (sm.rbest[i] > best || (sm.rbest[i] == best && sm.ridx[i] < bi)) {
+            best = sm.rbest[i];
+            bi = sm.ridx[i];
+          }
+        sm.tok = bi;
+        if (blockIdx.x == 0) P.tok[s + 1] = bi;
+      }
+      __syncthreads();
+      if (sm.tok == P.eos) break;
+    }
+  }
+#undef BAR
+  const int planned = nsteps * barriers_per_step;
+  if (threadIdx.x == 0 && done_barriers < planned) atomicAdd(bar_ctr, (unsigned)(planned - done_barriers));
+}
+
 }  // namespace
 
 bool mt_decode_persistent_supported(int dim, int ffn, int heads, int vocab, int max_pos, int T) {
@@ -380,9 +563,11 @@ int mt_decode_persistent(const MtDecodeParams& P, const MtLayerP* layers_dev, in
   MtDecodeParams p = P;
   unsigned bar_target = *bar_target_host;
   void* args[] = {(void*)&p, (void*)&layers_dev, (void*)&step0, (void*)&nsteps, (void*)&max_len, (void*)&T, (void*)&bar_ctr, (void*)&bar_target};
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)mt_decode_persistent_kernel, dim3(grid), dim3(MTT), args, 0, st);
+  const bool v2 = P.part != nullptr && P.delta != nullptr && P.heads == 8 && grid >= 8 * GRP;
+  cudaError_t e = cudaLaunchCooperativeKernel(v2 ? (void*)mt_decode_persistent_kernel_v2 : (void*)mt_decode_persistent_kernel, dim3(grid), dim3(MTT), args,
+                                              0, st);
   if (e != cudaSuccess) return -2;
-  *bar_target_host += (unsigned)grid * (unsigned)(nsteps * (P.n_layers * 8 + 1));
+  *bar_target_host += (unsigned)grid * (unsigned)(nsteps * (P.n_layers * (v2 ? 6 : 8) + 1));
   return 0;
 }
 

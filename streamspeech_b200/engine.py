@@ -198,6 +198,7 @@ class Engine:
         self.set_option("umma2_fused_reduce", int(os.environ.get("SS_UMMA2_FUSED_REDUCE", "0")))
         self.set_option("fbank_tma", int(os.environ.get("SS_FBANK_TMA", "1")))
         self.set_option("persistent_ffn_fused", int(os.environ.get("SS_PERSISTENT_FFN_FUSED", "1")))
+        self.set_option("persistent_mt_v2", int(os.environ.get("SS_PERSISTENT_MT_V2", "1")))
         self.set_option("persistent_mt_prefix", int(os.environ.get("SS_PERSISTENT_MT_PREFIX", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))
         self.set_option("unit_grouped", int(os.environ.get("SS_UNIT_GROUPED", "1")))

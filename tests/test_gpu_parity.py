@@ -601,11 +601,12 @@ def test_ctc_pair_equals_single_heads(eng3, gold):
             assert toks == g[f"ctc_{name}_tokens"].tolist() and idx == g[f"ctc_{name}_index"].tolist(), (row0, name)
 
 
-@pytest.mark.parametrize("option", ["persistent_ffn_fused", "persistent_mt_prefix"])
+@pytest.mark.parametrize("option", ["persistent_ffn_fused", "persistent_mt_prefix", "persistent_mt_v2"])
 def test_persistent_kernel_variants_agree(full, option):
     """A / B of the round-2 persistent-kernel restructurings against the paths they replace: fused FFN phases (hidden-split
     rank-16 updates + deterministic reduce) vs separate W1 / W2 phases in the encoder step; cooperative MT prefix pass vs the
-    per-kernel prefix pass.  Same function, different summation order."""
+    per-kernel prefix pass; single-token MT kernel with 6 barriers per layer (head-group partial projections) vs 8.  Same function,
+    different summation order."""
     cfg, e, o = full
     e.set_chunk(8, 8)
     feats = e.fbank(cuda(synth.make_audio(3.0, seed=5)))

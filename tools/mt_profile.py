@@ -15,11 +15,11 @@ enc = torch.randn(1024, 256, device="cuda") * 0.5
 res = {}
 toks, _ = eng.mt_greedy(enc[:160], None, 40)
 toks = (toks + [17] * 40)[:40]
-for prefix_kernel in (1, 0):
-  eng.set_option("persistent_mt_prefix", prefix_kernel)
+for prefix_kernel in (1, 0):   # here: A / B of the single-token kernel version (1 = 6 barriers per layer, 0 = 8)
+  eng.set_option("persistent_mt_v2", prefix_kernel)
   for T in (160,):
     for npre in (10, 30, 40):
-        for new in (0, 3):
+        for new in (0, 3, 12):
             for stable in (T - 16,):
                 def fn():
                     eng.encoder_stream_reset()
