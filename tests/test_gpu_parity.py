@@ -764,3 +764,32 @@ def test_umma2_in_kernel_split_reduction_is_bit_identical(eng3, gold):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     report("umma2_fused_reduce", launches_separate=res[0][2], launches_fused=res[1][2])
     assert res[1][2] < res[0][2]
+
+
+def test_capacity_and_misuse_fail_loudly(eng3):
+    """Error behaviour of the C-ABI (status codes, never a silent wrong answer): sequences beyond the configured
+    maximum, a chunk-less model on the streaming entry point, a prefix the incremental MT state did not produce."""
+    from streamspeech_b200.engine import Engine, EngineError
+
+    cfg = golden_cfg()
+    e = Engine(cfg, synth.make_model_state_dict(cfg, 0), None, None, max_enc_frames=64)
+    try:
+        e.set_chunk(8, 8)
+        feats = torch.zeros(64 * 4 + 40, cfg.feat_dim, device="cuda")
+        buf = torch.zeros(128, cfg.enc_dim, device="cuda")
+        with pytest.raises(EngineError, match="max_enc_frames"):
+            e.encoder_stream_step(feats, buf)
+        with pytest.raises(EngineError, match="max_enc_frames"):
+            e.encoder(feats.unsqueeze(0))
+        e.set_chunk(None)
+        with pytest.raises(EngineError, match="chunked model"):
+            e.encoder_stream_step(feats[:40].contiguous(), buf)
+        e.set_chunk(8, 8)
+        enc = torch.randn(20, cfg.enc_dim, device="cuda")
+        e.mt_incremental_reset()
+        with pytest.raises(EngineError, match="incremental MT state is shorter"):
+            e.mt_greedy_incremental(enc, [17, 18, 19], 2, 100)
+        with pytest.raises(EngineError, match="no vocoder"):
+            e.vocoder_durations(torch.zeros(4, dtype=torch.int64, device="cuda"))
+    finally:
+        e.close()

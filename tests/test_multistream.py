@@ -127,3 +127,40 @@ def test_pooled_agents_batch_behind_push_pop():
             ref.append("" if o.is_empty else o.content)
         assert texts[j] == ref, j
     single.engine.close()
+
+
+def test_pool_edge_cases_and_errors():
+    """Empty / too-short inputs give empty results, misuse and capacity overruns fail loudly (negative status -> EngineError)."""
+    from streamspeech_b200.agent import StreamSpeechASRAgent
+    from streamspeech_b200.engine import EngineError
+    from streamspeech_b200.scheduler import StreamPool
+
+    single = StreamSpeechASRAgent(asr_args(160))
+    eng = single.engine
+    pool = StreamPool(eng, n_slots=3, max_seconds=2, ctc_heads=1)
+    a, b, c = (pool.acquire() for _ in range(3))
+    # nothing pushed at all / fewer samples than one fbank frame: T = 0, no tokens
+    pool.push(a, [])
+    pool.push(b, [0.01] * 300)
+    pool.flush()
+    assert pool.results[a]["T"] == 0 and pool.results[a]["ctc"][0] == ([], [])
+    assert pool.results[b]["T"] == 0 and pool.results[b]["ctc"][0] == ([], [])
+    # a stream that got nothing new in a round keeps its result (same T) while the other advances
+    w = synth.make_audio(1.0, seed=3)
+    pool.push(c, w[:8000])
+    pool.flush()
+    t1 = pool.results[c]["T"]
+    pool.push(c, [])
+    pool.reset(b)
+    pool.push(b, w[:8000])
+    pool.flush()
+    assert pool.results[c]["T"] == t1 and pool.results[b]["T"] == t1
+    with pytest.raises(EngineError, match="listed twice"):
+        eng.pool_step([a, a])
+    with pytest.raises(EngineError, match="bad pool slot"):
+        eng.pool_step([7])
+    with pytest.raises(EngineError, match="capacity"):
+        eng.pool_push_audio(a, torch.zeros(16000 * 3))  # the pool was sized for 2 s
+    with pytest.raises(EngineError, match="already has a stream pool"):
+        eng.pool_create(2, 2)
+    single.engine.close()
