@@ -459,7 +459,15 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
         ev0 = ev1 = nullptr;
       }
     }
-    if (persistent)
+    bool cluster_done = false;
+    if (persistent && h->persistent_encoder_cluster && h->cl_blobs && h->persist_bar &&
+        encoder_layers_cluster_supported(nA, D, c.enc_ffn, c.enc_heads, T, c.dw_kernel)) {
+      cluster_done = encoder_layers_cluster(h->persist_layers, h->cl_blobs, c.enc_layers, x, h->st_k, h->st_v, h->st_glu, nA, a0, T, h->Tpos, h->attn_chunk, cc,
+                                            c.dw_kernel, h->persist_bar, &h->persist_bar_target, h->persistent_profile ? h->persist_ts : nullptr, st) == 0;
+      if (cluster_done) ++h->cl_steps;
+      if (!cluster_done) cudaGetLastError();  // refused launch: the 148-CTA kernel below takes the step
+    }
+    if (persistent && !cluster_done)
       persistent = encoder_layers_persistent(h->persistent_alias ? h->persist_alias : h->persist_layers, c.enc_layers, x, hid, qb, att, dw, h->st_k, h->st_v, h->st_glu, nA, a0, T, D,
                                              c.enc_ffn, c.enc_heads, h->Tpos, h->attn_chunk, cc, c.dw_kernel,
                                              h->persistent_profile ? h->persist_ts : nullptr,
@@ -1141,6 +1149,18 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "umma2_fused_reduce") g_umma2_fused_reduce = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
   else if (n == "persistent_ffn_fused") h->persistent_ffn_fused = value;
+  else if (n == "persistent_encoder_cluster") {  // kernels_persist_cl.cu: weights repacked once into per-(layer, rank) blobs
+    if (value && !h->cl_blobs) {
+      if (!h->persist_layers || !h->persist_bar) return h->fail(SS_ERR_STATE, "persistent_encoder_cluster needs a finalized engine");
+      const size_t n_f = encoder_layers_cluster_blob_floats(h->cfg.enc_layers);
+      if (h->cfg.enc_dim != 256 || h->cfg.enc_ffn != 2048) return h->fail(SS_ERR_INVALID, "persistent_encoder_cluster: encoder must be 256 / 2048");
+      if (cudaMalloc(&h->cl_blobs, n_f * sizeof(float)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
+      h->dev_allocs.push_back(h->cl_blobs);
+      encoder_layers_cluster_pack(h->persist_layers, h->cfg.enc_layers, h->cfg.enc_ffn, h->cl_blobs, 0);
+      if (cudaDeviceSynchronize() != cudaSuccess) return h->fail(SS_ERR_CUDA, "packing the cluster weight blobs failed");
+    }
+    h->persistent_encoder_cluster = value;
+  }
   else if (n == "vocoder_streams") h->vocoder_streams = value;
   else if (n == "persistent_mt") h->persistent_mt = value;
   else if (n == "persistent_mt_prefix") h->persistent_mt_prefix = value;
@@ -1187,6 +1207,11 @@ int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes) 
   if (n == "umma2_ts") {
     if (!g_umma2_dbg || bytes > 16 * sizeof(unsigned long long)) return h->fail(SS_ERR_STATE, "no stamps (set option umma2_debug)");
     if (cudaMemcpy(host_dst, g_umma2_dbg, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMemcpy failed");
+    return SS_OK;
+  }
+  if (n == "cluster_steps") {  // long long: encoder steps taken by the cluster kernel so far
+    if (bytes < sizeof(long long)) return h->fail(SS_ERR_INVALID, "cluster_steps needs a long long");
+    *(long long*)host_dst = h->cl_steps;
     return SS_OK;
   }
   if (n == "persist_time") {  // double[3] = {summed ms, launches, summed algorithmic bytes} since the last query

@@ -25,6 +25,15 @@ int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, floa
                               unsigned* barrier_target_host, int prefetch /*0 off, 1 next layer, 2 also layer 0*/,
                               float* ffn_scratch_or_null /* [FFN/16][16][D]: fused FFN phases; nullptr = W1 / W2 phases */, cudaStream_t st);
 
+// ---- cluster version of the encoder step (kernels_persist_cl.cu): 4 clusters x 16 CTAs, activations in distributed shared memory,
+// weights streamed from per-(layer, rank) blobs.  nA <= 16 rows.
+size_t encoder_layers_cluster_blob_floats(int n_layers);
+void encoder_layers_cluster_pack(const PersistLayer* layers_dev, int n_layers, int FFN, float* blobs_dev, cudaStream_t st);
+bool encoder_layers_cluster_supported(int nA, int D, int FFN, int H, int T, int dw_k);
+int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_dev, int n_layers, float* x, float* kc, float* vc, float* gc, int nA,
+                           int a0, int T, int Tpos, int chunk, int conv_chunk, int dw_k, unsigned* bar_ctr, unsigned* bar_target_host,
+                           unsigned long long* ts_or_null, cudaStream_t st);
+
 // ---- MT decoder, single-token greedy steps (kernels_persist_mt.cu)
 struct MtLayerP {  // device pointers of one pre-LN decoder layer (fp32, [N][K] weights)
   const float *self_g, *self_b, *wqkv, *bqkv, *wo, *bo;

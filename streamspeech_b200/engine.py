@@ -198,6 +198,8 @@ class Engine:
         self.set_option("umma2_fused_reduce", int(os.environ.get("SS_UMMA2_FUSED_REDUCE", "0")))
         self.set_option("fbank_tma", int(os.environ.get("SS_FBANK_TMA", "1")))
         self.set_option("persistent_ffn_fused", int(os.environ.get("SS_PERSISTENT_FFN_FUSED", "1")))
+        if int(os.environ.get("SS_PERSISTENT_ENCODER_CLUSTER", "0")):
+            self.set_option("persistent_encoder_cluster", 1)
         self.set_option("persistent_mt_v2", int(os.environ.get("SS_PERSISTENT_MT_V2", "1")))
         self.set_option("persistent_mt_prefix", int(os.environ.get("SS_PERSISTENT_MT_PREFIX", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))
@@ -478,6 +480,12 @@ class Engine:
         buf = (ctypes.c_double * 3)()
         self._check(self.lib.ss_debug_copy(self._h, b"persist_time", buf, ctypes.sizeof(buf)))
         return float(buf[0]), int(buf[1]), float(buf[2])
+
+    def cluster_steps(self) -> int:
+        """encoder steps taken by the cluster kernel (option persistent_encoder_cluster) since the engine was created"""
+        buf = ctypes.c_longlong(0)
+        self._check(self.lib.ss_debug_copy(self._h, b"cluster_steps", ctypes.byref(buf), ctypes.sizeof(buf)))
+        return int(buf.value)
 
     # ------------------------------------------------------------------ multi-stream pool (ss_pool_*)
     def pool_create(self, n_slots: int, max_seconds: int = 60):

@@ -627,6 +627,40 @@ def test_persistent_kernel_variants_agree(full, option):
     e.encoder_stream_reset()
 
 
+@pytest.mark.parametrize("attn_chunk,conv_chunk,step_frames", [(8, 8, 32), (16, 16, 64), (16, 8, 64), (8, 8, 17), (32, 16, 128)])
+def test_cluster_encoder_kernel_agrees(full, attn_chunk, conv_chunk, step_frames):
+    """A / B of the cluster encoder kernel (kernels_persist_cl.cu: 4 clusters x 16 CTAs, activations in distributed shared memory,
+    weights streamed from repacked blobs) against the 148-CTA kernel on the same stream of calls, including ragged step sizes and a
+    chunk size whose steps exceed 16 active rows (those steps must fall back to the 148-CTA kernel, not fail).  Same function, different
+    summation order; the streaming caches written by one kernel are read by the other in the mixed case."""
+    cfg, e, o = full
+    e.set_chunk(attn_chunk, conv_chunk)
+    feats = e.fbank(cuda(synth.make_audio(4.0, seed=9)))
+    outs = {}
+    steps = {}
+    for v in (0, 1):
+        e.set_option("persistent_encoder_cluster", v)
+        buf = torch.zeros(1024, cfg.enc_dim, device="cuda")
+        e.encoder_stream_reset()
+        n0 = e.cluster_steps()
+        T = 0
+        snaps = []
+        for F in list(range(step_frames - 2, feats.shape[0], step_frames)) + [feats.shape[0]]:
+            T, Tf = e.encoder_stream_step(feats[:F].contiguous(), buf)
+            snaps.append(buf[:T].clone())
+        steps[v] = e.cluster_steps() - n0
+        toks = [e.ctc_greedy(h, buf[:T].contiguous())["argmax"].tolist() for h in (0, 1)]
+        outs[v] = (snaps, toks)
+    e.set_option("persistent_encoder_cluster", 0)
+    e.check_async_error()
+    assert steps[0] == 0
+    assert steps[1] > 0 or attn_chunk > 16, steps
+    d = max(maxdiff(a, b) for a, b in zip(outs[0][0], outs[1][0]))
+    report(f"cluster_encoder_{attn_chunk}_{conv_chunk}_{step_frames}", enc=d, cluster_steps=steps[1], calls=len(outs[0][0]))
+    assert d < 5e-5 and outs[0][1] == outs[1][1], d
+    e.encoder_stream_reset()
+
+
 def test_resample_48k_to_16k_vs_torchaudio(eng3):
     """f3 wire format: ss_resample_48k_to_16k against torchaudio.functional.resample (the CPU oracle of this front end; the
     reference's sox `rate` is not available in this image) on whole signals of awkward lengths, and the streaming rule
