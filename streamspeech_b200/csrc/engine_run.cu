@@ -462,8 +462,10 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
     bool cluster_done = false;
     if (persistent && h->persistent_encoder_cluster && h->cl_blobs && h->persist_bar &&
         encoder_layers_cluster_supported(nA, D, c.enc_ffn, c.enc_heads, T, c.dw_kernel)) {
-      cluster_done = encoder_layers_cluster(h->persist_layers, h->cl_blobs, c.enc_layers, x, h->st_k, h->st_v, h->st_glu, nA, a0, T, h->Tpos, h->attn_chunk, cc,
-                                            c.dw_kernel, h->persist_bar, &h->persist_bar_target, h->persistent_profile ? h->persist_ts : nullptr, st) == 0;
+      const float* pos_tabs[16];
+      for (int i = 0; i < 16; ++i) pos_tabs[i] = i < c.enc_layers ? h->enc[i].pos_proj : nullptr;
+      cluster_done = c.enc_layers <= 16 && encoder_layers_cluster(h->persist_layers, h->cl_blobs, c.enc_layers, x, h->st_k, h->st_v, h->st_glu, nA, a0, T, h->Tpos, h->attn_chunk, cc,
+                                            c.dw_kernel, h->persist_bar, &h->persist_bar_target, h->persistent_profile ? h->persist_ts : nullptr, pos_tabs, st) == 0;
       if (cluster_done) ++h->cl_steps;
       if (!cluster_done) cudaGetLastError();  // refused launch: the 148-CTA kernel below takes the step
     }
@@ -1156,7 +1158,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
       if (h->cfg.enc_dim != 256 || h->cfg.enc_ffn != 2048) return h->fail(SS_ERR_INVALID, "persistent_encoder_cluster: encoder must be 256 / 2048");
       if (cudaMalloc(&h->cl_blobs, n_f * sizeof(float)) != cudaSuccess) return h->fail(SS_ERR_CUDA, "cudaMalloc failed");
       h->dev_allocs.push_back(h->cl_blobs);
-      encoder_layers_cluster_pack(h->persist_layers, h->cfg.enc_layers, h->cfg.enc_ffn, h->cl_blobs, 0);
+      encoder_layers_cluster_pack(h->persist_layers, h->cfg.enc_layers, h->cfg.dw_kernel, h->cl_blobs, 0);
       if (cudaDeviceSynchronize() != cudaSuccess) return h->fail(SS_ERR_CUDA, "packing the cluster weight blobs failed");
     }
     h->persistent_encoder_cluster = value;

@@ -28,11 +28,12 @@ int encoder_layers_persistent(const PersistLayer* layers_dev, int n_layers, floa
 // ---- cluster version of the encoder step (kernels_persist_cl.cu): 4 clusters x 16 CTAs, activations in distributed shared memory,
 // weights streamed from per-(layer, rank) blobs.  nA <= 16 rows.
 size_t encoder_layers_cluster_blob_floats(int n_layers);
-void encoder_layers_cluster_pack(const PersistLayer* layers_dev, int n_layers, int FFN, float* blobs_dev, cudaStream_t st);
+void encoder_layers_cluster_pack(const PersistLayer* layers_dev, int n_layers, int dw_k, float* blobs_dev, cudaStream_t st);
 bool encoder_layers_cluster_supported(int nA, int D, int FFN, int H, int T, int dw_k);
 int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_dev, int n_layers, float* x, float* kc, float* vc, float* gc, int nA,
                            int a0, int T, int Tpos, int chunk, int conv_chunk, int dw_k, unsigned* bar_ctr, unsigned* bar_target_host,
-                           unsigned long long* ts_or_null, cudaStream_t st);
+                           unsigned long long* ts_or_null, const float* const* pos_proj_host /* n_layers (<= 16) device pointers */,
+                           cudaStream_t st);
 
 // ---- MT decoder, single-token greedy steps (kernels_persist_mt.cu)
 struct MtLayerP {  // device pointers of one pre-LN decoder layer (fp32, [N][K] weights)

@@ -29,14 +29,15 @@ namespace cg = cooperative_groups;
 namespace ss {
 namespace {
 
-constexpr int CT = 256;
+constexpr int CT = 256;              // compute threads (8 warps); warp 8 is the weight-copy producer
 constexpr int CWP = CT / 32;
+constexpr int CT_ALL = CT + 32;
 constexpr int CS = 16;               // cluster size
 constexpr int CR = 4;                // rows per cluster
 constexpr int NCL = 4;               // clusters
 constexpr int CD = 256;              // model dim
 constexpr int CHD = 64;
-constexpr int NSLOT = 6;
+constexpr int NSLOT = 5;
 constexpr int SLOT_FLOATS = 32 * CD; // 32 KB
 constexpr int CHUNKS_PER_LAYER = 21;
 
@@ -48,6 +49,15 @@ __host__ __device__ constexpr int chunk_row0(int j) {
   return r;
 }
 constexpr int BLOB_ROWS = chunk_row0(CHUNKS_PER_LAYER);  // 624
+// small per-layer vectors of a rank (LayerNorm parameters, the rank's bias slices, its head's pos biases, its 16 depthwise channels):
+// one 15 KB block in front of the weight rows, double-buffered in shared memory so no phase waits on a global load
+constexpr int PO_FFN1_G = 0, PO_FFN1_B = 256, PO_ATTN_G = 512, PO_ATTN_B = 768, PO_CONV_G = 1024, PO_CONV_B = 1280, PO_FFN2_G = 1536,
+              PO_FFN2_B = 1792, PO_FIN_G = 2048, PO_FIN_B = 2304, PO_FFN1_B1 = 2560, PO_FFN2_B1 = 2688, PO_FFN1_B2 = 2816, PO_FFN2_B2 = 2832,
+              PO_BQKV = 2848, PO_BO = 2896, PO_PW1B = 2912, PO_PW2B = 2944, PO_BN_S = 2960, PO_BN_H = 2976, PO_POSU = 2992, PO_POSV = 3056,
+              PO_DW = 3120, PO_END = PO_DW + 31 * 16;
+constexpr int PAR_FLOATS = 15 * CD;  // 3840 >= PO_END (3616)
+static_assert(PO_END <= PAR_FLOATS, "parameter block");
+constexpr size_t BLOB_STRIDE = (size_t)PAR_FLOATS + (size_t)BLOB_ROWS * CD;  // floats per (layer, rank)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -67,8 +77,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// CTA barrier of the 8 compute warps (the producer warp never joins it)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
-  __syncthreads();
+  csync();
   target += gridDim.x;
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
@@ -79,7 +92,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     if ((int)(v - target) < 0) atomicExch(ctr + SS_BAR_ERR_WORD, 1u);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
-  __syncthreads();
+  csync();
 }
 
 struct ClSmem {
@@ -93,11 +106,14 @@ struct ClSmem {
   float pv[CWP][CHD];
   float redw[CWP];
   float outc[CR][48];        // raw outputs of a column-split GEMM (q | k | v, or 32 GLU inputs, or 16 columns)
+  float par[2][PAR_FLOATS];  // parameter block of layer li in par[li & 1]
   unsigned long long full[NSLOT];
+  unsigned long long empty[NSLOT];  // one arrival per warp when it has finished reading the slot
+  unsigned long long parfull[2];
 };
 
 // As[r][:] = LN(xs[r][:]) * g + b (warp r; rows are complete in every CTA); ends with a CTA barrier
-__device__ __forceinline__ void stage_ln(ClSmem& sm, const float* __restrict__ g, const float* __restrict__ b) {
+__device__ __forceinline__ void stage_ln(ClSmem& sm, const float* g, const float* b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp < CR) {
     float v[8];
@@ -120,72 +136,114 @@ __device__ __forceinline__ void stage_ln(ClSmem& sm, const float* __restrict__ g
       sm.As[warp][c] = (v[i] - mean) * rstd * g[c] + b[c];
     }
   }
-  __syncthreads();
+  csync();
 }
 
-// out(j, r, value) = sum_k As[r][k] * w[j][k] for the `rows` (<= 32) weight rows of a ring chunk (row-major, 256 floats each).
-// Warp w takes weight rows w, w + 8, w + 16, w + 24; the 16 (weight row, activation row) sums of a warp are reduced with a halving
-// tree (16 shuffles); even lane 2v ends with the value v = slot * 4 + r.
-template <typename F>
-__device__ __forceinline__ void chunk_gemm(const ClSmem& sm, const float* wchunk, int rows, F&& out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 x[CR][2];
+// Column-split GEMM of one ring chunk (row-major weight rows of 256 floats, `rows` = 32 or 16 of them) against the 4 staged rows As.
+// Lane l holds x[r][4 l .. 4 l + 4) and x[r][128 + 4 l ..) of the 4 rows in registers for the whole phase (load_x) and reads its 32 B
+// of each weight row (every lane a distinct 16 B: full-rate 128-bit shared-memory loads, each weight byte read once); the 16 (weight
+// row j = warp + 8 s, activation row r) partial sums of a warp are reduced over the 32 lanes with a halving tree (16 shuffles);
+// even lane 2 v ends with the sum v = s * 4 + r.  (A (k group, row) lane mapping needs 4 shuffles but 4 x the shared-memory
+// wavefronts -- lanes sharing a 16 B address still cost a quarter-warp phase each -- and measured slower.)
+struct XRegs {
+  float4 v[CR][2];
+};
+__device__ __forceinline__ void load_x(const ClSmem& sm, XRegs& x) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < CR; ++r) {
-    x[r][0] = *reinterpret_cast<const float4*>(&sm.As[r][lane * 4]);
-    x[r][1] = *reinterpret_cast<const float4*>(&sm.As[r][128 + lane * 4]);
+    x.v[r][0] = *reinterpret_cast<const float4*>(&sm.As[r][lane * 4]);
+    x.v[r][1] = *reinterpret_cast<const float4*>(&sm.As[r][128 + lane * 4]);
   }
-  float acc[16];
+}
+
+template <int rows>
+__device__ __forceinline__ void chunk_fma(const XRegs& x, const float* wchunk, float (&acc)[16]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
-    const int j = warp + s * CWP;
-    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-    if (j < rows) {
-      w0 = *reinterpret_cast<const float4*>(wchunk + j * CD + lane * 4);
-      w1 = *reinterpret_cast<const float4*>(wchunk + j * CD + 128 + lane * 4);
+    if (s * CWP >= rows) {  // (compile time: a 16-row chunk has two weight rows per warp)
+#pragma unroll
+      for (int r = 0; r < CR; ++r) acc[s * 4 + r] = 0.f;
+      continue;
     }
+    const float4 w0 = *reinterpret_cast<const float4*>(wchunk + (warp + s * CWP) * CD + lane * 4);
+    const float4 w1 = *reinterpret_cast<const float4*>(wchunk + (warp + s * CWP) * CD + 128 + lane * 4);
 #pragma unroll
     for (int r = 0; r < CR; ++r) {
-      float a = x[r][0].x * w0.x;
-      a = fmaf(x[r][0].y, w0.y, a);
-      a = fmaf(x[r][0].z, w0.z, a);
-      a = fmaf(x[r][0].w, w0.w, a);
-      a = fmaf(x[r][1].x, w1.x, a);
-      a = fmaf(x[r][1].y, w1.y, a);
-      a = fmaf(x[r][1].z, w1.z, a);
-      a = fmaf(x[r][1].w, w1.w, a);
+      float a = x.v[r][0].x * w0.x;
+      a = fmaf(x.v[r][0].y, w0.y, a);
+      a = fmaf(x.v[r][0].z, w0.z, a);
+      a = fmaf(x.v[r][0].w, w0.w, a);
+      a = fmaf(x.v[r][1].x, w1.x, a);
+      a = fmaf(x.v[r][1].y, w1.y, a);
+      a = fmaf(x.v[r][1].z, w1.z, a);
+      a = fmaf(x.v[r][1].w, w1.w, a);
       acc[s * 4 + r] = a;
     }
   }
+}
+
+template <int rows>
+__device__ __forceinline__ float chunk_tree(const float (&acc)[16]) {
+  const int lane = threadIdx.x & 31;
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-  float w8[8], w4[4], w2[2];
+  float w4[4], w2[2];
+  if (rows > 16) {
+    float w8[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = b4 ? acc[i] : acc[i + 8];
-    const float keep = b4 ? acc[i + 8] : acc[i];
-    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    for (int i = 0; i < 8; ++i) w8[i] = (b4 ? acc[i + 8] : acc[i]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[i] : acc[i + 8], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w4[i] = (b3 ? w8[i + 4] : w8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? w8[i] : w8[i + 4], 8);
+  } else {
+    // slots 0, 1 only: 8 sums; bit 4 is summed in full, bit 3 selects the slot
+    float w8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w8[i] = acc[i] + __shfl_xor_sync(0xffffffffu, acc[i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w4[i] = (b3 ? w8[i + 4] : w8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? w8[i] : w8[i + 4], 8);
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = b3 ? w8[i] : w8[i + 4];
-    const float keep = b3 ? w8[i + 4] : w8[i];
-    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  for (int i = 0; i < 2; ++i) w2[i] = (b2 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? w4[i] : w4[i + 2], 4);
+  float v = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// out(j, r, value) on the lane that owns (weight row j of the chunk, activation row r).  rows = 32: lane bits (4, 3) = s, bits (2, 1)
+// = r; rows = 16: bit 3 = s (bit 4 lanes hold copies), bits (2, 1) = r
+template <int rows, typename F>
+__device__ __forceinline__ void chunk_epi(float v, F&& out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool owner = rows > 16 ? (lane & 1) == 0 : (lane & 17) == 0;
+  if (owner) {
+    const int s = rows > 16 ? (lane >> 3) : ((lane >> 3) & 1);
+    out(warp + s * CWP, (lane >> 1) & 3, v);
   }
+}
+
+template <int rows, typename F>
+__device__ __forceinline__ void chunk_gemm(const XRegs& x, const float* wchunk, F&& out) {
+  float acc[16];
+  chunk_fma<rows>(x, wchunk, acc);
+  chunk_epi<rows>(chunk_tree<rows>(acc), out);
+}
+
+// Two 32-row chunks through ONE tree: 32 partial sums (index = chunk * 16 + s * 4 + r) -> every lane ends with one complete sum
+// (lane bit 4 = chunk, bits (3, 2) = s, bits (1, 0) = r): 31 shuffles for two chunks in 5 dependent levels instead of 2 x 5
+__device__ __forceinline__ float pair_tree(const float (&a0)[16], const float (&a1)[16]) {
+  const int lane = threadIdx.x & 31;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+  float w16[16], w8[8], w4[4], w2[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = b2 ? w4[i] : w4[i + 2];
-    const float keep = b2 ? w4[i + 2] : w4[i];
-    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const float send = b1 ? w2[0] : w2[1];
-  const float keep = b1 ? w2[1] : w2[0];
-  float v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-  if ((lane & 1) == 0) {
-    const int v = lane >> 1;  // = slot * 4 + r
-    const int j = warp + (v >> 2) * CWP;
-    if (j < rows) out(j, v & 3, v1);
-  }
+  for (int i = 0; i < 16; ++i) w16[i] = (b4 ? a1[i] : a0[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a0[i] : a1[i], 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w8[i] = (b3 ? w16[i + 8] : w16[i]) + __shfl_xor_sync(0xffffffffu, b3 ? w16[i] : w16[i + 8], 8);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w4[i] = (b2 ? w8[i + 4] : w8[i]) + __shfl_xor_sync(0xffffffffu, b2 ? w8[i] : w8[i + 4], 4);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) w2[i] = (b1 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(0xffffffffu, b1 ? w4[i] : w4[i + 2], 2);
+  return (b0 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1);
 }
 
 struct ClParams {
@@ -197,10 +255,11 @@ struct ClParams {
   int nA, a0, T, Tpos, chunk, conv_chunk, dw_k;
   unsigned* bar_ctr;
   unsigned bar_target;
+  const float* pos_proj[16];   // per layer: projected relative-position table [2 * Tpos - 1][256]
   unsigned long long* ts;      // profiling (option persistent_profile): ts[0] = number of stamps, then (id, ns) pairs of CTA 0, layer 1
 };
 
-__global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams P) {
+__global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClParams P) {  // (9 warps are allocated like 12: 168 registers)
   extern __shared__ __align__(128) unsigned char dyn[];
   ClSmem& sm = *reinterpret_cast<ClSmem*>(dyn);
   float* ring = reinterpret_cast<float*>(dyn + ((sizeof(ClSmem) + 127) & ~(size_t)127));
@@ -219,34 +278,94 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
     const int slot = qi % NSLOT;
     const int li = qi / CHUNKS_PER_LAYER, j = qi - li * CHUNKS_PER_LAYER;
     const uint32_t bytes = (uint32_t)chunk_rows(j) * CD * 4u;
-    const float* src = P.blobs + ((size_t)(li * CS + c) * BLOB_ROWS + chunk_row0(j)) * CD;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the slot are ordered before the async write
+    const float* src = P.blobs + (size_t)(li * CS + c) * BLOB_STRIDE + PAR_FLOATS + (size_t)chunk_row0(j) * CD;
+    // (WAR on the slot: the readers' mbarrier arrivals, observed by this thread, order their reads before the copy)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm.full[slot])), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ring + (size_t)slot * SLOT_FLOATS)),
                  "l"(src), "r"(bytes), "r"(smem_u32(&sm.full[slot]))
                  : "memory");
   };
+  auto issue_par = [&](int li) {
+    if (li >= P.n_layers) return;
+    const uint32_t bytes = PAR_FLOATS * 4u;
+    const uint32_t bar = smem_u32(&sm.parfull[li & 1]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm.par[li & 1][0])),
+                 "l"(P.blobs + (size_t)(li * CS + c) * BLOB_STRIDE), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.full[i])));
+    for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sm.empty[i])), "r"(CWP));
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.parfull[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue_par(0);
+    issue_par(1);
     for (int i = 0; i < NSLOT; ++i) issue(i);
   }
   // residual rows of the cluster (zero rows where the cluster has fewer than 4)
-  for (int i = tid; i < CR * CD; i += CT) {
+  for (int i = tid; i < CR * CD; i += CT_ALL) {
     const int r = i / CD;
     sm.xs[r][i - r * CD] = r < nr ? P.x[(int64_t)(r_lo + r) * CD + (i - r * CD)] : 0.f;
   }
   __syncthreads();
   cluster.sync();  // every CTA of the cluster runs and has initialised its shared memory before any DSMEM traffic
 
+  if (warp == CWP) {
+    // ---- producer warp: lane 0 refills a slot as soon as all 8 compute warps have released it.  It joins every cluster barrier (all
+    // threads of the cluster must), so it services exactly the releases that precede each one: per layer
+    //   FFN 8 | 0 | q k v 2 | attention 0 | Wo 1 | PW1 1 | PW2 1 | FFN 8 | 0
+    int issued = NSLOT;
+    auto service = [&](int n) {
+      if (lane == 0) {
+        for (int k = 0; k < n && issued < total_chunks; ++k, ++issued) {
+          mbar_wait(smem_u32(&sm.empty[issued % NSLOT]), (uint32_t)(((issued - NSLOT) / NSLOT) & 1));
+          issue(issued);
+        }
+      }
+      __syncwarp();
+    };
+    // L2 prefetch of what this CTA's attention task of layer `pl` will read (rows of earlier steps: the weight stream of a step evicts them)
+    auto prefetch_attn = [&](int pl) {
+      const int r = c & 3, h = c >> 2;
+      if (pl < P.n_layers && r < nr) {
+        const int i = P.a0 + r_lo + r;
+        const int lim = min(P.chunk > 0 ? min((i / P.chunk + 1) * P.chunk, P.T) : P.T, P.a0);
+        const char* kb = reinterpret_cast<const char*>(P.kc + (size_t)pl * P.Tpos * CD + h * CHD);
+        const char* vb = reinterpret_cast<const char*>(P.vc + (size_t)pl * P.Tpos * CD + h * CHD);
+        const char* pb = reinterpret_cast<const char*>(P.pos_proj[pl] + h * CHD);
+        for (int x = lane; x < 2 * lim; x += 32) {
+          const int j = x >> 1;
+          const size_t off = (size_t)j * CD * 4 + (x & 1) * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + off));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + off));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)(i - j + P.Tpos - 1) * CD * 4 + (x & 1) * 128));
+        }
+      }
+    };
+    prefetch_attn(0);
+    for (int li = 0; li < P.n_layers; ++li) {
+      const int seg[9] = {8, 0, 2, 0, 1, 1, 1, 8, 0};
+#pragma unroll
+      for (int x = 0; x < 9; ++x) {
+        service(seg[x]);
+        cluster.sync();
+        // every compute thread of the CTA is past layer li - 1 (it has arrived at this layer's first barrier): its parameter buffer is free
+        if (x == 0 && li >= 1 && lane == 0) issue_par(li + 1);
+        if (x == 2) prefetch_attn(li + 1);  // (the attention segment: nothing to refill)
+      }
+    }
+    cluster.sync();
+    return;
+  }
   int q = 0;  // chunk counter
   auto acquire = [&]() -> const float* {
     mbar_wait(smem_u32(&sm.full[q % NSLOT]), (uint32_t)((q / NSLOT) & 1));
     return ring + (size_t)(q % NSLOT) * SLOT_FLOATS;
   };
-  auto release = [&]() {  // every thread has finished reading the slot -> refill it with the chunk NSLOT ahead
-    __syncthreads();
-    if (tid == 0) issue(q + NSLOT);
+  auto release = [&]() {  // this warp has finished reading the slot
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.empty[q % NSLOT])) : "memory");
     ++q;
   };
   int nts = 0;
@@ -261,25 +380,47 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
   auto peer = [&](float* p, int rank) -> float* { return cluster.map_shared_rank(p, rank); };
 
   // ---- FFN block: xs += 0.5 * (W2 silu(W1 LN(xs) + b1) + b2); chunks [base, base + 8) of the layer
-  auto ffn = [&](const float* __restrict__ g_, const float* __restrict__ b_, const float* __restrict__ b1, const float* __restrict__ b2) {
+  int li_ = 0;
+  auto ffn = [&](const float* g_, const float* b_, const float* b1, const float* b2) {
     stage_ln(sm, g_, b_);
-    for (int part = 0; part < 4; ++part) {
-      const float* w = acquire();
-      chunk_gemm(sm, w, 32, [&](int j, int r, float v) {
-        const float y = v + b1[c * 128 + part * 32 + j];
-        sm.hs[r][part * 32 + j] = y / (1.0f + expf(-y));
-      });
-      release();  // (its CTA barrier also publishes hs)
+    stamp(5);
+    {
+      XRegs x;
+      load_x(sm, x);
+#pragma unroll
+      for (int pair = 0; pair < 2; ++pair) {
+        float a0[16], a1[16];
+        chunk_fma<32>(x, acquire(), a0);
+        release();
+        chunk_fma<32>(x, acquire(), a1);
+        release();
+        const float v = pair_tree(a0, a1);
+        // lane = chunk * 16 + s * 4 + r  ->  hidden unit (of this rank's 128) = (2 pair + chunk) * 32 + warp + 8 s
+        const int u = (2 * pair + (lane >> 4)) * 32 + warp + ((lane >> 2) & 3) * CWP;
+        const float y = v + b1[u];
+        sm.hs[lane & 3][u] = __fdividef(y, 1.0f + expf(-y));
+      }
     }
+    csync();  // hs complete
     stamp(1);
     float acc[CR] = {0.f, 0.f, 0.f, 0.f};  // thread n = tid: output column n of the rank-128 update
     for (int part = 0; part < 4; ++part) {
       const float* w = acquire();
-#pragma unroll 8
-      for (int u = 0; u < 32; ++u) {
-        const float wv = w[u * CD + tid];
 #pragma unroll
-        for (int r = 0; r < CR; ++r) acc[r] = fmaf(sm.hs[r][part * 32 + u], wv, acc[r]);
+      for (int u = 0; u < 32; u += 4) {
+        float wv[4];
+        float4 hv[CR];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) wv[x] = w[(u + x) * CD + tid];
+#pragma unroll
+        for (int r = 0; r < CR; ++r) hv[r] = *reinterpret_cast<const float4*>(&sm.hs[r][part * 32 + u]);
+#pragma unroll
+        for (int r = 0; r < CR; ++r) {
+          acc[r] = fmaf(hv[r].x, wv[0], acc[r]);
+          acc[r] = fmaf(hv[r].y, wv[1], acc[r]);
+          acc[r] = fmaf(hv[r].z, wv[2], acc[r]);
+          acc[r] = fmaf(hv[r].w, wv[3], acc[r]);
+        }
       }
       release();
     }
@@ -294,7 +435,7 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
       float t = sm.red[0][r][j];
 #pragma unroll
       for (int s = 1; s < CS; ++s) t += sm.red[s][r][j];
-      const float y = sm.xs[r][c * 16 + j] + 0.5f * (t + b2[c * 16 + j]);
+      const float y = sm.xs[r][c * 16 + j] + 0.5f * (t + b2[j]);
 #pragma unroll
       for (int d = 0; d < CS; ++d) peer(&sm.xs[r][c * 16 + j], d)[0] = y;
     }
@@ -302,11 +443,11 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
     stamp(4);
   };
   // xs[:, 16c..16c+16) += outc[:, 0..16) + bias, all-gathered (column-split GEMM epilogue)
-  auto residual_gather = [&](const float* __restrict__ bias) {
-    __syncthreads();
+  auto residual_gather = [&](const float* bias) {
+    csync();
     if (tid < CR * 16) {
       const int r = tid >> 4, j = tid & 15;
-      const float y = sm.xs[r][c * 16 + j] + (sm.outc[r][j] + (bias ? bias[c * 16 + j] : 0.f));
+      const float y = sm.xs[r][c * 16 + j] + (sm.outc[r][j] + bias[j]);
 #pragma unroll
       for (int d = 0; d < CS; ++d) peer(&sm.xs[r][c * 16 + j], d)[0] = y;
     }
@@ -314,23 +455,29 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
   };
 
   for (int li = 0; li < P.n_layers; ++li) {
-    const PersistLayer L = P.layers[li];
+    const float* pos_proj = P.pos_proj[li];
+    li_ = li;
+    mbar_wait(smem_u32(&sm.parfull[li & 1]), (uint32_t)((li >> 1) & 1));
+    const float* par = sm.par[li & 1];
     stamping = P.ts != nullptr && blockIdx.x == 0 && li == 1;
     stamp(0);
     float* kc = P.kc + (size_t)li * P.Tpos * CD;
     float* vc = P.vc + (size_t)li * P.Tpos * CD;
     float* gc = P.gc + (size_t)li * P.Tpos * CD;
-    ffn(L.ffn1_g, L.ffn1_b, L.ffn1_b1, L.ffn1_b2);
+    ffn(par + PO_FFN1_G, par + PO_FFN1_B, par + PO_FFN1_B1, par + PO_FFN1_B2);
     // ================= attention block =================
-    stage_ln(sm, L.attn_g, L.attn_b);
+    stage_ln(sm, par + PO_ATTN_G, par + PO_ATTN_B);
     {
+      XRegs x;
+      load_x(sm, x);
       const float* w = acquire();  // q rows 0..15, k rows 16..31
-      chunk_gemm(sm, w, 32, [&](int j, int r, float v) { sm.outc[r][j] = v + L.bqkv[(j >> 4) * CD + c * 16 + (j & 15)]; });
+      chunk_gemm<32>(x, w, [&](int j, int r, float v) { sm.outc[r][j] = v + par[PO_BQKV + j]; });
       release();
       w = acquire();               // v rows
-      chunk_gemm(sm, w, 16, [&](int j, int r, float v) { sm.outc[r][32 + j] = v + L.bqkv[2 * CD + c * 16 + j]; });
+      chunk_gemm<16>(x, w, [&](int j, int r, float v) { sm.outc[r][32 + j] = v + par[PO_BQKV + 32 + j]; });
       release();
     }
+    csync();
     if (tid < CR * 16) {
       const int r = tid >> 4, j = tid & 15;
       if (r < nr) {
@@ -354,42 +501,56 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
         const int n = max(1, lim);
         if (tid < CHD) {
           const float val = sm.qh[tid];
-          sm.qa[tid] = val + L.pos_u[h * CHD + tid];
-          sm.qb[tid] = val + L.pos_v[h * CHD + tid];
+          sm.qa[tid] = val + par[PO_POSU + tid];
+          sm.qb[tid] = val + par[PO_POSV + tid];
         }
-        __syncthreads();
+        csync();
+        stamp(120);
         const float* kb = kc + h * CHD;
         const float* vb = vc + h * CHD;
-        const float* pb = L.pos_proj + h * CHD;
+        const float* pb = pos_proj + h * CHD;
         float mx = -INFINITY;
-        for (int j = tid; j < n; j += CT) {
-          const float* kr = kb + (int64_t)j * CD;
-          const float* pr = pb + (int64_t)(i - j + P.Tpos - 1) * CD;
-          float4 kk[CHD / 4], pp[CHD / 4];
+        {
+          // half a warp per key: lane l16 holds dims [4 * l16, 4 * l16 + 4) of q + u, q + v and loads 16 B of the key row and of the
+          // relative-position row (256 B contiguous per half-warp); 8 keys per half-warp in flight
+          const int hw = lane >> 4, l16 = lane & 15;
+          const float4 qa4 = *reinterpret_cast<const float4*>(&sm.qa[4 * l16]);
+          const float4 qb4 = *reinterpret_cast<const float4*>(&sm.qb[4 * l16]);
+          for (int j0 = 0; j0 < n; j0 += 8 * 2 * CWP) {
+            float4 kk[8], pp[8];
 #pragma unroll
-          for (int d = 0; d < CHD / 4; ++d) {
-            kk[d] = *reinterpret_cast<const float4*>(kr + 4 * d);
-            pp[d] = *reinterpret_cast<const float4*>(pr + 4 * d);
-          }
-          float ac = 0.f, bd = 0.f;
+            for (int u = 0; u < 8; ++u) {
+              const int j = j0 + u * 2 * CWP + warp * 2 + hw;
+              const bool ok = j < n;
+              kk[u] = ok ? *reinterpret_cast<const float4*>(kb + (int64_t)j * CD + 4 * l16) : make_float4(0.f, 0.f, 0.f, 0.f);
+              pp[u] = ok ? *reinterpret_cast<const float4*>(pb + (int64_t)(i - j + P.Tpos - 1) * CD + 4 * l16) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-          for (int d = 0; d < CHD / 4; ++d) {
-            ac = fmaf(sm.qa[4 * d], kk[d].x, ac); ac = fmaf(sm.qa[4 * d + 1], kk[d].y, ac);
-            ac = fmaf(sm.qa[4 * d + 2], kk[d].z, ac); ac = fmaf(sm.qa[4 * d + 3], kk[d].w, ac);
-            bd = fmaf(sm.qb[4 * d], pp[d].x, bd); bd = fmaf(sm.qb[4 * d + 1], pp[d].y, bd);
-            bd = fmaf(sm.qb[4 * d + 2], pp[d].z, bd); bd = fmaf(sm.qb[4 * d + 3], pp[d].w, bd);
+            for (int u = 0; u < 8; ++u) {
+              const int j = j0 + u * 2 * CWP + warp * 2 + hw;
+              float sc = qa4.x * kk[u].x;
+              sc = fmaf(qa4.y, kk[u].y, sc); sc = fmaf(qa4.z, kk[u].z, sc); sc = fmaf(qa4.w, kk[u].w, sc);
+              sc = fmaf(qb4.x, pp[u].x, sc); sc = fmaf(qb4.y, pp[u].y, sc); sc = fmaf(qb4.z, pp[u].z, sc); sc = fmaf(qb4.w, pp[u].w, sc);
+              sc += __shfl_xor_sync(0xffffffffu, sc, 8);
+              sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+              sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+              sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+              if (l16 == 0 && j < n) {
+                sc *= 0.125f;
+                sm.S[j] = sc;
+                mx = fmaxf(mx, sc);
+              }
+            }
           }
-          const float s = (ac + bd) * 0.125f;
-          sm.S[j] = s;
-          mx = fmaxf(mx, s);
         }
+        stamp(121);
         mx = warp_max(mx);
         if (lane == 0) sm.redw[warp] = mx;
-        __syncthreads();
+        csync();
         mx = sm.redw[0];
 #pragma unroll
         for (int x = 1; x < CWP; ++x) mx = fmaxf(mx, sm.redw[x]);
-        __syncthreads();
+        csync();
         float sum = 0.f;
         for (int j = tid; j < n; j += CT) {
           const float e = expf(sm.S[j] - mx);
@@ -398,10 +559,11 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
         }
         sum = warp_sum(sum);
         if (lane == 0) sm.redw[warp] = sum;
-        __syncthreads();
+        csync();
         sum = sm.redw[0];
 #pragma unroll
         for (int x = 1; x < CWP; ++x) sum += sm.redw[x];
+        stamp(122);
         float a0_ = 0.f, a1_ = 0.f;
         for (int j0 = warp; j0 < n; j0 += CWP * 16) {
           float2 vv[16];
@@ -419,9 +581,10 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
             a1_ = fmaf(p[u], vv[u].y, a1_);
           }
         }
+        stamp(123);
         sm.pv[warp][2 * lane] = a0_;
         sm.pv[warp][2 * lane + 1] = a1_;
-        __syncthreads();
+        csync();
         if (tid < CHD) {
           float t = 0.f;
 #pragma unroll
@@ -439,20 +602,25 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
     cluster.sync();
     stamp(14);
     {
+      XRegs x;
+      load_x(sm, x);
       const float* w = acquire();  // Wo rows [16c, 16c+16)
-      chunk_gemm(sm, w, 16, [&](int j, int r, float v) { sm.outc[r][j] = v; });
+      chunk_gemm<16>(x, w, [&](int j, int r, float v) { sm.outc[r][j] = v; });
       release();
     }
     stamp(15);
-    residual_gather(L.bo);
+    residual_gather(par + PO_BO);
     stamp(16);
     // ================= conv module =================
-    stage_ln(sm, L.conv_g, L.conv_b);
+    stage_ln(sm, par + PO_CONV_G, par + PO_CONV_B);
     {
+      XRegs x;
+      load_x(sm, x);
       const float* w = acquire();  // PW1: interleaved (value, gate) rows of channels [16c, 16c+16)
-      chunk_gemm(sm, w, 32, [&](int j, int r, float v) { sm.outc[r][j] = v + (L.pw1_b ? L.pw1_b[c * 32 + j] : 0.f); });
+      chunk_gemm<32>(x, w, [&](int j, int r, float v) { sm.outc[r][j] = v + par[PO_PW1B + j]; });
       release();
     }
+    csync();
     if (tid < CR * 16) {
       const int r = tid >> 4, ch = tid & 15;
       if (r < nr) {
@@ -469,12 +637,16 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
       if (r < nr) {
         const int t = P.a0 + r_lo + r, half = (P.dw_k - 1) >> 1;
         const int lim = P.conv_chunk > 0 ? min(P.T, (t / P.conv_chunk + 1) * P.conv_chunk) : P.T;
-        float a = 0.f;
-        for (int j = 0; j < P.dw_k; ++j) {
+        float gv[31];
+#pragma unroll
+        for (int j = 0; j < 31; ++j) {  // all taps in flight (rows outside the sequence / chunk and taps >= dw_k contribute 0)
           const int p = t - half + j;
-          if (p >= 0 && p < lim) a = fmaf(L.dw_w[j * CD + oc], gc[(int64_t)p * CD + oc], a);
+          gv[j] = (j < P.dw_k && p >= 0 && p < lim) ? gc[(int64_t)p * CD + oc] : 0.f;
         }
-        const float v = a * L.bn_scale[oc] + L.bn_shift[oc];
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 31; ++j) a = fmaf(par[PO_DW + j * 16 + ch], gv[j], a);
+        const float v = a * par[PO_BN_S + ch] + par[PO_BN_H + ch];
         y = v / (1.0f + expf(-v));
       }
 #pragma unroll
@@ -484,14 +656,16 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
     cluster.sync();
     stamp(23);
     {
+      XRegs x;
+      load_x(sm, x);
       const float* w = acquire();  // PW2 rows [16c, 16c+16)
-      chunk_gemm(sm, w, 16, [&](int j, int r, float v) { sm.outc[r][j] = v; });
+      chunk_gemm<16>(x, w, [&](int j, int r, float v) { sm.outc[r][j] = v; });
       release();
     }
     stamp(24);
-    residual_gather(L.pw2_b);
+    residual_gather(par + PO_PW2B);
     stamp(25);
-    ffn(L.ffn2_g, L.ffn2_b, L.ffn2_b1, L.ffn2_b2);
+    ffn(par + PO_FFN2_G, par + PO_FFN2_B, par + PO_FFN2_B1, par + PO_FFN2_B2);
     // final LayerNorm of the layer, in place (every CTA holds the complete rows: no exchange)
     if (warp < CR) {
       float v[8];
@@ -511,12 +685,14 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int cc = lane + (i << 5);
-        sm.xs[warp][cc] = (v[i] - mean) * rstd * L.fin_g[cc] + L.fin_b[cc];
+        sm.xs[warp][cc] = (v[i] - mean) * rstd * par[PO_FIN_G + cc] + par[PO_FIN_B + cc];
       }
     }
-    __syncthreads();
+    csync();
     stamp(30);
-    if (stamping && tid == 0) P.ts[0] = (unsigned long long)nts;
+    if (stamping && tid == 0) {
+      P.ts[0] = (unsigned long long)nts;
+    }
   }
   if (c == 0) {
     for (int i = tid; i < nr * CD; i += CT) P.x[(int64_t)r_lo * CD + i] = sm.xs[i / CD][i % CD];
@@ -524,8 +700,8 @@ __global__ void __launch_bounds__(CT, 1) encoder_layers_cluster_kernel(ClParams 
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
 
-// blob row `row` of (layer li, rank c): see chunk table above.  One thread per float4.
-__global__ void cluster_pack_kernel(const PersistLayer* __restrict__ layers, int n_layers, int FFN, float* __restrict__ blobs) {
+// weight row `row` of (layer li, rank c): see the chunk table above.  One thread per float4.
+__global__ void cluster_pack_kernel(const PersistLayer* __restrict__ layers, int n_layers, float* __restrict__ blobs) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   const int64_t total = (int64_t)n_layers * CS * BLOB_ROWS * (CD / 4);
   if (idx >= total) return;
@@ -546,17 +722,48 @@ __global__ void cluster_pack_kernel(const PersistLayer* __restrict__ layers, int
   else if (row < 368) src = L.pw2 + (int64_t)(c * 16 + row - 352) * CD;
   else if (row < 496) src = L.ffn2_w1 + (int64_t)(c * 128 + row - 368) * CD;
   else src = L.ffn2_w2t + (int64_t)(c * 128 + row - 496) * CD;
-  (void)FFN;
-  reinterpret_cast<float4*>(blobs)[idx] = reinterpret_cast<const float4*>(src)[k4];
+  float* dst = blobs + (size_t)(li * CS + c) * BLOB_STRIDE + PAR_FLOATS + (size_t)row * CD;
+  reinterpret_cast<float4*>(dst)[k4] = reinterpret_cast<const float4*>(src)[k4];
+}
+
+// parameter block of (layer li, rank c): one thread per float
+__global__ void cluster_pack_params_kernel(const PersistLayer* __restrict__ layers, int n_layers, int dw_k, float* __restrict__ blobs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_layers * CS * PAR_FLOATS) return;
+  const int o = idx % PAR_FLOATS, c = (idx / PAR_FLOATS) % CS, li = idx / (PAR_FLOATS * CS);
+  const PersistLayer& L = layers[li];
+  float v = 0.f;
+  if (o < PO_FFN1_B1) {
+    const float* tab[10] = {L.ffn1_g, L.ffn1_b, L.attn_g, L.attn_b, L.conv_g, L.conv_b, L.ffn2_g, L.ffn2_b, L.fin_g, L.fin_b};
+    v = tab[o >> 8][o & 255];
+  } else if (o < PO_FFN2_B1) v = L.ffn1_b1[c * 128 + o - PO_FFN1_B1];
+  else if (o < PO_FFN1_B2) v = L.ffn2_b1[c * 128 + o - PO_FFN2_B1];
+  else if (o < PO_FFN2_B2) v = L.ffn1_b2[c * 16 + o - PO_FFN1_B2];
+  else if (o < PO_BQKV) v = L.ffn2_b2[c * 16 + o - PO_FFN2_B2];
+  else if (o < PO_BO) v = L.bqkv[((o - PO_BQKV) >> 4) * CD + c * 16 + ((o - PO_BQKV) & 15)];
+  else if (o < PO_PW1B) v = L.bo[c * 16 + o - PO_BO];
+  else if (o < PO_PW2B) v = L.pw1_b ? L.pw1_b[c * 32 + o - PO_PW1B] : 0.f;
+  else if (o < PO_BN_S) v = L.pw2_b ? L.pw2_b[c * 16 + o - PO_PW2B] : 0.f;
+  else if (o < PO_BN_H) v = L.bn_scale[c * 16 + o - PO_BN_S];
+  else if (o < PO_POSU) v = L.bn_shift[c * 16 + o - PO_BN_H];
+  else if (o < PO_POSV) v = L.pos_u[(c >> 2) * CHD + o - PO_POSU];
+  else if (o < PO_DW) v = L.pos_v[(c >> 2) * CHD + o - PO_POSV];
+  else if (o < PO_END) {
+    const int tap = (o - PO_DW) >> 4, ch = (o - PO_DW) & 15;
+    v = tap < dw_k ? L.dw_w[tap * CD + c * 16 + ch] : 0.f;
+  }
+  blobs[(size_t)(li * CS + c) * BLOB_STRIDE + o] = v;
 }
 
 }  // namespace
 
-size_t encoder_layers_cluster_blob_floats(int n_layers) { return (size_t)n_layers * CS * BLOB_ROWS * CD; }
+size_t encoder_layers_cluster_blob_floats(int n_layers) { return (size_t)n_layers * CS * BLOB_STRIDE; }
 
-void encoder_layers_cluster_pack(const PersistLayer* layers_dev, int n_layers, int FFN, float* blobs_dev, cudaStream_t st) {
+void encoder_layers_cluster_pack(const PersistLayer* layers_dev, int n_layers, int dw_k, float* blobs_dev, cudaStream_t st) {
   const int64_t total = (int64_t)n_layers * CS * BLOB_ROWS * (CD / 4);
-  cluster_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(layers_dev, n_layers, FFN, blobs_dev);
+  cluster_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(layers_dev, n_layers, blobs_dev);
+  const int np = n_layers * CS * PAR_FLOATS;
+  cluster_pack_params_kernel<<<(np + 255) / 256, 256, 0, st>>>(layers_dev, n_layers, dw_k, blobs_dev);
 }
 
 bool encoder_layers_cluster_supported(int nA, int D, int FFN, int H, int T, int dw_k) {
@@ -565,7 +772,8 @@ bool encoder_layers_cluster_supported(int nA, int D, int FFN, int H, int T, int 
 
 int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_dev, int n_layers, float* x, float* kc, float* vc, float* gc, int nA,
                            int a0, int T, int Tpos, int chunk, int conv_chunk, int dw_k, unsigned* bar_ctr, unsigned* bar_target_host,
-                           unsigned long long* ts_or_null, cudaStream_t st) {
+                           unsigned long long* ts_or_null, const float* const* pos_proj_host, cudaStream_t st) {
+  if (n_layers > 16) return -1;
   ++g_launches;
   const size_t smem = ((sizeof(ClSmem) + 127) & ~(size_t)127) + (size_t)NSLOT * SLOT_FLOATS * sizeof(float);
   if (first_time_on_device((const void*)encoder_layers_cluster_kernel)) {
@@ -576,9 +784,10 @@ int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_de
   P.layers = layers_dev; P.blobs = blobs_dev; P.n_layers = n_layers; P.x = x; P.kc = kc; P.vc = vc; P.gc = gc;
   P.nA = nA; P.a0 = a0; P.T = T; P.Tpos = Tpos; P.chunk = chunk; P.conv_chunk = conv_chunk; P.dw_k = dw_k;
   P.bar_ctr = bar_ctr; P.bar_target = *bar_target_host; P.ts = ts_or_null;
+  for (int i = 0; i < 16; ++i) P.pos_proj[i] = i < n_layers ? pos_proj_host[i] : nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(NCL * CS);
-  cfg.blockDim = dim3(CT);
+  cfg.blockDim = dim3(CT_ALL);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
