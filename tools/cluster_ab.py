@@ -44,7 +44,6 @@ def main():
         T, _ = e.encoder_stream_step(feats[:F].contiguous(), buf)
     torch.cuda.synchronize()
     st = e.persistent_phase_stamps(240)
-    out["w1_chunk_cycles_wait_fma_release_tree_epi"] = [[int(v) for v in st[200 + 8 * k:205 + 8 * k]] for k in range(4)]
     n = int(st[0])
     pairs = [(int(st[1 + 2 * i]), int(st[2 + 2 * i])) for i in range(min(n, 60))]
     out["stamps_ns"] = [[pairs[i][0], pairs[i][1] - pairs[0][1], pairs[i][1] - pairs[i - 1][1] if i else 0] if pairs[i][0] < 200 else list(pairs[i]) for i in range(len(pairs))]
