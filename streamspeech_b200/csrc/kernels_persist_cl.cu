@@ -84,6 +84,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// cluster barrier with release / acquire ordering of the distributed-shared-memory stores (all 288 threads of all 16 CTAs)
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // CTA barrier of the 8 compute warps (the producer warp never joins it)
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -145,7 +150,7 @@ struct ClSmem {
 };
 
 // As[r][:] = LN(xs[r][:]) * g + b (warp r; rows are complete in every CTA); ends with a CTA barrier
-__device__ __forceinline__ void stage_ln(ClSmem& sm, const float* g, const float* b) {
+__device__ __noinline__ void stage_ln(ClSmem& sm, const float* g, const float* b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp < CR) {
     float v[8];
@@ -387,35 +392,34 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
     if (lane == 0) {
       issue_par(0);
       issue_par(1);
-      for (; issued < NSLOT && issued < total_chunks; ++issued) issue(issued);
     }
-    issued = NSLOT;
     prefetch_attn(0);
-    cluster.sync();  // (start-up barrier)
+    cluster_sync();  // (start-up barrier)
 #pragma unroll 1
     for (int li = 0; li < P.n_layers; ++li) {
 #pragma unroll 1
       for (int x = 0; x < 9; ++x) {
-        const int n = (int)((0x082030008ull >> (4 * x)) & 15);  // releases to service before barrier x: 8 0 0 0 3 0 2 8 0
+        // releases to service before barrier x: 8 0 0 0 3 0 2 8 0 (+ the initial fill of the ring before the very first barrier)
+        const int n = (int)((0x082030008ull >> (4 * x)) & 15) + (li == 0 && x == 0 ? NSLOT : 0);
         if (lane == 0) {
 #pragma unroll 1
           for (int k = 0; k < n && issued < total_chunks; ++k, ++issued) {
-            mbar_wait(smem_u32(&sm.empty[issued % NSLOT]), (uint32_t)(((issued - NSLOT) / NSLOT) & 1));
+            if (issued >= NSLOT) mbar_wait(smem_u32(&sm.empty[issued % NSLOT]), (uint32_t)(((issued - NSLOT) / NSLOT) & 1));
             issue(issued);
           }
         }
         __syncwarp();
-        cluster.sync();
+        cluster_sync();
         // every compute thread of the CTA is past layer li - 1 (it has arrived at this layer's first barrier): its parameter buffer is free
         if (x == 0 && li >= 1 && lane == 0) issue_par(li + 1);
         if (x == 2) prefetch_attn(li + 1);  // (the attention segment: nothing to refill)
       }
     }
-    cluster.sync();
+    cluster_sync();
     return;
   }
 
-  cluster.sync();  // every CTA of the cluster runs and has initialised its shared memory before any DSMEM traffic
+  cluster_sync();  // every CTA of the cluster runs and has initialised its shared memory before any DSMEM traffic
   int q = 0;       // chunk counter
   auto acquire = [&]() -> const float* {
     mbar_wait(smem_u32(&sm.full[q % NSLOT]), (uint32_t)((q / NSLOT) & 1));
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
 #pragma unroll 1
       for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y);
     }
-    cluster.sync();
+    cluster_sync();
   };
   const int h = c >> 2, p = c & 3;  // attention: head and key part of this CTA
   // keys row r may attend: [0, lim_of(r)); rows past the cluster's last valid one attend nothing
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         // reduce-scatter: column n belongs to rank n / 16
 #pragma unroll
         for (int r = 0; r < CR; ++r) st_peer(&sm.u.f.red[c][r][tid & 15], tid >> 4, acc[r]);
-        cluster.sync();
+        cluster_sync();
         if (tid < CR * 16) {
           const int r = tid >> 4, j = tid & 15;
           float t = sm.u.f.red[0][r][j];
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
 #pragma unroll 1
           for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y);
         }
-        cluster.sync();
+        cluster_sync();
       }
       stamp(half ? 11 : 1);
       if (half == 1) {
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         for (int pp = 0; pp < 4; ++pp) st_peer(&sm.qs[r][p * 16 + j], (c & ~3) + pp, sm.outc[r][j]);
       }
       grid_arrive(P.bar_ctr, bar_target);  // K / V rows of this CTA are published; the wait comes after the work on older keys
-      cluster.sync();                      // q gathered
+      cluster_sync();                      // q gathered
       stamp(2);
       {
         const int r = tid >> 6, d = tid & 63;
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         }
       }
       stamp(5);
-      cluster.sync();
+      cluster_sync();
       {
         // combine: As[r][hh * 64 + d] = sum_p e^(m_p - M) acc_p[d] / sum_p e^(m_p - M) l_p over the 4 key parts of head hh
         const int r = tid >> 6, d = tid & 63;
@@ -745,29 +749,30 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
       grid_arrive(P.bar_ctr, bar_target);
       stamp(8);
       grid_wait(P.bar_ctr, bar_target);  // GLU rows of all clusters are in the conv cache
-      if (tid < CR * 16) {
-        const int r = tid >> 4, ch = tid & 15, oc = c * 16 + ch;
-        float y = 0.f;
-        if (r < nr) {
-          const int t = P.a0 + r_lo + r, half_k = (P.dw_k - 1) >> 1;
-          const int lim = P.conv_chunk > 0 ? min(P.T, (t / P.conv_chunk + 1) * P.conv_chunk) : P.T;
-          float gv[31];
+      {
+        // depthwise conv + BatchNorm + SiLU of (row r, channel ch): 4 lanes take 8 taps each (all loads in flight), summed by shuffle
+        const int r = tid >> 6, ch = (tid >> 2) & 15, tg = tid & 3, oc = c * 16 + ch;
+        const int t = P.a0 + r_lo + r, half_k = (P.dw_k - 1) >> 1;
+        const int lim = r < nr ? (P.conv_chunk > 0 ? min(P.T, (t / P.conv_chunk + 1) * P.conv_chunk) : P.T) : 0;
+        float gv[8];
 #pragma unroll
-          for (int j = 0; j < 31; ++j) {  // all taps in flight (rows outside the sequence / chunk and taps >= dw_k contribute 0)
-            const int pz = t - half_k + j;
-            gv[j] = (j < P.dw_k && pz >= 0 && pz < lim) ? gc[(int64_t)pz * CD + oc] : 0.f;
-          }
-          float a = 0.f;
-#pragma unroll
-          for (int j = 0; j < 31; ++j) a = fmaf(par[PO_DW + j * 16 + ch], gv[j], a);
-          const float v = a * par[PO_BN_S + ch] + par[PO_BN_H + ch];
-          y = v / (1.0f + expf(-v));
+        for (int j = 0; j < 8; ++j) {  // (rows outside the sequence / chunk and taps >= dw_k contribute 0)
+          const int tap = tg * 8 + j, pz = t - half_k + tap;
+          gv[j] = (tap < P.dw_k && pz >= 0 && pz < lim) ? gc[(int64_t)pz * CD + oc] : 0.f;
         }
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(tg * 8 + j < 31 ? par[PO_DW + (tg * 8 + j) * 16 + ch] : 0.f, gv[j], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        const float v = a * par[PO_BN_S + ch] + par[PO_BN_H + ch];
+        const float y = r < nr ? v / (1.0f + expf(-v)) : 0.f;
+        // all-gather of the depthwise rows: lane tg stores to ranks tg, tg + 4, ...
 #pragma unroll 1
-        for (int d = 0; d < CS; ++d) st_peer(&sm.As[r][oc], d, y);  // all-gather of the depthwise rows
+        for (int d = tg; d < CS; d += 4) st_peer(&sm.As[r][oc], d, y);
       }
       stamp(9);
-      cluster.sync();
+      cluster_sync();
       gemm_chunk(&sm, acquire(), 16, 0, par + PO_END);  // PW2 rows [16 c, 16 c + 16)
       release();
       residual_gather(par + PO_PW2B);
@@ -777,7 +782,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
   if (c == 0) {
     for (int i = tid; i < nr * CD; i += CT) P.x[(int64_t)r_lo * CD + i] = sm.xs[i / CD][i % CD];
   }
-  cluster.sync();  // no CTA exits while a peer may still address its shared memory
+  cluster_sync();  // no CTA exits while a peer may still address its shared memory
 }
 
 // weight row `row` of (layer li, rank c): see the chunk table above.  One thread per float4.

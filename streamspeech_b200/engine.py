@@ -198,8 +198,8 @@ class Engine:
         self.set_option("umma2_fused_reduce", int(os.environ.get("SS_UMMA2_FUSED_REDUCE", "0")))
         self.set_option("fbank_tma", int(os.environ.get("SS_FBANK_TMA", "1")))
         self.set_option("persistent_ffn_fused", int(os.environ.get("SS_PERSISTENT_FFN_FUSED", "1")))
-        if int(os.environ.get("SS_PERSISTENT_ENCODER_CLUSTER", "0")):
-            self.set_option("persistent_encoder_cluster", 1)
+        # cluster kernel for encoder steps with <= 16 active rows (larger steps and refused launches take the 148-CTA kernel)
+        self.set_option("persistent_encoder_cluster", int(os.environ.get("SS_PERSISTENT_ENCODER_CLUSTER", "1")))
         self.set_option("persistent_mt_v2", int(os.environ.get("SS_PERSISTENT_MT_V2", "1")))
         self.set_option("persistent_mt_prefix", int(os.environ.get("SS_PERSISTENT_MT_PREFIX", "1")))
         self.set_option("vocoder_streams", int(os.environ.get("SS_VOCODER_STREAMS", "1")))

@@ -651,7 +651,7 @@ def test_cluster_encoder_kernel_agrees(full, attn_chunk, conv_chunk, step_frames
         steps[v] = e.cluster_steps() - n0
         toks = [e.ctc_greedy(h, buf[:T].contiguous())["argmax"].tolist() for h in (0, 1)]
         outs[v] = (snaps, toks)
-    e.set_option("persistent_encoder_cluster", 0)
+    e.set_option("persistent_encoder_cluster", 1)
     e.check_async_error()
     assert steps[0] == 0
     assert steps[1] > 0 or attn_chunk > 16, steps
