@@ -687,9 +687,9 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
           for (int u = 0; u < 16; ++u) vv[u] = sb + 4 * u < ns_all ? vb[(int64_t)(4 * (sb + 4 * u) + p) * CD] : 0.f;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int sl = min(sb + 4 * u, 255);  // (vv is 0 past the last slot)
+            const bool ok = sb + 4 * u < ns_all;  // (S past the last slot was never written: select, do not multiply by 0)
 #pragma unroll
-            for (int r = 0; r < CR; ++r) acc[r] = fmaf(sm.att.S[r][sl], vv[u], acc[r]);
+            for (int r = 0; r < CR; ++r) acc[r] = fmaf(ok ? sm.att.S[r][min(sb + 4 * u, 255)] : 0.f, vv[u], acc[r]);
           }
         }
 #pragma unroll

@@ -627,7 +627,7 @@ def test_persistent_kernel_variants_agree(full, option):
     e.encoder_stream_reset()
 
 
-@pytest.mark.parametrize("attn_chunk,conv_chunk,step_frames", [(8, 8, 32), (16, 16, 64), (16, 8, 64), (8, 8, 17), (32, 16, 128)])
+@pytest.mark.parametrize("attn_chunk,conv_chunk,step_frames", [(8, 8, 32), (16, 16, 64), (16, 8, 64), (8, 8, 17), (32, 16, 128), (4, 8, 16), (2, 8, 8)])
 def test_cluster_encoder_kernel_agrees(full, attn_chunk, conv_chunk, step_frames):
     """A / B of the cluster encoder kernel (kernels_persist_cl.cu: 4 clusters x 16 CTAs, activations in distributed shared memory,
     weights streamed from repacked blobs) against the 148-CTA kernel on the same stream of calls, including ragged step sizes and a
