@@ -151,32 +151,44 @@ def run_reference(args):
 
 
 def encoder_roofline(engine, peaks, run_utterance):
-    """Dominant kernel of the step = encoder_layers_persistent_kernel (one launch per 320 ms chunk runs all 12 Conformer
-    layers over the <= 16 not-yet-final rows; 19 % of the step's GPU time in profiles/r1_launches_v4_bench_window.md).
+    """Dominant kernel of the step = the encoder-stack kernel (one launch per 320 ms chunk runs all 12 Conformer layers over the
+    <= 16 not-yet-final rows): encoder_layers_cluster_kernel (4 clusters x 16 CTAs, activations in distributed shared memory,
+    weights streamed by TMA from repacked blobs) when the step has <= 16 rows, else encoder_layers_persistent_kernel (148 CTAs).
     It streams every GEMM weight of the stack once per launch -> HBM roofline.  Measured live: the engine brackets each
     launch with CUDA events on the launching stream while one more resident utterance is streamed (32 launches).
     algorithmic bytes per launch = 12 x (4*D*FFN + 7*D*D) x 4 B of weights (122.7 MB) + the K / V cache and
     relative-position rows the attention reads (12 x (3T + nA) x D x 4 B)."""
     engine.set_option("persistent_time", 1)
     engine.persistent_time()  # drop stale records
+    c0 = engine.cluster_steps()
     run_utterance()
     ms, n, nbytes = engine.persistent_time()
+    cl = engine.cluster_steps() - c0
     engine.set_option("persistent_time", 0)
     peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")
+    cluster = n > 0 and cl * 2 > n  # which kernel took most of the timed launches
+    tp = os.path.join(ROOT, "profiles", "r2_cluster_kernel_traffic.json" if cluster else "r2_dominant_kernel_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     if n == 0:
         return {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
                 "kernel": "encoder_layers_persistent_kernel", "note": "no persistent launches were recorded"}
     ach = nbytes / (ms * 1e-3) / 1e9
+    if cluster:
+        kernel = ("encoder_layers_cluster_kernel (fp32, all 12 Conformer layers of one streaming step; 4 clusters x 16 CTAs, DSMEM "
+                  "activation exchange, TMA weight ring)")
+        note_ = ("batch-1 streaming: 16 rows per launch; 9 cluster barriers + 2 grid barriers per layer; bound by dependent-phase "
+                 "latency (barriers, instruction fetch, one L2 round trip per phase), not by bandwidth")
+    else:
+        kernel = "encoder_layers_persistent_kernel<2048> (fp32, all 12 Conformer layers of one streaming step, 148 CTAs cooperative)"
+        note_ = ("batch-1 streaming: 16 rows per launch, 108 grid barriers; the kernel is bound by dependent-phase latency "
+                 "(barrier + one L2/HBM round trip per phase), not by bandwidth")
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-            "kernel": "encoder_layers_persistent_kernel<2048> (fp32, all 12 Conformer layers of one streaming step, 148 CTAs cooperative)",
+            "kernel": kernel, "cluster_kernel_launches": cl,
             "algorithmic_bytes_per_launch": nbytes / n, "launches_timed": n, "us_per_launch": ms / n * 1e3,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-            "note": "batch-1 streaming: 16 rows per launch, 108 grid barriers; the kernel is bound by dependent-phase latency "
-                    "(barrier + one L2/HBM round trip per phase), not by bandwidth"}
+            "note": note_}
 
 
 def gemm_rooflines(engine, peaks):

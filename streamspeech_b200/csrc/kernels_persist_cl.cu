@@ -85,8 +85,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // cluster barrier with release / acquire ordering of the distributed-shared-memory stores (all 288 threads of all 16 CTAs)
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+__device__ __forceinline__ void cluster_sync(int relaxed = 0) {
+  if (relaxed) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");  // timing experiment
+  else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // CTA barrier of the 8 compute warps (the producer warp never joins it)
@@ -293,6 +294,7 @@ struct ClParams {
   unsigned* bar_ctr;
   unsigned bar_target;
   const float* pos_proj[16];   // per layer: projected relative-position table [2 * Tpos - 1][256]
+  int relaxed_sync;            // timing experiment only: cluster barriers without the release fence (results may be wrong)
   unsigned long long* ts;      // profiling (option persistent_profile): ts[0] = number of stamps, then (id, ns) pairs of CTA 0, layer 1
 };
 
@@ -305,9 +307,8 @@ __device__ __noinline__ void gemm_chunk(ClSmem* smp, const float* wchunk, int ro
   XRegs x;
   load_x(sm, x);
   float acc[16];
-  if (rows > 16) chunk_fma<32>(x, wchunk, acc);
-  else chunk_fma<16>(x, wchunk, acc);
-  const float v = chunk_tree<32>(acc);  // (the 32-row tree is also right for 16 rows: slots 2, 3 are zero)
+  chunk_fma<32>(x, wchunk, acc);  // (a 16-row chunk: slots 2, 3 read stale rows of the ring slot; their sums are dropped below)
+  const float v = chunk_tree<32>(acc);
   if ((lane & 1) == 0) {
     const int j = warp + (lane >> 3) * CWP;
     if (j < rows) sm.outc[(lane >> 1) & 3][off + j] = v + bias[off + j];
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
           }
         }
         __syncwarp();
-        cluster_sync();
+        cluster_sync(P.relaxed_sync);
         // every compute thread of the CTA is past layer li - 1 (it has arrived at this layer's first barrier): its parameter buffer is free
         if (x == 0 && li >= 1 && lane == 0) issue_par(li + 1);
         if (x == 2) prefetch_attn(li + 1);  // (the attention segment: nothing to refill)
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
 #pragma unroll 1
       for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y);
     }
-    cluster_sync();
+    cluster_sync(P.relaxed_sync);
   };
   const int h = c >> 2, p = c & 3;  // attention: head and key part of this CTA
   // keys row r may attend: [0, lim_of(r)); rows past the cluster's last valid one attend nothing
@@ -495,32 +496,50 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
           }
         }
         csync();  // hs complete
-        float acc[CR] = {0.f, 0.f, 0.f, 0.f};  // thread n = tid: output column n of the rank-128 update
+        // rank-128 update: thread = (column pair cp = tid % 128, half kh = tid / 128 of each chunk's 32 hidden units): one 8-byte weight
+        // load and four broadcast loads per 8 FMAs; the two halves are added through shared memory
+        float acc[CR][2] = {};
+        {
+          const int cp = tid & 127, kh = tid >> 7;
 #pragma unroll 1
-        for (int part = 0; part < 4; ++part) {
-          const float* w = acquire();
+          for (int part = 0; part < 4; ++part) {
+            const float* w = acquire() + (kh * 16) * CD + 2 * cp;
+            const float* hb = &sm.u.f.hs[0][part * 32 + kh * 16];
 #pragma unroll
-          for (int u = 0; u < 32; u += 4) {
-            float wv[4];
-            float4 hv[CR];
+            for (int u = 0; u < 16; u += 4) {
+              float2 wv[4];
+              float4 hv[CR];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) wv[x] = w[(u + x) * CD + tid];
+              for (int x = 0; x < 4; ++x) wv[x] = *reinterpret_cast<const float2*>(w + (u + x) * CD);
 #pragma unroll
-            for (int r = 0; r < CR; ++r) hv[r] = *reinterpret_cast<const float4*>(&sm.u.f.hs[r][part * 32 + u]);
+              for (int r = 0; r < CR; ++r) hv[r] = *reinterpret_cast<const float4*>(hb + r * 128 + u);
+#pragma unroll
+              for (int r = 0; r < CR; ++r) {
+                acc[r][0] = fmaf(hv[r].x, wv[0].x, acc[r][0]); acc[r][1] = fmaf(hv[r].x, wv[0].y, acc[r][1]);
+                acc[r][0] = fmaf(hv[r].y, wv[1].x, acc[r][0]); acc[r][1] = fmaf(hv[r].y, wv[1].y, acc[r][1]);
+                acc[r][0] = fmaf(hv[r].z, wv[2].x, acc[r][0]); acc[r][1] = fmaf(hv[r].z, wv[2].y, acc[r][1]);
+                acc[r][0] = fmaf(hv[r].w, wv[3].x, acc[r][0]); acc[r][1] = fmaf(hv[r].w, wv[3].y, acc[r][1]);
+              }
+            }
+            release();
+          }
+          // halves: kh = 1 hands its sums to kh = 0 through As (free until the next LayerNorm staging)
+          if (kh == 1) {
+#pragma unroll
+            for (int r = 0; r < CR; ++r) *reinterpret_cast<float2*>(&sm.As[r][2 * cp]) = make_float2(acc[r][0], acc[r][1]);
+          }
+          csync();
+          if (kh == 0) {
 #pragma unroll
             for (int r = 0; r < CR; ++r) {
-              acc[r] = fmaf(hv[r].x, wv[0], acc[r]);
-              acc[r] = fmaf(hv[r].y, wv[1], acc[r]);
-              acc[r] = fmaf(hv[r].z, wv[2], acc[r]);
-              acc[r] = fmaf(hv[r].w, wv[3], acc[r]);
+              const float2 o = *reinterpret_cast<const float2*>(&sm.As[r][2 * cp]);
+              // reduce-scatter: column n belongs to rank n / 16
+              st_peer(&sm.u.f.red[c][r][(2 * cp) & 15], (2 * cp) >> 4, acc[r][0] + o.x);
+              st_peer(&sm.u.f.red[c][r][(2 * cp + 1) & 15], (2 * cp + 1) >> 4, acc[r][1] + o.y);
             }
           }
-          release();
         }
-        // reduce-scatter: column n belongs to rank n / 16
-#pragma unroll
-        for (int r = 0; r < CR; ++r) st_peer(&sm.u.f.red[c][r][tid & 15], tid >> 4, acc[r]);
-        cluster_sync();
+        cluster_sync(P.relaxed_sync);
         if (tid < CR * 16) {
           const int r = tid >> 4, j = tid & 15;
           float t = sm.u.f.red[0][r][j];
@@ -530,7 +549,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
 #pragma unroll 1
           for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y);
         }
-        cluster_sync();
+        cluster_sync(P.relaxed_sync);
       }
       stamp(half ? 11 : 1);
       if (half == 1) {
@@ -582,7 +601,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         for (int pp = 0; pp < 4; ++pp) st_peer(&sm.qs[r][p * 16 + j], (c & ~3) + pp, sm.outc[r][j]);
       }
       grid_arrive(P.bar_ctr, bar_target);  // K / V rows of this CTA are published; the wait comes after the work on older keys
-      cluster_sync();                      // q gathered
+      cluster_sync(P.relaxed_sync);                      // q gathered
       stamp(2);
       {
         const int r = tid >> 6, d = tid & 63;
@@ -593,7 +612,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
       csync();
       {
         // scores: half a warp per key (lane l16 holds dims [4 l16, 4 l16 + 4) of q + u, q + v of the 4 rows and loads 16 B of the key row
-        // and of the 4 relative-position rows), 2 keys per half-warp in flight; first the keys of earlier steps, then -- after the
+        // and of the 4 relative-position rows), 2 keys per half-warp in flight (4 measured slower); first the keys of earlier steps, then -- after the
         // grid barrier -- the keys of this step
         const float* kb = kc + h * CHD;
         const float* pb = pos_proj + h * CHD;
@@ -705,7 +724,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         }
       }
       stamp(5);
-      cluster_sync();
+      cluster_sync(P.relaxed_sync);
       {
         // combine: As[r][hh * 64 + d] = sum_p e^(m_p - M) acc_p[d] / sum_p e^(m_p - M) l_p over the 4 key parts of head hh
         const int r = tid >> 6, d = tid & 63;
@@ -772,7 +791,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         for (int d = tg; d < CS; d += 4) st_peer(&sm.As[r][oc], d, y);
       }
       stamp(9);
-      cluster_sync();
+      cluster_sync(P.relaxed_sync);
       gemm_chunk(&sm, acquire(), 16, 0, par + PO_END);  // PW2 rows [16 c, 16 c + 16)
       release();
       residual_gather(par + PO_PW2B);
@@ -857,7 +876,7 @@ bool encoder_layers_cluster_supported(int nA, int D, int FFN, int H, int T, int 
 
 int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_dev, int n_layers, float* x, float* kc, float* vc, float* gc, int nA,
                            int a0, int T, int Tpos, int chunk, int conv_chunk, int dw_k, unsigned* bar_ctr, unsigned* bar_target_host,
-                           unsigned long long* ts_or_null, const float* const* pos_proj_host, cudaStream_t st) {
+                           unsigned long long* ts_or_null, const float* const* pos_proj_host, int relaxed_sync, cudaStream_t st) {
   if (n_layers > 16) return -1;
   ++g_launches;
   const size_t smem = ((sizeof(ClSmem) + 127) & ~(size_t)127) + (size_t)NSLOT * SLOT_FLOATS * sizeof(float);
@@ -868,7 +887,7 @@ int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_de
   ClParams P;
   P.layers = layers_dev; P.blobs = blobs_dev; P.n_layers = n_layers; P.x = x; P.kc = kc; P.vc = vc; P.gc = gc;
   P.nA = nA; P.a0 = a0; P.T = T; P.Tpos = Tpos; P.chunk = chunk; P.conv_chunk = conv_chunk; P.dw_k = dw_k;
-  P.bar_ctr = bar_ctr; P.bar_target = *bar_target_host; P.ts = ts_or_null;
+  P.bar_ctr = bar_ctr; P.bar_target = *bar_target_host; P.ts = ts_or_null; P.relaxed_sync = relaxed_sync;
   for (int i = 0; i < 16; ++i) P.pos_proj[i] = i < n_layers ? pos_proj_host[i] : nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(NCL * CS);
