@@ -61,11 +61,23 @@ constexpr size_t BLOB_STRIDE = (size_t)PAR_FLOATS + (size_t)BLOB_ROWS * CD;  // 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// store into the shared memory of CTA `rank` of the cluster (32-bit shared::cluster address: nothing for the compiler to hoist and spill)
-__device__ __forceinline__ void st_peer(const float* local, int rank, float v) {
+// Exchange channels: a receive buffer in every CTA's shared memory plus an mbarrier that counts the bytes landing in it.  Senders
+// store with st.async (remote write + complete_tx on the receiver's mbarrier); the receiver arms the expected byte count and waits
+// for the phase -- no cluster barrier and no cluster-scope release fence (which is a MEMBAR.ALL.GPU: ~0.5 us each, measured).
+// A buffer is reused only after an all-to-all exchange on another channel, which a sender cannot pass before every receiver has
+// finished reading (it needs the receiver's own contribution, sent after those reads), so no flow control is needed.
+enum { CH_RED = 0, CH_XS = 1, CH_QS = 2, CH_ATTP = 3, CH_AS = 4, N_CH = 5 };
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, int rank) {
   uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+  return remote;
+}
+// value -> `local`'s address in CTA `rank`, counted on that CTA's mbarrier `bar_local` (both given as this CTA's addresses)
+__device__ __forceinline__ void st_peer(const float* local, int rank, float v, const unsigned long long* bar_local) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(mapa_u32(smem_u32(local), rank)),
+               "r"(__float_as_uint(v)), "r"(mapa_u32(smem_u32(bar_local), rank))
+               : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -148,6 +160,8 @@ struct ClSmem {
   unsigned long long full[NSLOT];
   unsigned long long empty[NSLOT];  // one arrival per warp when it has finished reading the slot
   unsigned long long parfull[2];
+  unsigned long long parfree[2];    // the compute warps are done with the parameter buffer (one arrival per layer)
+  unsigned long long xbar[N_CH];    // exchange channels (bytes landed in the receive buffers)
 };
 
 // As[r][:] = LN(xs[r][:]) * g + b (warp r; rows are complete in every CTA); ends with a CTA barrier
@@ -332,6 +346,8 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
     for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.full[i])));
     for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sm.empty[i])), "r"(CWP));
     for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.parfull[i])));
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.parfree[i])));
+    for (int i = 0; i < N_CH; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.xbar[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // residual rows of the cluster (zero rows where the cluster has fewer than 4)
@@ -389,7 +405,6 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         }
       }
     };
-    int issued = 0;
     if (lane == 0) {
       issue_par(0);
       issue_par(1);
@@ -397,26 +412,24 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
     prefetch_attn(0);
     cluster_sync();  // (start-up barrier)
 #pragma unroll 1
-    for (int li = 0; li < P.n_layers; ++li) {
-#pragma unroll 1
-      for (int x = 0; x < 9; ++x) {
-        // releases to service before barrier x: 8 0 0 0 3 0 2 8 0 (+ the initial fill of the ring before the very first barrier)
-        const int n = (int)((0x082030008ull >> (4 * x)) & 15) + (li == 0 && x == 0 ? NSLOT : 0);
-        if (lane == 0) {
-#pragma unroll 1
-          for (int k = 0; k < n && issued < total_chunks; ++k, ++issued) {
-            if (issued >= NSLOT) mbar_wait(smem_u32(&sm.empty[issued % NSLOT]), (uint32_t)(((issued - NSLOT) / NSLOT) & 1));
-            issue(issued);
-          }
+    for (int issued = 0; issued < total_chunks; ++issued) {
+      const int li = issued / CHUNKS_PER_LAYER, j = issued - li * CHUNKS_PER_LAYER;
+      if (lane == 0) {
+        if (issued >= NSLOT) mbar_wait(smem_u32(&sm.empty[issued % NSLOT]), (uint32_t)(((issued - NSLOT) / NSLOT) & 1));
+        issue(issued);
+      }
+      __syncwarp();
+      if (j == 8) {
+        // the compute warps are past chunk 3 of layer li, so layer li - 1 is done: its parameter buffer takes layer li + 1
+        const int L = li + 1;
+        if (L >= 2 && L < P.n_layers && lane == 0) {
+          mbar_wait(smem_u32(&sm.parfree[L & 1]), (uint32_t)(((L - 2) >> 1) & 1));
+          issue_par(L);
         }
-        __syncwarp();
-        cluster_sync(P.relaxed_sync);
-        // every compute thread of the CTA is past layer li - 1 (it has arrived at this layer's first barrier): its parameter buffer is free
-        if (x == 0 && li >= 1 && lane == 0) issue_par(li + 1);
-        if (x == 2) prefetch_attn(li + 1);  // (the attention segment: nothing to refill)
+        prefetch_attn(L);
       }
     }
-    cluster_sync();
+    cluster_sync();  // (exit barrier)
     return;
   }
 
@@ -430,6 +443,13 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.empty[q % NSLOT])) : "memory");
     ++q;
+  };
+  unsigned xph = 0;  // phase parity per exchange channel
+  auto xwait = [&](int ch, uint32_t bytes) {
+    const uint32_t bar = smem_u32(&sm.xbar[ch]);
+    if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    mbar_wait(bar, (xph >> ch) & 1u);
+    xph ^= 1u << ch;
   };
   int nts = 0;
   bool stamping = false;
@@ -447,9 +467,9 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
       const int r = tid >> 4, j = tid & 15;
       const float y = sm.xs[r][c * 16 + j] + (sm.outc[r][j] + bias[j]);
 #pragma unroll 1
-      for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y);
+      for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y, &sm.xbar[CH_XS]);
     }
-    cluster_sync(P.relaxed_sync);
+    xwait(CH_XS, CS * CR * 16 * 4);
   };
   const int h = c >> 2, p = c & 3;  // attention: head and key part of this CTA
   // keys row r may attend: [0, lim_of(r)); rows past the cluster's last valid one attend nothing
@@ -534,12 +554,12 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
             for (int r = 0; r < CR; ++r) {
               const float2 o = *reinterpret_cast<const float2*>(&sm.As[r][2 * cp]);
               // reduce-scatter: column n belongs to rank n / 16
-              st_peer(&sm.u.f.red[c][r][(2 * cp) & 15], (2 * cp) >> 4, acc[r][0] + o.x);
-              st_peer(&sm.u.f.red[c][r][(2 * cp + 1) & 15], (2 * cp + 1) >> 4, acc[r][1] + o.y);
+              st_peer(&sm.u.f.red[c][r][(2 * cp) & 15], (2 * cp) >> 4, acc[r][0] + o.x, &sm.xbar[CH_RED]);
+              st_peer(&sm.u.f.red[c][r][(2 * cp + 1) & 15], (2 * cp + 1) >> 4, acc[r][1] + o.y, &sm.xbar[CH_RED]);
             }
           }
         }
-        cluster_sync(P.relaxed_sync);
+        xwait(CH_RED, CS * CR * 16 * 4);
         if (tid < CR * 16) {
           const int r = tid >> 4, j = tid & 15;
           float t = sm.u.f.red[0][r][j];
@@ -547,9 +567,9 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
           for (int s = 1; s < CS; ++s) t += sm.u.f.red[s][r][j];
           const float y = sm.xs[r][c * 16 + j] + 0.5f * (t + b2[j]);
 #pragma unroll 1
-          for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y);
+          for (int d = 0; d < CS; ++d) st_peer(&sm.xs[r][c * 16 + j], d, y, &sm.xbar[CH_XS]);
         }
-        cluster_sync(P.relaxed_sync);
+        xwait(CH_XS, CS * CR * 16 * 4);
       }
       stamp(half ? 11 : 1);
       if (half == 1) {
@@ -576,6 +596,7 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
           }
         }
         csync();
+        if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.parfree[li & 1])) : "memory");
         stamp(12);
         if (stamping && tid == 0) P.ts[0] = (unsigned long long)nts;
         break;
@@ -598,10 +619,10 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         }
         // q columns [16 c, 16 c + 16) = dims [16 p, 16 p + 16) of head h: to the 4 CTAs of the head
 #pragma unroll 1
-        for (int pp = 0; pp < 4; ++pp) st_peer(&sm.qs[r][p * 16 + j], (c & ~3) + pp, sm.outc[r][j]);
+        for (int pp = 0; pp < 4; ++pp) st_peer(&sm.qs[r][p * 16 + j], (c & ~3) + pp, sm.outc[r][j], &sm.xbar[CH_QS]);
       }
       grid_arrive(P.bar_ctr, bar_target);  // K / V rows of this CTA are published; the wait comes after the work on older keys
-      cluster_sync(P.relaxed_sync);                      // q gathered
+      xwait(CH_QS, 4 * CR * 16 * 4);       // q gathered
       stamp(2);
       {
         const int r = tid >> 6, d = tid & 63;
@@ -719,12 +740,12 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         const float mv = sm.att.ml[r][d & 1];
 #pragma unroll 1
         for (int dst = 0; dst < CS; ++dst) {
-          st_peer(&sm.u.attp[c][r][d], dst, tot);
-          if (d < 2) st_peer(&sm.u.attp[c][r][CHD + d], dst, mv);
+          st_peer(&sm.u.attp[c][r][d], dst, tot, &sm.xbar[CH_ATTP]);
+          if (d < 2) st_peer(&sm.u.attp[c][r][CHD + d], dst, mv, &sm.xbar[CH_ATTP]);
         }
       }
       stamp(5);
-      cluster_sync(P.relaxed_sync);
+      xwait(CH_ATTP, CS * CR * (CHD + 2) * 4);
       {
         // combine: As[r][hh * 64 + d] = sum_p e^(m_p - M) acc_p[d] / sum_p e^(m_p - M) l_p over the 4 key parts of head hh
         const int r = tid >> 6, d = tid & 63;
@@ -788,10 +809,10 @@ __global__ void __launch_bounds__(CT_ALL, 1) encoder_layers_cluster_kernel(ClPar
         const float y = r < nr ? v / (1.0f + expf(-v)) : 0.f;
         // all-gather of the depthwise rows: lane tg stores to ranks tg, tg + 4, ...
 #pragma unroll 1
-        for (int d = tg; d < CS; d += 4) st_peer(&sm.As[r][oc], d, y);
+        for (int d = tg; d < CS; d += 4) st_peer(&sm.As[r][oc], d, y, &sm.xbar[CH_AS]);
       }
       stamp(9);
-      cluster_sync(P.relaxed_sync);
+      xwait(CH_AS, CS * CR * 16 * 4);
       gemm_chunk(&sm, acquire(), 16, 0, par + PO_END);  // PW2 rows [16 c, 16 c + 16)
       release();
       residual_gather(par + PO_PW2B);

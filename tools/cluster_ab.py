@@ -36,16 +36,6 @@ def main():
             finals[v] = buf[:T].clone()
             out[f"rep{rep}_cluster{v}"] = {"us_per_launch": 1e3 * ms / max(n, 1), "launches": n, "cluster_steps": e.cluster_steps() - n0,
                                             "GBps": by / max(ms, 1e-9) / 1e6}
-    # timing experiment: cluster barriers without the release fence (what do the MEMBARs cost?)
-    e.set_option("persistent_encoder_cluster", 1)
-    e.set_option("cluster_relaxed_sync", 1)
-    e.encoder_stream_reset()
-    e.persistent_time()
-    for F in list(range(4 * chunk, feats.shape[0], 4 * chunk)) + [feats.shape[0]]:
-        T, _ = e.encoder_stream_step(feats[:F].contiguous(), buf)
-    ms, n, by = e.persistent_time()
-    out["relaxed_sync_experiment"] = {"us_per_launch": 1e3 * ms / max(n, 1), "maxdiff_vs_148cta": float((finals[0] - buf[:T]).abs().max())}
-    e.set_option("cluster_relaxed_sync", 0)
     # phase stamps of the cluster kernel (CTA 0, layer 1) on one more pass
     e.set_option("persistent_profile", 1)
     e.set_option("persistent_encoder_cluster", 1)
