@@ -105,7 +105,7 @@ struct ss_engine {
   std::map<std::tuple<int, uintptr_t, int, int, int>, std::pair<cudaGraphExec_t, int>> voc_graphs;
   float* persist_ffn_scratch = nullptr;  // [enc_ffn / 16][16][enc_dim] partial sums of the fused FFN phases
   float* cl_blobs = nullptr;             // [enc_layers][16][624][256] weight blobs of the cluster encoder kernel (allocated when the option is set)
-  int cluster_relaxed_sync = 0;          // experiment: cluster barriers without the release fence
+  int cluster_cooperative = 1;           // cooperative launch attribute of the cluster kernel (0 only under a serialising profiler)
   long long cl_steps = 0;                // steps the cluster kernel has taken (ss_debug_copy "cluster_steps")
   int persistent_encoder_cluster = 0;    // kernels_persist_cl.cu instead of kernels_persist.cu for steps with <= 16 active rows
   int persistent_ffn_fused = 1;          // fused FFN phases in the persistent encoder kernel (0: separate W1 / W2 phases)

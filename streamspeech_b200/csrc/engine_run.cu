@@ -465,7 +465,7 @@ int ss_encoder_stream_step(ss_engine* h, void* stream, const float* feats_dev, i
       const float* pos_tabs[16];
       for (int i = 0; i < 16; ++i) pos_tabs[i] = i < c.enc_layers ? h->enc[i].pos_proj : nullptr;
       cluster_done = c.enc_layers <= 16 && encoder_layers_cluster(h->persist_layers, h->cl_blobs, c.enc_layers, x, h->st_k, h->st_v, h->st_glu, nA, a0, T, h->Tpos, h->attn_chunk, cc,
-                                            c.dw_kernel, h->persist_bar, &h->persist_bar_target, h->persistent_profile ? h->persist_ts : nullptr, pos_tabs, h->cluster_relaxed_sync, st) == 0;
+                                            c.dw_kernel, h->persist_bar, &h->persist_bar_target, h->persistent_profile ? h->persist_ts : nullptr, pos_tabs, h->cluster_cooperative, st) == 0;
       if (cluster_done) ++h->cl_steps;
       if (!cluster_done) cudaGetLastError();  // refused launch: the 148-CTA kernel below takes the step
     }
@@ -1151,7 +1151,7 @@ int ss_set_option(ss_engine* h, const char* name, int value) {
   else if (n == "umma2_fused_reduce") g_umma2_fused_reduce = value;
   else if (n == "persistent_encoder") h->persistent_encoder = value;
   else if (n == "persistent_ffn_fused") h->persistent_ffn_fused = value;
-  else if (n == "cluster_relaxed_sync") h->cluster_relaxed_sync = value;  // timing experiment (tools/cluster_ab.py); results may be wrong
+  else if (n == "cluster_cooperative") h->cluster_cooperative = value;  // 0: plain cluster launch (ncu cannot replay cooperative cluster launches)
   else if (n == "persistent_encoder_cluster") {  // kernels_persist_cl.cu: weights repacked once into per-(layer, rank) blobs
     if (value && !h->cl_blobs) {
       if (!h->persist_layers || !h->persist_bar) return h->fail(SS_ERR_STATE, "persistent_encoder_cluster needs a finalized engine");

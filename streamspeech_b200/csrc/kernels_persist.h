@@ -32,7 +32,7 @@ void encoder_layers_cluster_pack(const PersistLayer* layers_dev, int n_layers, i
 bool encoder_layers_cluster_supported(int nA, int D, int FFN, int H, int T, int dw_k);
 int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_dev, int n_layers, float* x, float* kc, float* vc, float* gc, int nA,
                            int a0, int T, int Tpos, int chunk, int conv_chunk, int dw_k, unsigned* bar_ctr, unsigned* bar_target_host,
-                           unsigned long long* ts_or_null, const float* const* pos_proj_host /* n_layers (<= 16) device pointers */, int relaxed_sync /* experiment: 0 */,
+                           unsigned long long* ts_or_null, const float* const* pos_proj_host /* n_layers (<= 16) device pointers */, int cooperative /* 1; 0 only under a profiler that cannot replay cooperative cluster launches */,
                            cudaStream_t st);
 
 // ---- MT decoder, single-token greedy steps (kernels_persist_mt.cu)

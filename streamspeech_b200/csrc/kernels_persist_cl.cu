@@ -97,9 +97,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // cluster barrier with release / acquire ordering of the distributed-shared-memory stores (all 288 threads of all 16 CTAs)
-__device__ __forceinline__ void cluster_sync(int relaxed = 0) {
-  if (relaxed) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");  // timing experiment
-  else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // CTA barrier of the 8 compute warps (the producer warp never joins it)
@@ -308,7 +307,6 @@ struct ClParams {
   unsigned* bar_ctr;
   unsigned bar_target;
   const float* pos_proj[16];   // per layer: projected relative-position table [2 * Tpos - 1][256]
-  int relaxed_sync;            // timing experiment only: cluster barriers without the release fence (results may be wrong)
   unsigned long long* ts;      // profiling (option persistent_profile): ts[0] = number of stamps, then (id, ns) pairs of CTA 0, layer 1
 };
 
@@ -897,7 +895,7 @@ bool encoder_layers_cluster_supported(int nA, int D, int FFN, int H, int T, int 
 
 int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_dev, int n_layers, float* x, float* kc, float* vc, float* gc, int nA,
                            int a0, int T, int Tpos, int chunk, int conv_chunk, int dw_k, unsigned* bar_ctr, unsigned* bar_target_host,
-                           unsigned long long* ts_or_null, const float* const* pos_proj_host, int relaxed_sync, cudaStream_t st) {
+                           unsigned long long* ts_or_null, const float* const* pos_proj_host, int cooperative, cudaStream_t st) {
   if (n_layers > 16) return -1;
   ++g_launches;
   const size_t smem = ((sizeof(ClSmem) + 127) & ~(size_t)127) + (size_t)NSLOT * SLOT_FLOATS * sizeof(float);
@@ -908,7 +906,7 @@ int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_de
   ClParams P;
   P.layers = layers_dev; P.blobs = blobs_dev; P.n_layers = n_layers; P.x = x; P.kc = kc; P.vc = vc; P.gc = gc;
   P.nA = nA; P.a0 = a0; P.T = T; P.Tpos = Tpos; P.chunk = chunk; P.conv_chunk = conv_chunk; P.dw_k = dw_k;
-  P.bar_ctr = bar_ctr; P.bar_target = *bar_target_host; P.ts = ts_or_null; P.relaxed_sync = relaxed_sync;
+  P.bar_ctr = bar_ctr; P.bar_target = *bar_target_host; P.ts = ts_or_null;
   for (int i = 0; i < 16; ++i) P.pos_proj[i] = i < n_layers ? pos_proj_host[i] : nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(NCL * CS);
@@ -923,7 +921,7 @@ int encoder_layers_cluster(const PersistLayer* layers_dev, const float* blobs_de
   attr[1].id = cudaLaunchAttributeCooperative;  // all 4 clusters co-resident (they meet in a grid barrier)
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = cooperative ? 2 : 1;  // (without the attribute co-residency is not guaranteed: only under a profiler that serialises kernels)
   int max_clusters = 0;
   if (cudaOccupancyMaxActiveClusters(&max_clusters, encoder_layers_cluster_kernel, &cfg) != cudaSuccess || max_clusters < NCL) {
     cudaGetLastError();
