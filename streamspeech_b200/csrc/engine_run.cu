@@ -645,6 +645,7 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
     P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
     P.tok = h->mt_tok_dev; P.feats = feats_out_dev; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
         if (h->persistent_mt_v2 && h->mt_part) { P.part = h->mt_part; P.delta = h->mt_part + (size_t)8 * c.mt_dim; }
+        if (h->persistent_profile) P.ts = h->persist_ts;
     if (mt_prefix_persistent(P, h->mt_persist_layers, start, T, h->persist_bar, &h->persist_bar_target, st) == 0)
       fed = start;
     else
@@ -666,6 +667,7 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
         P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
         P.tok = h->mt_tok_dev; P.feats = feats_out_dev; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
         if (h->persistent_mt_v2 && h->mt_part) { P.part = h->mt_part; P.delta = h->mt_part + (size_t)8 * c.mt_dim; }
+        if (h->persistent_profile) P.ts = h->persist_ts;
         if (mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, T, h->persist_bar, &h->persist_bar_target, st) == 0) {
           fed = step + cnt;
           if (step + cnt - 1 >= max_len) done = true;
@@ -785,6 +787,7 @@ int ss_mt_greedy_incremental(ss_engine* h, void* stream, const float* enc_dev, i
     P.self_k = h->mt_self_k; P.self_v = h->mt_self_v; P.cross_kv = h->mt_cross_kv;
     P.tok = h->mt_tok_dev; P.feats = feats; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
         if (h->persistent_mt_v2 && h->mt_part) { P.part = h->mt_part; P.delta = h->mt_part + (size_t)8 * c.mt_dim; }
+        if (h->persistent_profile) P.ts = h->persist_ts;
     if (mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, Tk, h->persist_bar, &h->persist_bar_target, st) != 0) {
       cudaGetLastError();
       return h->fail(SS_ERR_CUDA, "cooperative launch of the persistent MT kernel was refused");

@@ -51,6 +51,7 @@ struct MtDecodeParams {
   int64_t* tok;                             // device token buffer: tok[s] is fed at step s, the arg-max goes to tok[s + 1]
   float* feats;                             // [.][dim] final-LN features, row s
   float *x, *q, *attn, *hid, *logits;       // scratch: dim, dim, dim, ffn, vocab floats
+  unsigned long long* ts = nullptr;         // profiling (option persistent_profile): ns stamps of CTA 0 for the 2nd step's layer 1
   float *part = nullptr, *delta = nullptr;  // version-2 step (6 barriers per layer): per-head out-projection partials [8][dim], FFN delta [dim];
                                             // nullptr selects the 8-barrier kernel
 };

@@ -94,6 +94,26 @@ __device__ __forceinline__ void ln_to_v(MtSmem& sm, const float* __restrict__ g,
   __syncthreads();
 }
 
+// LayerNorm parameters of this thread's two columns, loaded ahead of use (the loads fly while the phase's input arrives)
+struct LnP {
+  float g0, g1, b0, b1;
+};
+__device__ __forceinline__ LnP ln_load(const float* __restrict__ g, const float* __restrict__ b) {
+  const int t = threadIdx.x;
+  return LnP{__ldg(g + t), __ldg(g + t + MTT), __ldg(b + t), __ldg(b + t + MTT)};
+}
+__device__ __forceinline__ void ln_to_v(MtSmem& sm, const LnP& p, int dim) {
+  const int t = threadIdx.x;
+  float a0 = sm.x[t], a1 = sm.x[t + MTT];
+  float mean = block_reduce_sum(sm, a0 + a1) / (float)dim;
+  float d0 = a0 - mean, d1 = a1 - mean;
+  float var = block_reduce_sum(sm, fmaf(d0, d0, d1 * d1)) / (float)dim;
+  float rstd = 1.0f / sqrtf(var + 1e-5f);
+  sm.v[t] = d0 * rstd * p.g0 + p.b0;
+  sm.v[t + MTT] = d1 * rstd * p.g1 + p.b1;
+  __syncthreads();
+}
+
 // coherent copy global -> shared (activations written by other CTAs before the last barrier)
 __device__ __forceinline__ void load_vec(float* dst, const float* src, int n) {
   for (int i = threadIdx.x * 4; i < n; i += MTT * 4) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
@@ -106,6 +126,7 @@ __device__ __forceinline__ void load_vec(float* dst, const float* src, int n) {
 template <int K, int MAXC>
 struct GemvW {
   float4 w[MAXC][K / 128];
+  float bias[MAXC];  // (filled by gemv_issue_b: the epilogue of gemv_finish_b receives acc + bias)
 };
 template <int K, int MAXC>
 __device__ __forceinline__ void gemv_issue(GemvW<K, MAXC>& r, const float* __restrict__ W, int N) {
@@ -117,6 +138,40 @@ __device__ __forceinline__ void gemv_issue(GemvW<K, MAXC>& r, const float* __res
 #pragma unroll
     for (int it = 0; it < K / 128; ++it)
       r.w[c][it] = col < N ? ldw(W + (int64_t)col * K + it * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// variant with the bias of each column loaded together with its weights (no global load left in the epilogue)
+template <int K, int MAXC>
+__device__ __forceinline__ void gemv_issue_b(GemvW<K, MAXC>& r, const float* __restrict__ W, int N, const float* __restrict__ bias) {
+  gemv_issue(r, W, N);
+  const int gw = blockIdx.x * MW + (threadIdx.x >> 5), nw = gridDim.x * MW;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = gw + c * nw;
+    r.bias[c] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+  }
+}
+template <int K, int MAXC, typename F>
+__device__ __forceinline__ void gemv_finish_b(const GemvW<K, MAXC>& r, const float* xs, int N, F&& epi) {
+  constexpr int NIT = K / 128;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * MW + (threadIdx.x >> 5), nw = gridDim.x * MW;
+  float4 xv[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) xv[it] = *reinterpret_cast<const float4*>(xs + it * 128 + lane * 4);
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      acc = fmaf(xv[it].x, r.w[c][it].x, acc);
+      acc = fmaf(xv[it].y, r.w[c][it].y, acc);
+      acc = fmaf(xv[it].z, r.w[c][it].z, acc);
+      acc = fmaf(xv[it].w, r.w[c][it].w, acc);
+    }
+    acc = warp_sum(acc);
+    const int col = gw + c * nw;
+    if (lane == 0 && col < N) epi(col, acc + r.bias[c]);
   }
 }
 template <int K, int MAXC, typename F>
@@ -369,6 +424,89 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel(MtDecodePa
 //              [x += sum, LN + FC1 + ReLU] | [FC2 -> delta]          (next layer / final LN: x += delta)
 constexpr int GRP = 16;                 // CTAs per head group (8 heads x 16 = 128 CTAs)
 constexpr int PCOLS = 512 / GRP;        // out-projection columns per CTA of a group
+constexpr int PCOLS_PER_WARP = PCOLS / MW;
+
+// attend_head with every independent load issued up front: the key row of this thread, the first 8 value rows of its part and the
+// query are all in flight together (one L2 round trip instead of three dependent ones); n <= 256 keys take a single pass
+__device__ void attend_head_early(MtSmem& sm, const float* q, const float* kbase, const float* vbase, int ld, int n, float* out) {
+  const int tid = threadIdx.x;
+  const int q4 = (tid & 15) * 4, part = tid >> 4;
+  float4 kk[MHD / 4];
+  {
+    const bool ok = tid < n;
+    const float* kr = kbase + (int64_t)(ok ? tid : 0) * ld;
+#pragma unroll
+    for (int d = 0; d < MHD / 4; ++d) kk[d] = ok ? *reinterpret_cast<const float4*>(kr + 4 * d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 vv0[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = part + 16 * u;
+    vv0[u] = j < n ? *reinterpret_cast<const float4*>(vbase + (int64_t)j * ld + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  if (tid < MHD) sm.qh[tid] = q[tid] * 0.125f;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < n; j += MTT) {
+    if (j != tid) {
+      const float* kr = kbase + (int64_t)j * ld;
+#pragma unroll
+      for (int d = 0; d < MHD / 4; ++d) kk[d] = *reinterpret_cast<const float4*>(kr + 4 * d);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < MHD / 4; ++d) {
+      s = fmaf(sm.qh[4 * d], kk[d].x, s);
+      s = fmaf(sm.qh[4 * d + 1], kk[d].y, s);
+      s = fmaf(sm.qh[4 * d + 2], kk[d].z, s);
+      s = fmaf(sm.qh[4 * d + 3], kk[d].w, s);
+    }
+    sm.S[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce_max(sm, mx);
+  float sum = 0.f;
+  for (int j = tid; j < n; j += MTT) {
+    float e = expf(sm.S[j] - mx);
+    sm.S[j] = e;
+    sum += e;
+  }
+  sum = block_reduce_sum(sm, sum);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int j0 = part; j0 < n; j0 += 16 * 8) {
+    float4 vv[8];
+    float pp[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + 16 * u;
+      const bool ok = j < n;
+      vv[u] = j0 == part ? vv0[u] : (ok ? *reinterpret_cast<const float4*>(vbase + (int64_t)j * ld + q4) : make_float4(0.f, 0.f, 0.f, 0.f));
+      pp[u] = ok ? sm.S[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a.x = fmaf(pp[u], vv[u].x, a.x);
+      a.y = fmaf(pp[u], vv[u].y, a.y);
+      a.z = fmaf(pp[u], vv[u].z, a.z);
+      a.w = fmaf(pp[u], vv[u].w, a.w);
+    }
+  }
+  *reinterpret_cast<float4*>(&sm.pv[part][q4]) = a;
+  __syncthreads();
+  if (tid < MHD) {
+    float t = 0.f;
+#pragma unroll
+    for (int x = 0; x < 16; ++x) t += sm.pv[x][tid];
+    out[tid] = t / sum;
+  }
+}
+
+// the out-projection weights head_partial_proj multiplies with, loaded before the attention they follow
+struct HpW {
+  float w0[PCOLS_PER_WARP], w1[PCOLS_PER_WARP];
+};
 
 // partial[h][32 j + c] = sum_{i < 64} a[i] * W[(32 j + c)][64 h + i]   (W row-major [512][512]); a = this CTA's attention output
 __device__ __forceinline__ void head_partial_proj(const float* a, const float* __restrict__ W, int h, int j, float* part_h) {
@@ -381,6 +519,28 @@ __device__ __forceinline__ void head_partial_proj(const float* a, const float* _
     float acc = fmaf(a0, __ldg(w + lane), a1 * __ldg(w + lane + 32));
     acc = warp_sum(acc);
     if (lane == 0) part_h[col] = acc;
+  }
+}
+
+__device__ __forceinline__ HpW hp_load(const float* __restrict__ W, int h, int j) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  HpW r;
+#pragma unroll
+  for (int c = 0; c < PCOLS_PER_WARP; ++c) {
+    const float* w = W + (int64_t)(j * PCOLS + warp * PCOLS_PER_WARP + c) * 512 + h * MHD;
+    r.w0[c] = __ldg(w + lane);
+    r.w1[c] = __ldg(w + lane + 32);
+  }
+  return r;
+}
+__device__ __forceinline__ void head_partial_proj_w(const float* a, const HpW& hw, int j, float* part_h) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float a0 = a[lane], a1 = a[lane + 32];
+#pragma unroll
+  for (int c = 0; c < PCOLS_PER_WARP; ++c) {
+    float acc = fmaf(a0, hw.w0[c], a1 * hw.w1[c]);
+    acc = warp_sum(acc);
+    if (lane == 0) part_h[j * PCOLS + warp * PCOLS_PER_WARP + c] = acc;
   }
 }
 
@@ -412,6 +572,17 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecod
 #define BAR()                          \
   grid_barrier(bar_ctr, bar_target);   \
   ++done_barriers;
+  int nts = 0;
+  bool stamping = false;
+#define STAMP(id)                                          \
+  if (stamping && tid == 0) {                              \
+    unsigned long long t_;                                 \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    P.ts[1 + 2 * nts] = (id);                              \
+    P.ts[2 + 2 * nts] = t_;                                \
+    ++nts;                                                 \
+    P.ts[0] = nts;                                         \
+  }
   for (int si = 0; si < nsteps; ++si) {
     const int s = step0 + si;
     {
@@ -422,69 +593,85 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecod
     }
     for (int l = 0; l < P.n_layers; ++l) {
       const MtLayerP L = layers[l];
+      stamping = P.ts != nullptr && blockIdx.x == 0 && si == 1 && l == 1;
+      STAMP(0);
       float* kc = P.self_k + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
       float* vc = P.self_v + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
       // (1) x += FFN delta of the previous layer; q | k | v = LN(x) Wqkv^T
       GemvW<DIM, 2> w_qkv;
-      gemv_issue(w_qkv, L.wqkv, 3 * DIM);
+      gemv_issue_b(w_qkv, L.wqkv, 3 * DIM, L.bqkv);
+      const LnP ln_self = ln_load(L.self_g, L.self_b);
       if (l > 0) {
         for (int c = tid; c < DIM; c += MTT) sm.x[c] = sm.x[c] + delta[c];
         __syncthreads();
       }
-      ln_to_v(sm, L.self_g, L.self_b, DIM);
-      gemv_finish(w_qkv, sm.v, 3 * DIM, [&](int col, float acc) {
-        float y = acc + (L.bqkv ? L.bqkv[col] : 0.f);
+      ln_to_v(sm, ln_self, DIM);
+      gemv_finish_b(w_qkv, sm.v, 3 * DIM, [&](int col, float y) {
         if (col < DIM) P.q[col] = y;
         else if (col < 2 * DIM) kc[col - DIM] = y;
         else vc[col - 2 * DIM] = y;
       });
+      STAMP(1);
       BAR();
+      STAMP(2);
       // (2) self-attention of head grp_h (every CTA of the group) + partial out-projection of this CTA's 32 columns
       if (in_group) {
-        attend_head(sm, P.q + grp_h * MHD, P.self_k + (size_t)l * P.max_pos * DIM + grp_h * MHD, P.self_v + (size_t)l * P.max_pos * DIM + grp_h * MHD, DIM,
-                    s + P.kv_off + 1, att_h);
+        const HpW hw = hp_load(L.wo, grp_h, grp_j);
+        attend_head_early(sm, P.q + grp_h * MHD, P.self_k + (size_t)l * P.max_pos * DIM + grp_h * MHD, P.self_v + (size_t)l * P.max_pos * DIM + grp_h * MHD,
+                          DIM, s + P.kv_off + 1, att_h);
         __syncthreads();
-        head_partial_proj(att_h, L.wo, grp_h, grp_j, part + grp_h * DIM);
+        head_partial_proj_w(att_h, hw, grp_j, part + grp_h * DIM);
       }
+      STAMP(3);
       BAR();
+      STAMP(4);
       // (3) x += sum_h partials + bo; q = LN(x) Wcq^T
       GemvW<DIM, 1> w_cq;
-      gemv_issue(w_cq, L.wcq, DIM);
+      gemv_issue_b(w_cq, L.wcq, DIM, L.bcq);
+      const LnP ln_cross = ln_load(L.cross_g, L.cross_b);
       add_head_partials(sm, part, L.bo);
-      ln_to_v(sm, L.cross_g, L.cross_b, DIM);
-      gemv_finish(w_cq, sm.v, DIM, [&](int col, float acc) { P.q[col] = acc + (L.bcq ? L.bcq[col] : 0.f); });
+      ln_to_v(sm, ln_cross, DIM);
+      gemv_finish_b(w_cq, sm.v, DIM, [&](int col, float y) { P.q[col] = y; });
+      STAMP(5);
       BAR();
+      STAMP(6);
       // (4) cross-attention of head grp_h + partial out-projection
       if (in_group) {
         const float* cross = P.cross_kv + (size_t)l * P.cross_cap * 2 * DIM;
-        attend_head(sm, P.q + grp_h * MHD, cross + grp_h * MHD, cross + DIM + grp_h * MHD, 2 * DIM, T, att_h);
+        const HpW hw = hp_load(L.wco, grp_h, grp_j);
+        attend_head_early(sm, P.q + grp_h * MHD, cross + grp_h * MHD, cross + DIM + grp_h * MHD, 2 * DIM, T, att_h);
         __syncthreads();
-        head_partial_proj(att_h, L.wco, grp_h, grp_j, part + grp_h * DIM);
+        head_partial_proj_w(att_h, hw, grp_j, part + grp_h * DIM);
       }
+      STAMP(7);
       BAR();
+      STAMP(8);
       // (5) x += sum_h partials + bco; hid = relu(LN(x) W1^T)
       GemvW<DIM, 2> w_1;
-      gemv_issue(w_1, L.w1, FFN);
+      gemv_issue_b(w_1, L.w1, FFN, L.b1);
+      const LnP ln_fin = ln_load(L.fin_g, L.fin_b);
       add_head_partials(sm, part, L.bco);
-      ln_to_v(sm, L.fin_g, L.fin_b, DIM);
-      gemv_finish(w_1, sm.v, FFN, [&](int col, float acc) {
-        float y = acc + (L.b1 ? L.b1[col] : 0.f);
-        P.hid[col] = y > 0.f ? y : 0.f;
-      });
+      ln_to_v(sm, ln_fin, DIM);
+      gemv_finish_b(w_1, sm.v, FFN, [&](int col, float y) { P.hid[col] = y > 0.f ? y : 0.f; });
+      STAMP(9);
       BAR();
+      STAMP(10);
       // (6) delta = hid W2^T + b2
       GemvW<FFN, 1> w_2;
-      gemv_issue(w_2, L.w2, DIM);
+      gemv_issue_b(w_2, L.w2, DIM, L.b2);
       load_vec(sm.v, P.hid, FFN);
-      gemv_finish(w_2, sm.v, DIM, [&](int col, float acc) { delta[col] = acc + (L.b2 ? L.b2[col] : 0.f); });
+      gemv_finish_b(w_2, sm.v, DIM, [&](int col, float y) { delta[col] = y; });
+      STAMP(11);
       BAR();
+      STAMP(12);
     }
     const bool forced_eos = s >= max_len;
     GemvW<DIM, 6> w_out;
     if (!forced_eos) gemv_issue(w_out, P.emb, P.vocab);
+    const LnP ln_out = ln_load(P.out_g, P.out_b);
     for (int c = tid; c < DIM; c += MTT) sm.x[c] = sm.x[c] + delta[c];
     __syncthreads();
-    ln_to_v(sm, P.out_g, P.out_b, DIM);
+    ln_to_v(sm, ln_out, DIM);
     if (blockIdx.x == 0)
       for (int c = tid; c < DIM; c += MTT) P.feats[(size_t)s * DIM + c] = sm.v[c];
     if (!forced_eos) gemv_finish(w_out, sm.v, P.vocab, [&](int col, float acc) { P.logits[col] = acc; });
@@ -538,6 +725,7 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecod
     }
   }
 #undef BAR
+#undef STAMP
   const int planned = nsteps * barriers_per_step;
   if (threadIdx.x == 0 && done_barriers < planned) atomicAdd(bar_ctr, (unsigned)(planned - done_barriers));
 }
