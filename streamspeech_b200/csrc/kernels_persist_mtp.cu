@@ -57,44 +57,63 @@ __device__ __forceinline__ void stage_ln512(float* As, const float* x, int M, in
                                             const int64_t* src_tok, const float* __restrict__ emb, const float* __restrict__ pos, int pad,
                                             float emb_scale, float* xg) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int m = warp; m < Mpad; m += QW) {
-    float v[16];
-    if (m < M) {
-      if (src_tok != nullptr) {
-        const int64_t tok = src_tok[m];
-        const int p = (tok == pad) ? pad : pad + 1 + m;
+  // the LayerNorm parameters of this lane's 16 columns and the rows of 2 row slots are all in flight before the first reduction
+  // (one row at a time meant two dependent L2 round trips per row: ~6 us per phase at 30 rows)
+  float gv[16], bv[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = lane + (i << 5);
-          v[i] = emb_scale * emb[tok * QD + c] + pos[(int64_t)p * QD + c];
-        }
-        if (blockIdx.x == 0) {
+  for (int i = 0; i < 16; ++i) {
+    gv[i] = __ldg(g + lane + (i << 5));
+    bv[i] = __ldg(b + lane + (i << 5));
+  }
+  for (int m0 = warp; m0 < Mpad; m0 += 2 * QW) {
+    float v[2][16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) xg[(int64_t)m * QD + lane + (i << 5)] = v[i];
+    for (int u = 0; u < 2; ++u) {
+      const int m = m0 + u * QW;
+      if (m < M) {
+        if (src_tok != nullptr) {
+          const int64_t tok = src_tok[m];
+          const int p = (tok == pad) ? pad : pad + 1 + m;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = lane + (i << 5);
+            v[u][i] = emb_scale * emb[tok * QD + c] + pos[(int64_t)p * QD + c];
+          }
+          if (blockIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xg[(int64_t)m * QD + lane + (i << 5)] = v[u][i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[u][i] = x[(int64_t)m * QD + lane + (i << 5)];
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = x[(int64_t)m * QD + lane + (i << 5)];
+        for (int i = 0; i < 16; ++i) v[u][i] = 0.f;
       }
-      float s = 0.f;
+    }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) s += v[i];
-      const float mean = warp_sum(s) / (float)QD;
-      float q = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      const int m = m0 + u * QW;
+      if (m >= Mpad) continue;
+      if (m < M) {
+        float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float d = v[i] - mean;
-        q = fmaf(d, d, q);
+        for (int i = 0; i < 16; ++i) s += v[u][i];
+        const float mean = warp_sum(s) / (float)QD;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float d = v[u][i] - mean;
+          q = fmaf(d, d, q);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)QD + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) As[m * QD + lane + (i << 5)] = (v[u][i] - mean) * rstd * gv[i] + bv[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) As[m * QD + lane + (i << 5)] = 0.f;
       }
-      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)QD + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = lane + (i << 5);
-        As[m * QD + c] = (v[i] - mean) * rstd * g[c] + b[c];
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) As[m * QD + lane + (i << 5)] = 0.f;
     }
   }
 }
@@ -111,8 +130,10 @@ __device__ __forceinline__ void stage_copy512(float* As, const float* a, int M, 
 
 // epi(m, col, value) for every m < M, col < N of  A[M][K] @ W[N][K]^T.  STAGED: A = As in shared memory (K == QD);
 // otherwise every warp reads its K-slice of A from global memory (coherent loads: written by other CTAs before the barrier).
-template <int CPT, int KS, int K, bool STAGED, typename Epi>
-__device__ __forceinline__ void pgemm(QSmem& sm, const float* As, const float* A, const float* __restrict__ W, int M, int N, Epi&& epi) {
+// `stage` (staging of As + CTA barrier, or nothing) runs after the weight loads of the CTA's first task have been issued, so the
+// weights fly while the activations are staged; CTAs without a task skip it.
+template <int CPT, int KS, int K, bool STAGED, typename Stage, typename Epi>
+__device__ __forceinline__ void pgemm(QSmem& sm, const float* As, const float* A, const float* __restrict__ W, int M, int N, Stage&& stage, Epi&& epi) {
   constexpr int KSLICE = K / KS;
   constexpr int NIT = KSLICE / 128;
   static_assert(KSLICE % 128 == 0, "K slice must be a multiple of 128");
@@ -134,6 +155,7 @@ __device__ __forceinline__ void pgemm(QSmem& sm, const float* As, const float* A
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
         wv[it][c] = active ? ldw(W + (int64_t)(n0 + c) * K + k_lo + it * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tbase == (int)blockIdx.x * TPC) stage();
     for (int mb = 0; mb < M; mb += QRB) {
       float acc[CPT][QRB];
 #pragma unroll
@@ -292,9 +314,10 @@ __global__ void __launch_bounds__(QT, 1) mt_prefix_persistent_kernel(MtDecodePar
     float* kc = P.self_k + (size_t)l * P.max_pos * QD;
     float* vc = P.self_v + (size_t)l * P.max_pos * QD;
     // (1) q | k | v = LN(x) Wqkv^T  (layer 0 builds x from the embeddings while staging)
-    stage_ln512(As, x, M, Mpad, L.self_g, L.self_b, l == 0 ? P.tok : nullptr, P.emb, P.pos, P.pad, emb_scale, x);
-    __syncthreads();
-    pgemm<4, 2, QD, true>(sm, As, nullptr, L.wqkv, M, 3 * QD, [&](int m, int col, float acc) {
+    pgemm<4, 2, QD, true>(sm, As, nullptr, L.wqkv, M, 3 * QD, [&]() {
+      stage_ln512(As, x, M, Mpad, L.self_g, L.self_b, l == 0 ? P.tok : nullptr, P.emb, P.pos, P.pad, emb_scale, x);
+      __syncthreads();
+    }, [&](int m, int col, float acc) {
       const float y = acc + (L.bqkv ? L.bqkv[col] : 0.f);
       if (col < QD) qb[(int64_t)m * QD + col] = y;
       else if (col < 2 * QD) kc[(int64_t)m * QD + col - QD] = y;
@@ -309,16 +332,18 @@ __global__ void __launch_bounds__(QT, 1) mt_prefix_persistent_kernel(MtDecodePar
     }
     BAR();
     // (3) x += attn Wo^T
-    stage_copy512(As, att, M, Mpad);
-    __syncthreads();
-    pgemm<2, 2, QD, true>(sm, As, nullptr, L.wo, M, QD, [&](int m, int col, float acc) {
+    pgemm<2, 2, QD, true>(sm, As, nullptr, L.wo, M, QD, [&]() {
+      stage_copy512(As, att, M, Mpad);
+      __syncthreads();
+    }, [&](int m, int col, float acc) {
       x[(int64_t)m * QD + col] = (acc + (L.bo ? L.bo[col] : 0.f)) + x[(int64_t)m * QD + col];
     });
     BAR();
     // (4) q = LN(x) Wcq^T
-    stage_ln512(As, x, M, Mpad, L.cross_g, L.cross_b, nullptr, nullptr, nullptr, 0, 0.f, nullptr);
-    __syncthreads();
-    pgemm<2, 2, QD, true>(sm, As, nullptr, L.wcq, M, QD, [&](int m, int col, float acc) { qb[(int64_t)m * QD + col] = acc + (L.bcq ? L.bcq[col] : 0.f); });
+    pgemm<2, 2, QD, true>(sm, As, nullptr, L.wcq, M, QD, [&]() {
+      stage_ln512(As, x, M, Mpad, L.cross_g, L.cross_b, nullptr, nullptr, nullptr, 0, 0.f, nullptr);
+      __syncthreads();
+    }, [&](int m, int col, float acc) { qb[(int64_t)m * QD + col] = acc + (L.bcq ? L.bcq[col] : 0.f); });
     BAR();
     // (5) cross-attention over the T encoder rows (K | V rows projected before the launch)
     {
@@ -331,22 +356,24 @@ __global__ void __launch_bounds__(QT, 1) mt_prefix_persistent_kernel(MtDecodePar
     }
     BAR();
     // (6) x += attn Wco^T
-    stage_copy512(As, att, M, Mpad);
-    __syncthreads();
-    pgemm<2, 2, QD, true>(sm, As, nullptr, L.wco, M, QD, [&](int m, int col, float acc) {
+    pgemm<2, 2, QD, true>(sm, As, nullptr, L.wco, M, QD, [&]() {
+      stage_copy512(As, att, M, Mpad);
+      __syncthreads();
+    }, [&](int m, int col, float acc) {
       x[(int64_t)m * QD + col] = (acc + (L.bco ? L.bco[col] : 0.f)) + x[(int64_t)m * QD + col];
     });
     BAR();
     // (7) hid = relu(LN(x) W1^T)
-    stage_ln512(As, x, M, Mpad, L.fin_g, L.fin_b, nullptr, nullptr, nullptr, 0, 0.f, nullptr);
-    __syncthreads();
-    pgemm<4, 2, QD, true>(sm, As, nullptr, L.w1, M, QFFN, [&](int m, int col, float acc) {
+    pgemm<4, 2, QD, true>(sm, As, nullptr, L.w1, M, QFFN, [&]() {
+      stage_ln512(As, x, M, Mpad, L.fin_g, L.fin_b, nullptr, nullptr, nullptr, 0, 0.f, nullptr);
+      __syncthreads();
+    }, [&](int m, int col, float acc) {
       const float y = acc + (L.b1 ? L.b1[col] : 0.f);
       hid[(int64_t)m * QFFN + col] = y > 0.f ? y : 0.f;
     });
     BAR();
     // (8) x += hid W2^T
-    pgemm<4, 8, QFFN, false>(sm, nullptr, hid, L.w2, M, QD, [&](int m, int col, float acc) {
+    pgemm<4, 8, QFFN, false>(sm, nullptr, hid, L.w2, M, QD, [&]() {}, [&](int m, int col, float acc) {
       x[(int64_t)m * QD + col] = (acc + (L.b2 ? L.b2[col] : 0.f)) + x[(int64_t)m * QD + col];
     });
     BAR();
