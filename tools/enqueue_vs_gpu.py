@@ -46,3 +46,25 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(2000): eng.op_layer_norm(x, g, b)
 t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
 print("2000 LN launches via ctypes: enqueue us/launch", (t1 - t0) / 2000 * 1e6, "total us/launch", (t2 - t0) / 2000 * 1e6)
+# T2U + unit decoder and vocoder: host enqueue time vs GPU time of one call
+toks, f = eng.mt_greedy(enc[:160].contiguous(), None, 30)
+f = f.contiguous()
+codes = torch.randint(0, 1000, (40,), device="cuda")
+for name, fn in (("t2u_unit_decode S=%d" % f.shape[0], lambda: eng.t2u_unit_decode(f)),
+                 ("vocoder 30 new frames", None)):
+    if fn is None:
+        dur, cum = eng.vocoder_durations(codes)
+        total = int(cum[-1].item())
+        fn = lambda: eng.vocoder_generate(total, total - 30, 30, -1)
+    for _ in range(3):
+        fn()
+    hs, gs, ls = [], [], []
+    for _ in range(10):
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count(); t0 = time.perf_counter(); s.record()
+        fn()
+        e.record(); t1 = time.perf_counter(); torch.cuda.synchronize()
+        hs.append((t1 - t0) * 1e3); gs.append(s.elapsed_time(e)); ls.append(eng.launch_count() - l0)
+    hs.sort(); gs.sort()
+    print(name, ": host enqueue ms", round(hs[5], 3), "gpu ms", round(gs[5], 3), "launches", ls[0])
