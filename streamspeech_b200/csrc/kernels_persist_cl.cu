@@ -1,23 +1,27 @@
 // Cluster version of the streaming encoder step (option persistent_encoder_cluster): the <= 16 active rows are split over 4
 // thread-block clusters of 16 CTAs (4 rows per cluster), and inside a cluster the activations NEVER leave the chip: every CTA keeps
-// the cluster's residual rows in shared memory, GEMM outputs are exchanged through distributed shared memory (stores into the peers'
-// shared memory + barrier.cluster, ~0.3 us) instead of global memory + a 148-CTA grid barrier (~3 us per phase in
-// kernels_persist.cu, profiles/r2_persist_phases_*).  Only two steps per layer involve the other clusters -- the K / V rows and the
-// conv-module GLU rows of the step are published to the per-layer caches in global memory -- and keep a grid barrier (64 CTAs).
+// the cluster's residual rows in shared memory and GEMM outputs are exchanged through distributed shared memory instead of global
+// memory + a 148-CTA grid barrier (~3 us per phase in kernels_persist.cu, profiles/r2_persist_phases_*).  Only two steps per layer
+// involve the other clusters -- the K / V rows and the conv-module GLU rows of the step are published to the per-layer caches in
+// global memory -- and keep a (split) grid barrier over the 64 CTAs.
 //
 //   per layer and cluster (CTA rank c of 16):
 //     FFN  : LN (local) -> W1 rows [128c, 128c+128) -> SiLU -> rank-128 update with W2^T rows [128c, ..) -> partial [4][256]
-//            -> reduce-scatter over DSMEM (rank d sums the 16 partials of columns [16d, 16d+16) in rank order) -> bias, 0.5, residual
+//            -> reduce-scatter (rank d sums the 16 partials of columns [16d, 16d+16) in rank order) -> bias, 0.5, residual
 //            -> all-gather of the new residual columns
-//     MHA  : LN -> q | k | v columns [16c, 16c+16) -> k, v to the global cache, q to the CTA of its (row, head) -> GRID BARRIER ->
-//            rel-pos attention of (row c % 4, head c / 4) -> all-gather -> Wo columns [16c, ..) + residual -> all-gather
-//     conv : LN -> PW1 GLU channels [16c, ..) -> GLU rows to the global conv cache -> GRID BARRIER -> depthwise k31 + BN + SiLU on those
+//     MHA  : LN -> q | k | v columns [16c, 16c+16) -> k, v to the global cache, q to the 4 CTAs of its head -> grid arrive ->
+//            CTA (head c / 4, key part c % 4): scores of all 4 rows against its keys of earlier steps -> grid wait -> keys of this step ->
+//            partial softmax / PV -> all-gather of (acc[64], max, sum) -> every CTA combines -> Wo columns [16c, ..) + residual -> all-gather
+//     conv : LN -> PW1 GLU channels [16c, ..) -> GLU rows to the global conv cache -> grid barrier -> depthwise k31 + BN + SiLU on those
 //            channels -> all-gather -> PW2 columns + residual -> all-gather
 //     FFN, final LayerNorm (local: every CTA holds complete rows)
-//   weights: each (layer, rank) owns one contiguous blob in consumption order (21 chunks of <= 32 KB, packed once); thread 0 streams
-//   it with cp.async.bulk (TMA) into a 6-slot ring of shared memory, 5 chunks ahead of the compute and independent of every barrier.
-//   Each cluster reads all weights (4 x 123 MB through L2, 1 x from HBM).
-// fp32 CUDA-core arithmetic as in kernels_persist.cu (different summation order: ~1e-6).
+//   exchanges: st.async into the receiver's buffer, counted in bytes on the receiver's mbarrier (no cluster barriers: their release
+//   fence is a MEMBAR.ALL.GPU).
+//   weights: each (layer, rank) owns one contiguous blob in consumption order (a 15 KB parameter block + 21 chunks of <= 32 KB, packed
+//   once); a producer warp streams it with cp.async.bulk (TMA) into a 5-slot ring of shared memory, ahead of the 8 compute warps and
+//   independent of every exchange.  Each cluster reads all weights (4 x 123 MB through L2, 1 x from HBM: ncu 136 MB per launch).
+// fp32 CUDA-core arithmetic as in kernels_persist.cu (different summation order: ~2e-6 on the encoder output).
+// Design notes and measurements: DESIGN.md 5a.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -112,21 +116,6 @@ __device__ __forceinline__ void grid_arrive(unsigned* ctr, unsigned& target) {
 }
 __device__ __forceinline__ void grid_wait(unsigned* ctr, unsigned target) {
   if (threadIdx.x == 0) {
-    unsigned v, spins = 0;
-    do {
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while ((int)(v - target) < 0 && ++spins < (1u << 20));
-    if ((int)(v - target) < 0) atomicExch(ctr + SS_BAR_ERR_WORD, 1u);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  }
-  csync();
-}
-
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
-  csync();
-  target += gridDim.x;
-  if (threadIdx.x == 0) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned v, spins = 0;
     do {
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");

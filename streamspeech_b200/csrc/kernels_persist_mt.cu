@@ -508,20 +508,8 @@ struct HpW {
   float w0[PCOLS_PER_WARP], w1[PCOLS_PER_WARP];
 };
 
-// partial[h][32 j + c] = sum_{i < 64} a[i] * W[(32 j + c)][64 h + i]   (W row-major [512][512]); a = this CTA's attention output
-__device__ __forceinline__ void head_partial_proj(const float* a, const float* __restrict__ W, int h, int j, float* part_h) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float a0 = a[lane], a1 = a[lane + 32];
-#pragma unroll
-  for (int c = 0; c < PCOLS / MW; ++c) {  // 4 columns per warp
-    const int col = j * PCOLS + warp * (PCOLS / MW) + c;
-    const float* w = W + (int64_t)col * 512 + h * MHD;
-    float acc = fmaf(a0, __ldg(w + lane), a1 * __ldg(w + lane + 32));
-    acc = warp_sum(acc);
-    if (lane == 0) part_h[col] = acc;
-  }
-}
-
+// partial[h][32 j + c] = sum_{i < 64} a[i] * W[(32 j + c)][64 h + i]   (W row-major [512][512]); a = this CTA's attention output;
+// the weights are loaded (hp_load) before the attention they follow
 __device__ __forceinline__ HpW hp_load(const float* __restrict__ W, int h, int j) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   HpW r;
