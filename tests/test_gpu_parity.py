@@ -661,6 +661,35 @@ def test_cluster_encoder_kernel_agrees(full, attn_chunk, conv_chunk, step_frames
     e.encoder_stream_reset()
 
 
+def test_cluster_encoder_kernel_long_utterance(full):
+    """The cluster kernel on a 38 s stream (T up to ~950 rows: several batches of key slots per CTA in the attention, long L2 prefetch
+    lists) against the 148-CTA kernel; only every 8th call is compared in full."""
+    cfg, e, o = full
+    e.set_chunk(8, 8)
+    feats = e.fbank(cuda(synth.make_audio(38.0, seed=11)))
+    outs = {}
+    for v in (0, 1):
+        e.set_option("persistent_encoder_cluster", v)
+        buf = torch.zeros(1024, cfg.enc_dim, device="cuda")
+        e.encoder_stream_reset()
+        n0 = e.cluster_steps()
+        snaps = []
+        T = 0
+        for k, F in enumerate(list(range(30, feats.shape[0], 32)) + [feats.shape[0]]):
+            T, _ = e.encoder_stream_step(feats[:F].contiguous(), buf)
+            if k % 8 == 7:
+                snaps.append(buf[:T].clone())
+        snaps.append(buf[:T].clone())
+        outs[v] = (snaps, e.cluster_steps() - n0, T)
+    e.set_option("persistent_encoder_cluster", 1)
+    e.check_async_error()
+    assert outs[1][1] > 100 and outs[0][1] == 0 and outs[1][2] > 900, (outs[0][1:], outs[1][1:])
+    d = max(maxdiff(a, b) for a, b in zip(outs[0][0], outs[1][0]))
+    report("cluster_encoder_38s", enc=d, cluster_steps=outs[1][1], T=outs[1][2])
+    assert d < 5e-5, d
+    e.encoder_stream_reset()
+
+
 def test_resample_48k_to_16k_vs_torchaudio(eng3):
     """f3 wire format: ss_resample_48k_to_16k against torchaudio.functional.resample (the CPU oracle of this front end; the
     reference's sox `rate` is not available in this image) on whole signals of awkward lengths, and the streaming rule
