@@ -158,11 +158,21 @@ def encoder_roofline(engine, peaks, run_utterance):
     launch with CUDA events on the launching stream while one more resident utterance is streamed (32 launches).
     algorithmic bytes per launch = 12 x (4*D*FFN + 7*D*D) x 4 B of weights (122.7 MB) + the K / V cache and
     relative-position rows the attention reads (12 x (3T + nA) x D x 4 B)."""
+    import torch
+
     engine.set_option("persistent_time", 1)
     engine.persistent_time()  # drop stale records
+    engine.mt_time()
     c0 = engine.cluster_steps()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
     run_utterance()
+    t1.record()
+    torch.cuda.synchronize()
+    utt_ms = t0.elapsed_time(t1)
     ms, n, nbytes = engine.persistent_time()
+    mt_ms, mt_n, mt_steps = engine.mt_time()
     cl = engine.cluster_steps() - c0
     engine.set_option("persistent_time", 0)
     peak = peaks.get("hbm_gbs", 6650.0)
@@ -184,8 +194,18 @@ def encoder_roofline(engine, peaks, run_utterance):
         kernel = "encoder_layers_persistent_kernel<2048> (fp32, all 12 Conformer layers of one streaming step, 148 CTAs cooperative)"
         note_ = ("batch-1 streaming: 16 rows per launch, 108 grid barriers; the kernel is bound by dependent-phase latency "
                  "(barrier + one L2/HBM round trip per phase), not by bandwidth")
+    # second-largest kernel, measured the same way: the single-token MT kernel (one greedy step streams every decoder weight and the
+    # tied output projection once)
+    cfg = engine.cfg
+    mt_bytes_step = (cfg.mt_layers * (6 * cfg.mt_dim * cfg.mt_dim + 2 * cfg.mt_dim * cfg.mt_ffn) + cfg.tgt_vocab * cfg.mt_dim) * 4.0
+    mt = None
+    if mt_n > 0 and mt_ms > 0:
+        mt_ach = mt_bytes_step * mt_steps / (mt_ms * 1e-3) / 1e9
+        mt = {"kernel": "mt_decode_persistent_kernel_v2 (fp32, one launch per burst of greedy steps)", "bound": "hbm", "achieved": mt_ach,
+              "peak": peak, "unit": "GB/s", "frac": mt_ach / peak, "algorithmic_bytes_per_step": mt_bytes_step, "steps_timed": mt_steps,
+              "launches_timed": mt_n, "us_per_step": mt_ms / max(mt_steps, 1.0) * 1e3, "share_of_utterance_time": mt_ms / utt_ms}
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-            "kernel": kernel, "cluster_kernel_launches": cl,
+            "kernel": kernel, "cluster_kernel_launches": cl, "share_of_utterance_time": ms / utt_ms, "second_kernel": mt,
             "algorithmic_bytes_per_launch": nbytes / n, "launches_timed": n, "us_per_launch": ms / n * 1e3,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
             "note": note_}

@@ -188,6 +188,7 @@ struct ss_engine {
   int persistent_time = 0;           // record CUDA events around the persistent encoder kernel (bench roofline)
   struct TimedLaunch { cudaEvent_t e0, e1; double bytes; };
   std::vector<TimedLaunch> time_events;
+  std::vector<TimedLaunch> mt_time_events;  // the single-token MT kernel's launches (bytes field = steps executed)
   ss::PersistLayer* persist_alias = nullptr;   // debug: every layer entry = layer 0 (timing experiments only)
   int persistent_alias = 0;
   unsigned* persist_bar = nullptr;   // arrival counter of the kernel's own grid barrier (option persistent_barrier)

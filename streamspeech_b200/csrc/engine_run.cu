@@ -668,7 +668,17 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
         P.tok = h->mt_tok_dev; P.feats = feats_out_dev; P.x = x; P.q = s.q; P.attn = s.attn; P.hid = s.hid; P.logits = logits;
         if (h->persistent_mt_v2 && h->mt_part) { P.part = h->mt_part; P.delta = h->mt_part + (size_t)8 * c.mt_dim; }
         if (h->persistent_profile) P.ts = h->persist_ts;
-        if (mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, T, h->persist_bar, &h->persist_bar_target, st) == 0) {
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (h->persistent_time && h->mt_time_events.size() < 4096 && cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess)
+          cudaEventRecord(ev0, st);
+        else
+          ev0 = ev1 = nullptr;
+        const int rc_launch = mt_decode_persistent(P, h->mt_persist_layers, step, cnt, max_len, T, h->persist_bar, &h->persist_bar_target, st);
+        if (ev0 && ev1) {
+          cudaEventRecord(ev1, st);
+          h->mt_time_events.push_back({ev0, ev1, -1.0});  // steps executed: filled in below once the tokens are read
+        }
+        if (rc_launch == 0) {
           fed = step + cnt;
           if (step + cnt - 1 >= max_len) done = true;
           step += cnt;
@@ -704,14 +714,17 @@ int ss_mt_greedy(ss_engine* h, void* stream, const float* enc_dev, int T, const 
         *h->async_err_pinned = 0;
         return report_async_error(h, f, "ss_mt_greedy");
       }
+      int steps_run = produced;
       for (int i = 0; i < produced; ++i) {
         int64_t next = h->mt_next_pinned[i];
         if (next == c.eos) {
           done = true;
+          steps_run = i + 1;  // (the kernel stops after the step that produced eos)
           break;
         }
         tokens_out_host[n_tok++] = next;
       }
+      if (!h->mt_time_events.empty() && h->mt_time_events.back().bytes < 0.0) h->mt_time_events.back().bytes = (double)steps_run;
     }
     if (step > max_len) done = true;
   }
@@ -1218,6 +1231,25 @@ int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes) 
   if (n == "cluster_steps") {  // long long: encoder steps taken by the cluster kernel so far
     if (bytes < sizeof(long long)) return h->fail(SS_ERR_INVALID, "cluster_steps needs a long long");
     *(long long*)host_dst = h->cl_steps;
+    return SS_OK;
+  }
+  if (n == "mt_time") {  // double[3] = {summed ms, launches, summed steps} of the single-token MT kernel since the last query
+    if (bytes < 3 * sizeof(double)) return h->fail(SS_ERR_INVALID, "mt_time needs 3 doubles");
+    cudaDeviceSynchronize();
+    double* out = (double*)host_dst;
+    out[0] = out[1] = out[2] = 0.0;
+    for (auto& e : h->mt_time_events) {
+      float ms = 0.f;
+      if (e.bytes >= 0.0 && cudaEventElapsedTime(&ms, e.e0, e.e1) == cudaSuccess) {
+        out[0] += ms;
+        out[1] += 1.0;
+        out[2] += e.bytes;
+      }
+      cudaEventDestroy(e.e0);
+      cudaEventDestroy(e.e1);
+    }
+    cudaGetLastError();
+    h->mt_time_events.clear();
     return SS_OK;
   }
   if (n == "persist_time") {  // double[3] = {summed ms, launches, summed algorithmic bytes} since the last query

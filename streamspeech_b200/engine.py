@@ -482,6 +482,13 @@ class Engine:
         self._check(self.lib.ss_debug_copy(self._h, b"persist_time", buf, ctypes.sizeof(buf)))
         return float(buf[0]), int(buf[1]), float(buf[2])
 
+    def mt_time(self):
+        """(summed ms, launches, summed greedy steps) of the single-token MT kernel since the last query (CUDA events on the launching
+        stream; enable with set_option('persistent_time', 1))"""
+        buf = (ctypes.c_double * 3)()
+        self._check(self.lib.ss_debug_copy(self._h, b"mt_time", buf, ctypes.sizeof(buf)))
+        return float(buf[0]), int(buf[1]), float(buf[2])
+
     def cluster_steps(self) -> int:
         """encoder steps taken by the cluster kernel (option persistent_encoder_cluster) since the engine was created"""
         buf = ctypes.c_longlong(0)
