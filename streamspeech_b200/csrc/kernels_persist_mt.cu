@@ -543,6 +543,58 @@ __device__ __forceinline__ void add_head_partials(MtSmem& sm, const float* part,
   __syncthreads();
 }
 
+// L2 prefetch of the weight rows this warp's gemv phase will read (same column assignment as gemv_issue): one layer ahead, so that the
+// register loads of the phase hit L2 instead of HBM (the first pass over a layer's 14.7 MB otherwise costs a DRAM latency per phase)
+template <int K, int MAXC>
+__device__ __forceinline__ void gemv_prefetch(const float* __restrict__ W, int N) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * MW + (threadIdx.x >> 5), nw = gridDim.x * MW;
+  constexpr int LINES = K * 4 / 128;  // 128-byte lines per weight row
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = gw + c * nw;
+    if (col < N) {
+#pragma unroll
+      for (int l0 = 0; l0 < LINES; l0 += 32)
+        if (l0 + lane < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(W + (int64_t)col * K + (l0 + lane) * 32));
+    }
+  }
+}
+// ... and of the 32 x 64 out-projection block of (head h, column group j): 2 lines per column
+__device__ __forceinline__ void hp_prefetch(const float* __restrict__ W, int h, int j) {
+  const int t = threadIdx.x;
+  if (t < PCOLS * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(W + (int64_t)(j * PCOLS + (t >> 1)) * 512 + h * MHD + (t & 1) * 32));
+}
+__device__ __forceinline__ void layer_prefetch(const MtLayerP& L, bool in_group, int grp_h, int grp_j) {
+  gemv_prefetch<512, 2>(L.wqkv, 3 * 512);
+  gemv_prefetch<512, 1>(L.wcq, 512);
+  gemv_prefetch<512, 2>(L.w1, 2048);
+  gemv_prefetch<2048, 1>(L.w2, 512);
+  if (in_group) {
+    hp_prefetch(L.wo, grp_h, grp_j);
+    hp_prefetch(L.wco, grp_h, grp_j);
+  }
+}
+
+// split form of the grid barrier: arrive publishes this CTA's writes; everything issued between arrive and wait (the next phase's
+// weight, bias and LayerNorm-parameter loads: they do not depend on the phase that just ended) flies while the other CTAs arrive
+__device__ __forceinline__ void grid_arrive(unsigned* ctr, unsigned& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned* ctr, unsigned target) {
+  if (threadIdx.x == 0) {
+    unsigned v, spins = 0;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0 && ++spins < (1u << 20));
+    if ((int)(v - target) < 0) atomicExch(ctr + SS_BAR_ERR_WORD, 1u);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecodeParams P, const MtLayerP* __restrict__ layers, int step0,
                                                                          int nsteps, int max_len, int T, unsigned* bar_ctr,
                                                                          unsigned bar_target) {
@@ -560,6 +612,10 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecod
 #define BAR()                          \
   grid_barrier(bar_ctr, bar_target);   \
   ++done_barriers;
+#define ARRIVE()                       \
+  grid_arrive(bar_ctr, bar_target);    \
+  ++done_barriers;
+#define WAIT() grid_wait(bar_ctr, bar_target)
   int nts = 0;
   bool stamping = false;
 #define STAMP(id)                                          \
@@ -579,16 +635,25 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecod
       for (int c = tid; c < DIM; c += MTT) sm.x[c] = emb_scale * P.emb[tok * DIM + c] + P.pos[(int64_t)p * DIM + c];
       __syncthreads();
     }
+    GemvW<DIM, 2> w_qkv;  // weights of phase (1): issued at the start of the step (layer 0) or before the previous layer's last wait
+    LnP ln_self;
+    {
+      const MtLayerP L0 = layers[0];
+      gemv_issue_b(w_qkv, L0.wqkv, 3 * DIM, L0.bqkv);
+      ln_self = ln_load(L0.self_g, L0.self_b);
+    }
     for (int l = 0; l < P.n_layers; ++l) {
       const MtLayerP L = layers[l];
       stamping = P.ts != nullptr && blockIdx.x == 0 && si == 1 && l == 1;
       STAMP(0);
+      if (l + 1 < P.n_layers) layer_prefetch(layers[l + 1], in_group, grp_h, grp_j);
+      else {
+        gemv_prefetch<DIM, 6>(P.emb, P.vocab);                           // the tied output projection of this step
+        if (si + 1 < nsteps) layer_prefetch(layers[0], in_group, grp_h, grp_j);  // and layer 0 of the next one
+      }
       float* kc = P.self_k + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
       float* vc = P.self_v + ((size_t)l * P.max_pos + s + P.kv_off) * DIM;
       // (1) x += FFN delta of the previous layer; q | k | v = LN(x) Wqkv^T
-      GemvW<DIM, 2> w_qkv;
-      gemv_issue_b(w_qkv, L.wqkv, 3 * DIM, L.bqkv);
-      const LnP ln_self = ln_load(L.self_g, L.self_b);
       if (l > 0) {
         for (int c = tid; c < DIM; c += MTT) sm.x[c] = sm.x[c] + delta[c];
         __syncthreads();
@@ -600,57 +665,69 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecod
         else vc[col - 2 * DIM] = y;
       });
       STAMP(1);
-      BAR();
+      ARRIVE();
+      HpW hw;
+      if (in_group) hw = hp_load(L.wo, grp_h, grp_j);
+      WAIT();
       STAMP(2);
       // (2) self-attention of head grp_h (every CTA of the group) + partial out-projection of this CTA's 32 columns
       if (in_group) {
-        const HpW hw = hp_load(L.wo, grp_h, grp_j);
         attend_head_early(sm, P.q + grp_h * MHD, P.self_k + (size_t)l * P.max_pos * DIM + grp_h * MHD, P.self_v + (size_t)l * P.max_pos * DIM + grp_h * MHD,
                           DIM, s + P.kv_off + 1, att_h);
         __syncthreads();
         head_partial_proj_w(att_h, hw, grp_j, part + grp_h * DIM);
       }
       STAMP(3);
-      BAR();
-      STAMP(4);
-      // (3) x += sum_h partials + bo; q = LN(x) Wcq^T
+      ARRIVE();
       GemvW<DIM, 1> w_cq;
       gemv_issue_b(w_cq, L.wcq, DIM, L.bcq);
       const LnP ln_cross = ln_load(L.cross_g, L.cross_b);
+      WAIT();
+      STAMP(4);
+      // (3) x += sum_h partials + bo; q = LN(x) Wcq^T
       add_head_partials(sm, part, L.bo);
       ln_to_v(sm, ln_cross, DIM);
       gemv_finish_b(w_cq, sm.v, DIM, [&](int col, float y) { P.q[col] = y; });
       STAMP(5);
-      BAR();
+      ARRIVE();
+      if (in_group) hw = hp_load(L.wco, grp_h, grp_j);
+      WAIT();
       STAMP(6);
       // (4) cross-attention of head grp_h + partial out-projection
       if (in_group) {
         const float* cross = P.cross_kv + (size_t)l * P.cross_cap * 2 * DIM;
-        const HpW hw = hp_load(L.wco, grp_h, grp_j);
         attend_head_early(sm, P.q + grp_h * MHD, cross + grp_h * MHD, cross + DIM + grp_h * MHD, 2 * DIM, T, att_h);
         __syncthreads();
         head_partial_proj_w(att_h, hw, grp_j, part + grp_h * DIM);
       }
       STAMP(7);
-      BAR();
-      STAMP(8);
-      // (5) x += sum_h partials + bco; hid = relu(LN(x) W1^T)
+      ARRIVE();
       GemvW<DIM, 2> w_1;
       gemv_issue_b(w_1, L.w1, FFN, L.b1);
       const LnP ln_fin = ln_load(L.fin_g, L.fin_b);
+      WAIT();
+      STAMP(8);
+      // (5) x += sum_h partials + bco; hid = relu(LN(x) W1^T)
       add_head_partials(sm, part, L.bco);
       ln_to_v(sm, ln_fin, DIM);
       gemv_finish_b(w_1, sm.v, FFN, [&](int col, float y) { P.hid[col] = y > 0.f ? y : 0.f; });
       STAMP(9);
-      BAR();
-      STAMP(10);
-      // (6) delta = hid W2^T + b2
+      ARRIVE();
       GemvW<FFN, 1> w_2;
       gemv_issue_b(w_2, L.w2, DIM, L.b2);
+      WAIT();
+      STAMP(10);
+      // (6) delta = hid W2^T + b2
       load_vec(sm.v, P.hid, FFN);
       gemv_finish_b(w_2, sm.v, DIM, [&](int col, float y) { delta[col] = y; });
       STAMP(11);
-      BAR();
+      ARRIVE();
+      if (l + 1 < P.n_layers) {
+        const MtLayerP Ln = layers[l + 1];
+        gemv_issue_b(w_qkv, Ln.wqkv, 3 * DIM, Ln.bqkv);
+        ln_self = ln_load(Ln.self_g, Ln.self_b);
+      }
+      WAIT();
       STAMP(12);
     }
     const bool forced_eos = s >= max_len;
@@ -713,6 +790,8 @@ __global__ void __launch_bounds__(MTT, 1) mt_decode_persistent_kernel_v2(MtDecod
     }
   }
 #undef BAR
+#undef ARRIVE
+#undef WAIT
 #undef STAMP
   const int planned = nsteps * barriers_per_step;
   if (threadIdx.x == 0 && done_barriers < planned) atomicAdd(bar_ctr, (unsigned)(planned - done_barriers));
