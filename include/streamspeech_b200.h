@@ -228,9 +228,18 @@ int ss_op_conv1d(ss_engine* h, void* stream, const float* x_dev, int L, int C_in
  * shape fits, 0: one kernel per op; "persistent_barrier" = 1 (default): that kernel's own counter barrier instead of
  * cooperative-groups grid.sync(); "vocoder_streams" = 1 (default): the three parallel resblocks of a vocoder stage run
  * on the caller's stream plus two engine-owned streams (joined before the call returns control of the stream);
- * "persistent_profile" = 1: that kernel records a %globaltimer stamp per phase */
+ * "persistent_encoder_cluster" = 1 (0 on a fresh handle; the Python engine switches it on): steps with <= 16 active rows run on
+ * the cluster kernel (4 thread-block clusters x 16 CTAs, activations in distributed shared memory; allocates 123 MB of repacked
+ * weights the first time); larger steps and refused launches take the 148-CTA kernel; "cluster_cooperative" = 1 (default; 0 only
+ * under a profiler that serialises kernels and cannot replay cooperative cluster launches);
+ * "persistent_ffn_fused", "persistent_mt", "persistent_mt_v2", "persistent_mt_prefix", "fbank_tma" = 1 (default): kernel variants of
+ * round 2, each tested against the path it replaces; "umma2_fused_reduce" = 0 (default: measured slower);
+ * "persistent_profile" = 1: the persistent kernels record %globaltimer stamps per phase; "persistent_time" = 1: CUDA events around
+ * the encoder-stack kernel and the single-token MT kernel (read with ss_debug_copy "persist_time" / "mt_time") */
 int ss_set_option(ss_engine* h, const char* name, int value);
-/* synchronous copy of a diagnostic buffer to the host: "persist_ts" = uint64 ns stamps of the last persistent step */
+/* synchronous copy of a diagnostic buffer to the host: "persist_ts" = uint64 ns stamps of the last persistent step;
+ * "persist_time" / "mt_time" = double[3] {summed ms, launches, summed algorithmic bytes / executed steps} since the last query;
+ * "cluster_steps" = long long, encoder steps taken by the cluster kernel */
 int ss_debug_copy(ss_engine* h, const char* what, void* host_dst, size_t bytes);
 int ss_op_layer_norm(ss_engine* h, void* stream, const float* x_dev, int rows, int C, const float* g_dev, const float* b_dev,
                      float* out_dev);
