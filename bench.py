@@ -153,7 +153,8 @@ def run_reference(args):
 def encoder_roofline(engine, peaks, run_utterance):
     """Dominant kernel of the step = the encoder-stack kernel (one launch per 320 ms chunk runs all 12 Conformer layers over the
     <= 16 not-yet-final rows): encoder_layers_cluster_kernel (4 clusters x 16 CTAs, activations in distributed shared memory,
-    weights streamed by TMA from repacked blobs) when the step has <= 16 rows, else encoder_layers_persistent_kernel (148 CTAs).
+    weights streamed by TMA from repacked blobs) when the step has <= 16 rows, else encoder_layers_persistent_kernel (148 CTAs);
+    16.4 % of the summed kernel time in profiles/r2_launches_bench_window_cluster.md, 17.7 % of the utterance's device time measured here.
     It streams every GEMM weight of the stack once per launch -> HBM roofline.  Measured live: the engine brackets each
     launch with CUDA events on the launching stream while one more resident utterance is streamed (32 launches).
     algorithmic bytes per launch = 12 x (4*D*FFN + 7*D*D) x 4 B of weights (122.7 MB) + the K / V cache and
