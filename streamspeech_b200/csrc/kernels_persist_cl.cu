@@ -287,8 +287,8 @@ __device__ __forceinline__ float pair_tree(const float (&a0)[16], const float (&
 }
 
 struct ClParams {
-  const PersistLayer* layers;  // LayerNorm parameters, biases, pos tables, depthwise weights (device pointers as in kernels_persist.cu)
-  const float* blobs;          // [n_layers][CS][BLOB_ROWS][256]
+  const PersistLayer* layers;  // (not read by the kernel: every weight and parameter comes from the blobs; the pack kernels read it)
+  const float* blobs;          // [n_layers][CS][BLOB_STRIDE]: per (layer, rank) the parameter block, then 624 weight rows of 256 floats
   int n_layers;
   float* x;                    // [nA][256] active rows (in: encoder.linear output, out: layer-stack output)
   float *kc, *vc, *gc;         // per-layer caches [n_layers][Tpos][256]
