@@ -189,8 +189,8 @@ def encoder_roofline(engine, peaks, run_utterance):
     if cluster:
         kernel = ("encoder_layers_cluster_kernel (fp32, all 12 Conformer layers of one streaming step; 4 clusters x 16 CTAs, DSMEM "
                   "activation exchange, TMA weight ring)")
-        note_ = ("batch-1 streaming: 16 rows per launch; 9 cluster barriers + 2 grid barriers per layer; bound by dependent-phase "
-                 "latency (barriers, instruction fetch, one L2 round trip per phase), not by bandwidth")
+        note_ = ("batch-1 streaming: 16 rows per launch; per layer 9 distributed-shared-memory exchanges (st.async + mbarrier) and 2 split "
+                 "grid barriers; bound by ~25 dependent latencies per layer (mbarrier waits, shuffle trees, L2 round trips), not by bandwidth")
     else:
         kernel = "encoder_layers_persistent_kernel<2048> (fp32, all 12 Conformer layers of one streaming step, 148 CTAs cooperative)"
         note_ = ("batch-1 streaming: 16 rows per launch, 108 grid barriers; the kernel is bound by dependent-phase latency "
